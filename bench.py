@@ -1,0 +1,448 @@
+#!/usr/bin/env python
+"""Benchmark of the triplane hot path (BASELINE.json metric: triplane encode points/s + query-sample
+queries/s on B200, % of HBM peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--queries ...]
+
+Headline (`value`): occupancy decode of configs/triplane_occ.py at BASELINE.json's size — 640 000
+voxel queries sampled from three fp32 128x128 triplanes with C=32 (`configs[1]`) — in queries/s,
+inputs resident in HBM. A step = one pass of the decode path over one batch: 3 x NCHW->NHWC plane
+conversion + the fused 3-plane gather kernel (4 launches). Steps rotate over `nsets` disjoint
+buffer sets whose total footprint exceeds 3x the 126 MB L2, and are replayed from CUDA graphs so the
+Python launch cost is not what is measured. The same JSON line also carries the encode leg
+(`encode`: points/s for one synthetic nuScenes sweep at the config-exact geometry), `roofline`
+(dominant kernel, algorithmic bytes / CUDA-event time, vs MEASURED_PEAKS.json), `cpu_baseline`
+(the oracle on the box's host cores), `e2e` (host buffers through the C ABI) and `clocks`.
+
+Under torchrun (N > 1) every rank runs the same per-GPU workload on its own shard of queries /
+samples (weak scaling, no data-path collective: decode queries and encode samples are independent);
+time is the max over ranks, value the sum of work over ranks / that time.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+L2_BYTES = 126 * 1024 * 1024
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
+
+OCC_LO, OCC_VS, OCC_HALF = [-25.0, -25.0, -5.0], (0.4, 0.4, 0.1), [64.0] * 3
+C_DEC, PLANE = 32, 128
+
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback"
+
+
+def decode_queries(kind: str):
+    from efficient_multimodal_perception_b200 import synth
+    if kind == "lattice640k":
+        return synth.occ_gt_lattice().reshape(1, -1, 3).contiguous()
+    if kind == "uniform640k":
+        return synth.uniform_queries(640000, seed=1002).reshape(1, -1, 3).contiguous()
+    if kind == "roi":
+        return synth.roi_lattice().reshape(1, -1, 3).contiguous()
+    raise SystemExit(f"unknown --queries {kind}")
+
+
+def decode_bytes(Q: int, C_: int = C_DEC) -> int:
+    """Q*(12 + 4C) + 4C*sum(HW) per sample."""
+    return Q * (12 + 4 * C_) + 4 * C_ * 3 * PLANE * PLANE
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons with NVML while the timed regions run."""
+
+    def __init__(self, index: int, uuid=None):
+        super().__init__(daemon=True)
+        self.index, self.uuid, self.samples, self.reasons, self.max_mhz = index, uuid, [], set(), None
+        self._stop_evt = threading.Event()
+        self.active = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            try:  # CUDA_VISIBLE_DEVICES may renumber devices: prefer the UUID
+                h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + str(self.uuid)).encode())
+            except Exception:
+                h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            }
+            while not self._stop_evt.is_set():
+                if self.active.is_set():
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                time.sleep(0.004)
+        except Exception as e:  # NVML missing: report nulls rather than invent numbers
+            self.error = str(e)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------
+# b200 arm
+# --------------------------------------------------------------------------------------------------
+class DecodeSets:
+    """nsets disjoint (planes, queries, out) buffer sets + CUDA graphs of the 4-launch step."""
+
+    def __init__(self, q_host: torch.Tensor, nsets: int, dev):
+        from efficient_multimodal_perception_b200 import ops, synth
+        self.ops, self.dev, self.nsets = ops, dev, nsets
+        self.Q = q_host.shape[1]
+        self.sets = []
+        for s in range(nsets):
+            tri = synth.triplane_stacked(1, C_DEC, PLANE, seed=1002 + s).to(dev)
+            q = q_host.to(dev) if s == 0 else q_host.roll(s * 1013, 1).to(dev)
+            out = torch.empty(1, C_DEC, self.Q, device=dev)
+            self.sets.append((tri, q, out))
+        self.graph_all = self.graph_one = None
+
+    def step(self, s: int):
+        tri, q, out = self.sets[s % self.nsets]
+        self.ops.sample3(tri, q, OCC_LO, OCC_VS, OCC_HALF, out=out)
+
+    def capture(self):
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            for s in range(self.nsets):
+                self.step(s)
+        torch.cuda.synchronize()
+        self.graph_all = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_all):
+            for s in range(self.nsets):
+                self.step(s)
+        self.graph_one = []
+        for s in range(self.nsets):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.step(s)
+            self.graph_one.append(g)
+        torch.cuda.synchronize()
+
+    def run_steps(self, k: int):
+        full, rem = divmod(k, self.nsets)
+        for _ in range(full):
+            self.graph_all.replay()
+        for s in range(rem):
+            self.graph_one[s].replay()
+
+
+def time_region(fn, barrier):
+    """CUDA-event time (ms) of fn() on the current stream, barrier + synchronize on both sides."""
+    barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    fn()
+    b.record()
+    torch.cuda.synchronize()
+    barrier()
+    return a.elapsed_time(b)
+
+
+def kernel_time_ms(launch, reps: int, pre=None):
+    """Average CUDA-event duration of a single kernel launch (events around the launch only)."""
+    evs = []
+    for i in range(reps):
+        if pre:
+            pre(i)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        launch(i)
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    return sum(ts) / len(ts), ts[len(ts) // 2], ts[0]
+
+
+def bench_decode_device(args, dev, barrier, sampler):
+    q_host = decode_queries(args.queries)
+    Q = q_host.shape[1]
+    per_set = decode_bytes(Q) + 4 * C_DEC * 3 * PLANE * PLANE  # + the channels-last copy
+    nsets = max(4, -(-3 * L2_BYTES // per_set))
+    sets = DecodeSets(q_host, nsets, dev)
+    sets.capture()
+    sets.run_steps(args.warmup)
+    sampler.active.set()
+    ms = time_region(lambda: sets.run_steps(args.steps), barrier)
+    # per-kernel duration of the dominant kernel (the gather), channels-last copies prepared outside
+    ops = sets.ops
+    nhwc = [ops.planes_to_channels_last([t[:, 0], t[:, 1], t[:, 2]]) for t, _, _ in sets.sets]
+    reps = min(max(args.steps, 20), 400)
+
+    def launch(i):
+        _, q, out = sets.sets[i % nsets]
+        ops.sample3(nhwc[i % nsets], q, OCC_LO, OCC_VS, OCC_HALF, channels_last=True, out=out)
+
+    for i in range(8):
+        launch(i)
+    torch.cuda.synchronize()
+    k_avg, k_med, k_min = kernel_time_ms(launch, reps)
+    sampler.active.clear()
+    return dict(Q=Q, nsets=nsets, ms_total=ms, kernel_ms_avg=k_avg, kernel_ms_med=k_med, kernel_ms_min=k_min,
+                launches=args.steps * 4, sets=sets)
+
+
+def bench_decode_e2e(args, Q_host, barrier):
+    """Host buffers through the C ABI (tp_sample3_host_f32): H2D of planes + queries, conversion,
+    gather, D2H of the full [C,Q] result, synchronised, every step."""
+    from efficient_multimodal_perception_b200 import _lib as L
+    from efficient_multimodal_perception_b200 import synth
+    lib = L.lib()
+    Q = Q_host.shape[1]
+    tri = synth.triplane_stacked(1, C_DEC, PLANE, seed=1002).pin_memory()
+    q = Q_host.clone().pin_memory()
+    out = torch.empty(1, C_DEC, Q).pin_memory()
+    ptrs = (C.c_void_p * 3)(*[tri[:, k].data_ptr() for k in range(3)])
+    hw = (C.c_int32 * 6)(*[PLANE] * 6)
+    bs = (C.c_int64 * 3)(*[tri.stride(0)] * 3)
+    sg = L.make_sample_geom(OCC_LO, OCC_VS, OCC_HALF)
+
+    def call():
+        L.check(lib.tp_sample3_host_f32(C.byref(ptrs), C.byref(hw), C.byref(bs), C_DEC, q.data_ptr(), Q, 1,
+                                        C.byref(sg), L.TP_ARITH_TORCH_CUDA, out.data_ptr()), "tp_sample3_host_f32")
+
+    steps = max(5, min(args.steps, 100))
+    for _ in range(3):
+        call()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        call()
+    dt = time.perf_counter() - t0
+    barrier()
+    h2d = tri.numel() * 4 + q.numel() * 4
+    d2h = out.numel() * 4
+    return dict(qps=Q * steps / dt, steps=steps, h2d=h2d, d2h=d2h, ms=dt / steps * 1e3, out=out)
+
+
+def bench_encode_device(args, dev, barrier, sampler):
+    """Encode leg: configs/point_triplane.py geometry (128x128x80, pool 5/5/4, C=128), one synthetic
+    sweep (34 720 raw points), crop + index fused into the encode (raw points in)."""
+    from efficient_multimodal_perception_b200 import ops, synth
+    G = synth.GEOM_A
+    n, Cc = 34720, G["channels"]
+    pts = synth.lidar_sweep(n, seed=1001)
+    xyz = pts[:, :3].contiguous().to(dev)
+    feats = synth.point_features(n, Cc, seed=1001).to(dev)
+    off = synth.batch_offsets([n]).to(dev)
+    inside = int(((pts[:, 0].abs() < 25) & (pts[:, 1].abs() < 25) & (pts[:, 2] > -5) & (pts[:, 2] < 3)).sum())
+    cells = 128 * 128 * 20 + 2 * 128 * 80 * 25
+
+    def step():
+        return ops.encode(feats, off, G["pc_range"], G["voxel_size"], G["grid_size"], G["split"], points=xyz)
+
+    for _ in range(max(3, min(args.warmup, 10))):
+        outs = step()
+    steps = max(10, min(args.steps, 200))
+    sampler.active.set()
+    ms = time_region(lambda: [step() for _ in range(steps)], barrier)
+    sampler.active.clear()
+    bytes_alg = n * 12 + inside * 4 * Cc + 4 * Cc * cells
+    return dict(n=n, inside=inside, cells=cells, steps=steps, ms_per_step=ms / steps, bytes=bytes_alg,
+                launches=2 * steps)
+
+
+def cpu_baseline_decode(q_host, budget_s=15.0):
+    """The oracle (torch-CPU restatement of the reference, kind='port') on all host cores."""
+    from efficient_multimodal_perception_b200 import synth
+    from oracle import triplane_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    tri = synth.triplane_stacked(1, C_DEC, PLANE, seed=1002)
+    pts = q_host.view(1, 1, -1, 3)
+    O.sample_points_triplane_stacked(tri, pts, OCC_LO, OCC_VS)  # warm-up
+    ts, t_start = [], time.perf_counter()
+    while len(ts) < 10 and (time.perf_counter() - t_start < budget_s or len(ts) < 2):
+        t0 = time.perf_counter()
+        ref = O.sample_points_triplane_stacked(tri, pts, OCC_LO, OCC_VS)
+        ts.append(time.perf_counter() - t0)
+    med = statistics.median(ts)
+    return dict(value=q_host.shape[1] / med, unit="queries/s", cores=torch.get_num_threads(), kind="port",
+                sample=f"{len(ts)} full passes of the {q_host.shape[1]}-query workload, median "
+                       f"(oracle.sample_points_triplane_stacked = the reference's 3 x F.grid_sample path on torch-CPU)"), ref
+
+
+def run_b200(args):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU path (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        barrier = lambda: dist.barrier()  # noqa: E731
+    else:
+        barrier = lambda: None  # noqa: E731
+    import efficient_multimodal_perception_b200 as emp
+    emp.lib()
+    peak, peak_src = measured_hbm_peak()
+    sampler = ClockSampler(local, getattr(torch.cuda.get_device_properties(dev), "uuid", None))
+    sampler.start()
+
+    dec = bench_decode_device(args, dev, barrier, sampler)
+    enc = bench_encode_device(args, dev, barrier, sampler)
+    # max over ranks (device time)
+    t = torch.tensor([dec["ms_total"], enc["ms_per_step"], dec["kernel_ms_avg"]], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, enc_ms, k_avg = (float(x) for x in t.tolist())
+    clocks = sampler.stop()
+
+    q_host = decode_queries(args.queries)
+    e2e = bench_decode_e2e(args, q_host, barrier)
+    te = torch.tensor([e2e["ms"]], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te.item())
+
+    if rank == 0:
+        Q = dec["Q"]
+        ms_per_step = ms_total / args.steps
+        qps = world * Q * args.steps / (ms_total * 1e-3)
+        kbytes = decode_bytes(Q)
+        achieved = kbytes / (k_avg * 1e-3) / 1e9
+        cpu, parity = None, None
+        if world == 1:
+            cpu, ref = cpu_baseline_decode(q_host)
+            # live parity check of what was just timed (device result of set 0 and the e2e result)
+            tri0, q0, out0 = dec["sets"].sets[0]
+            dec["sets"].step(0)
+            torch.cuda.synchronize()
+            scale = float(ref.abs().max())
+            parity = {"device_vs_oracle_normwise": float((out0.cpu() - ref[:, :, 0]).abs().max()) / scale,
+                      "e2e_vs_oracle_normwise": float((e2e["out"] - ref[:, :, 0]).abs().max()) / scale, "bar": 1e-5}
+        line = {
+            "metric": "triplane decode queries/s (3-plane bilinear sample + sum, triplane_occ occupancy decode)",
+            "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"configs/triplane_occ.py occupancy decode: {Q} voxel queries ({args.queries}) "
+                                   f"x C={C_DEC} from 3 fp32 {PLANE}x{PLANE} triplanes, bs=1 per GPU",
+                       "queries": args.queries, "Q": Q, "C": C_DEC, "planes": [PLANE, PLANE],
+                       "step": "3x NCHW->NHWC plane conversion + fused gather kernel (4 launches, CUDA-graph replay)",
+                       "l2": f"{dec['nsets']} rotating buffer sets, total footprint "
+                             f"{dec['nsets'] * (kbytes + 4 * C_DEC * 3 * PLANE * PLANE) / 1e6:.0f} MB > 3x L2 (no flush kernel)",
+                       "parallelism": f"queries sharded over {world} GPU(s), no collective"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "tp::sample3_kernel<0>", "algorithmic_bytes": kbytes,
+                         "kernel_ms_avg": k_avg, "kernel_ms_median": dec["kernel_ms_med"],
+                         "kernel_ms_min": dec["kernel_ms_min"], "peak_source": peak_src,
+                         "step_frac": kbytes / (ms_per_step * 1e-3) / 1e9 / peak},
+            "cpu_baseline": cpu,
+            "e2e": {"value": world * Q / (e2e_ms * 1e-3), "unit": "queries/s",
+                    "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e_ms,
+                    "steps": e2e["steps"], "api": "tp_sample3_host_f32 (C ABI, pinned host buffers; H2D planes+queries, "
+                                                  "D2H full result, synchronised every step)"},
+            "gpu_launches": dec["launches"],
+            "clocks": clocks,
+            "parity": parity,
+            "encode": {"metric": "triplane encode points/s (fused crop+index+scatter-max into dense pooled planes)",
+                       "value": world * enc["n"] / (enc_ms * 1e-3), "unit": "points/s", "ms_per_step": enc_ms,
+                       "workload": f"configs/point_triplane.py geometry 128x128x80 pool 5/5/4 C=128, 1 sweep "
+                                   f"{enc['n']} raw pts ({enc['inside']} in range), bs=1 per GPU, "
+                                   f"{enc['cells']} pooled cells dense out",
+                       "roofline": {"bound": "hbm", "achieved": enc["bytes"] / (enc_ms * 1e-3) / 1e9, "peak": peak,
+                                    "unit": "GB/s", "frac": enc["bytes"] / (enc_ms * 1e-3) / 1e9 / peak,
+                                    "algorithmic_bytes": enc["bytes"], "note": "whole step (link + materialise)"},
+                       "steps": enc["steps"], "gpu_launches": enc["launches"]},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU implementation of the path (oracle port) on the host cores
+# --------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from efficient_multimodal_perception_b200 import synth
+    from oracle import triplane_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    q_host = decode_queries(args.queries)
+    Q = q_host.shape[1]
+    tri = synth.triplane_stacked(1, C_DEC, PLANE, seed=1002)
+    t0 = time.perf_counter()
+    O.sample_points_triplane_stacked(tri, q_host.view(1, 1, -1, 3), OCC_LO, OCC_VS)
+    t_full = time.perf_counter() - t0
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    Qs = int(max(4096, min(Q, Q * budget / max(t_full, 1e-6))))
+    sample = q_host[:, torch.randperm(Q, generator=torch.Generator().manual_seed(0))[:Qs]].contiguous().view(1, 1, -1, 3)
+    for _ in range(args.warmup):
+        O.sample_points_triplane_stacked(tri, sample, OCC_LO, OCC_VS)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.sample_points_triplane_stacked(tri, sample, OCC_LO, OCC_VS)
+    dt = time.perf_counter() - t0
+    qps = Qs * args.steps / dt
+    desc = (f"each step = {Qs} of the {Q} queries (random subset, seed 0) through "
+            f"oracle.sample_points_triplane_stacked (the reference's normalise + 3 x F.grid_sample + sum on torch-CPU)")
+    print(json.dumps({
+        "impl": "reference",
+        "metric": "triplane decode queries/s (3-plane bilinear sample + sum, triplane_occ occupancy decode)",
+        "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"configs/triplane_occ.py occupancy decode: {Q} voxel queries ({args.queries}) "
+                               f"x C={C_DEC} from 3 fp32 {PLANE}x{PLANE} triplanes, bs=1", "queries": args.queries,
+                   "Q": Q, "C": C_DEC, "sample_per_step": Qs},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": desc},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--queries", default="uniform640k", choices=["lattice640k", "uniform640k", "roi"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,16 @@
+"""B200-native triplane hot path of charyyev/efficient_multimodal_perception.
+
+Encode (points + camera-lifted features -> xy/yz/xz planes by fused voxel-index + scatter-max/mean)
+and decode (per-query bilinear sample of the three planes + sum) as hand-written sm_100a CUDA
+kernels in ``libtriplane.so`` (C ABI: include/triplane.h), behind the reference's module and
+method names. There is no CPU or PyTorch fallback: a missing library raises TriplaneError.
+"""
+from ._lib import LIB_PATH, TriplaneError, lib
+from . import ops, synth
+from .modules import (PointTriplaneProjector, TriplaneHotPathMixin, register_with_mmdet, roi,
+                      sample_points_triplane, voxelize_points)
+
+__all__ = ["LIB_PATH", "TriplaneError", "lib", "ops", "synth", "PointTriplaneProjector",
+           "TriplaneHotPathMixin", "register_with_mmdet", "roi", "sample_points_triplane", "voxelize_points"]
+
+register_with_mmdet()

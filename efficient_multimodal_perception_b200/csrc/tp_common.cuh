@@ -1,0 +1,107 @@
+// Shared device/host helpers for libtriplane (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "triplane.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libtriplane is written for sm_100a (B200) only"
+#endif
+
+namespace tp {
+
+constexpr int kSMs = 148;  // B200; grids are sized in multiples of this
+
+// ---- error plumbing (tp_api.cu owns the storage) -------------------------------------------
+int fail(int code, const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+#define TP_CUDA(expr)                                  \
+  do {                                                 \
+    cudaError_t _e = (expr);                           \
+    if (_e != cudaSuccess) return ::tp::check_cuda(_e, #expr); \
+  } while (0)
+#define TP_LAUNCH_CHECK(name)                          \
+  do {                                                 \
+    cudaError_t _e = cudaGetLastError();               \
+    if (_e != cudaSuccess) return ::tp::check_cuda(_e, name); \
+  } while (0)
+
+// ---- the reference's coordinate chain, op by op, never contracted -----------------------------
+// (p - lo) (/) vs : torch-CUDA multiplies by the fp32 reciprocal of the Python-float divisor,
+// torch-CPU divides (SURVEY §7 "bit-exact voxel indices").
+struct AxisMap {
+  float lo, d, rcp;  // d = divisor, rcp = 1.0f / d computed in fp32 on the host
+};
+
+template <int ARITH>
+__device__ __forceinline__ float tp_div(float a, float d, float rcp) {
+  if (ARITH == TP_ARITH_TORCH_CUDA) return __fmul_rn(a, rcp);
+  return __fdiv_rn(a, d);
+}
+
+// voxel coordinate v = (p - lo) / vs  (point_triplane.py:153-156)
+template <int ARITH>
+__device__ __forceinline__ float tp_voxel_coord(float p, float lo, float vs, float rcp_vs) {
+  return tp_div<ARITH>(__fsub_rn(p, lo), vs, rcp_vs);
+}
+
+struct GeomDev {
+  float lo[3], hi[3], vs[3], rcp_vs[3];
+  int grid[3], pool[3], pooled[3];  // pooled = (grid - pool) / pool + 1
+};
+
+inline GeomDev make_geom_dev(const tp_geom& g) {
+  GeomDev d;
+  for (int a = 0; a < 3; ++a) {
+    d.lo[a] = g.lo[a];
+    d.hi[a] = g.hi[a];
+    d.vs[a] = g.vs[a];
+    d.rcp_vs[a] = 1.0f / g.vs[a];
+    d.grid[a] = g.grid[a];
+    d.pool[a] = g.pool[a];
+    d.pooled[a] = (g.grid[a] - g.pool[a]) / g.pool[a] + 1;
+  }
+  return d;
+}
+
+// strict crop of point_triplane.py:148-150 + int32 truncation of :159
+template <int ARITH>
+__device__ __forceinline__ bool tp_crop_index(const GeomDev& g, float x, float y, float z, int& ix,
+                                              int& iy, int& iz) {
+  bool keep = (x > g.lo[0]) & (x < g.hi[0]) & (y > g.lo[1]) & (y < g.hi[1]) & (z > g.lo[2]) &
+              (z < g.hi[2]);
+  ix = __float2int_rz(tp_voxel_coord<ARITH>(x, g.lo[0], g.vs[0], g.rcp_vs[0]));
+  iy = __float2int_rz(tp_voxel_coord<ARITH>(y, g.lo[1], g.vs[1], g.rcp_vs[1]));
+  iz = __float2int_rz(tp_voxel_coord<ARITH>(z, g.lo[2], g.vs[2], g.rcp_vs[2]));
+  return keep;
+}
+
+// sample index of a concatenated row: largest b with offsets[b] <= i  (B is small)
+__device__ __forceinline__ int tp_find_batch(const int64_t* __restrict__ offsets, int batch,
+                                             int64_t i) {
+  int lo = 0, hi = batch;  // offsets[lo] <= i < offsets[hi]
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(offsets + mid) <= i) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ float4 ld_nc_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+// streaming store: written once, never re-read by this kernel
+__device__ __forceinline__ void st_cs_f4(float4* p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void st_cs_f1(float* p, float v) {
+  asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+}  // namespace tp

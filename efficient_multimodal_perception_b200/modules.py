@@ -1,0 +1,197 @@
+"""Drop-in host side of the triplane hot path: the reference's registered module and detector
+methods, same names / signatures / parameter names, arithmetic in libtriplane.so.
+
+Reference interface mirrored here (paths under /root/reference):
+* ``PointTriplaneProjector``            mmdet3d/models/backbones/point_triplane_projector.py:11-117
+* ``voxelize_points(self, points)``     mmdet3d/models/detectors/point_triplane.py:133-161
+* ``sample_points_triplane(self, triplane, points)``
+                                        triplane.py:490-514, triplane_occ.py:321-348, triplane_elev.py:286-313,
+                                        point_triplane.py:439-466, point_triplane_occ.py:407-440
+* ``roi(self)``                         triplane_occ.py:291-318
+
+The detectors themselves (backbones, necks, heads, losses) stay the reference's PyTorch code; a
+maintainer mixes ``TriplaneHotPathMixin`` into them.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Union
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import TriplaneError
+
+
+class PointTriplaneProjector(nn.Module):
+    """Projects point features to a triplane — same constructor, parameter names and forward()
+    contract as the reference class, so its checkpoints load by key+shape
+    (point_triplane_occ.py:118-129). ``pool_xy/yz/xz`` had no parameters; the fused CUDA encode
+    replaces torch.unique + scatter_max + 3 x SparseMaxPool3d + dense() + permute/flatten."""
+
+    def __init__(self, grid_size, in_channels=10, out_channels=256, base_channels=32, split=[4, 4, 4],
+                 track_running_stats=True, pc_range=None, voxel_size=None, clamp_zero=False):
+        super().__init__()
+        self.grid_size = grid_size
+        self.split = split
+        self.clamp_zero = clamp_zero
+        # only needed for forward_fused(): the reference passes grid_ind in, so geometry is optional
+        self.pc_range, self.voxel_size = pc_range, voxel_size
+        self.point_mlp = nn.Sequential(
+            nn.BatchNorm1d(in_channels, track_running_stats=track_running_stats),
+            nn.Linear(in_channels, 64),
+            nn.BatchNorm1d(64, track_running_stats=track_running_stats),
+            nn.ReLU(),
+            nn.Linear(64, 128),
+            nn.BatchNorm1d(128, track_running_stats=track_running_stats),
+            nn.ReLU(),
+            nn.Linear(128, 256),
+            nn.BatchNorm1d(256, track_running_stats=track_running_stats),
+            nn.ReLU(),
+            nn.Linear(256, out_channels),
+        )
+        self.reduce_cam_channels = nn.Linear(768, out_channels)
+        ins = [int(base_channels * s) for s in split]
+        outs = [int(base_channels) for _ in split]
+        self.mlp_xy = nn.Sequential(nn.Linear(ins[2], outs[2]), nn.ReLU(), nn.Linear(outs[2], outs[2]))
+        self.mlp_yz = nn.Sequential(nn.Linear(ins[0], outs[0]), nn.ReLU(), nn.Linear(outs[0], outs[0]))
+        self.mlp_xz = nn.Sequential(nn.Linear(ins[1], outs[1]), nn.ReLU(), nn.Linear(outs[1], outs[1]))
+
+    def point_features(self, points: Sequence[torch.Tensor], cam_point_features: Sequence[torch.Tensor]):
+        cat_pt_fea = torch.cat([p[:, 0:5] for p in points], dim=0)
+        cat_cam = self.reduce_cam_channels(torch.cat(list(cam_point_features), dim=0))
+        return self.point_mlp(cat_pt_fea) + cat_cam
+
+    def forward(self, points, grid_ind, cam_point_features):
+        """points: list of [N'_b, >=5]; grid_ind: list of int32 [N'_b, 3]; cam_point_features: list of
+        [N'_b, 768]. Returns [tpv_xy [B,C,X,Y], tpv_yz [B,C,Y,Z], tpv_xz [B,C,X,Z]]."""
+        feats = self.point_features(points, cam_point_features)
+        offsets = _offsets([g.shape[0] for g in grid_ind], feats.device)
+        cat_ind = torch.cat([g.to(torch.int32) for g in grid_ind], dim=0)
+        if torch.is_grad_enabled() and feats.requires_grad:
+            from .autograd import encode_max_autograd
+            xy, yz, xz = encode_max_autograd(feats, cat_ind, offsets, self.grid_size, self.split, self.clamp_zero)
+        else:
+            xy, yz, xz = ops.encode(feats, offsets, [0] * 6, (1, 1, 1), self.grid_size, self.split,
+                                    grid_ind=cat_ind, reduce="max", clamp_zero=self.clamp_zero)
+        tpv_xy = self.mlp_xy(xy).permute(0, 3, 1, 2)
+        tpv_yz = self.mlp_yz(yz).permute(0, 3, 1, 2)
+        tpv_xz = self.mlp_xz(xz).permute(0, 3, 1, 2)
+        return [tpv_xy, tpv_yz, tpv_xz]
+
+    @torch.no_grad()
+    def forward_fused(self, raw_points, cam_point_features, arith: str = "cuda"):
+        """Fused a1+a3 (inference): raw, uncropped points; crop + voxel index happen inside the encode
+        kernel, so no compaction and no host sync. cam_point_features are per RAW point here."""
+        if self.pc_range is None or self.voxel_size is None:
+            raise TriplaneError("forward_fused needs pc_range / voxel_size at construction")
+        feats = self.point_features(raw_points, cam_point_features)
+        offsets = _offsets([p.shape[0] for p in raw_points], feats.device)
+        pts = torch.cat([p[:, :3] for p in raw_points], dim=0)
+        xy, yz, xz = ops.encode(feats, offsets, self.pc_range, self.voxel_size, self.grid_size, self.split,
+                                points=pts, reduce="max", clamp_zero=self.clamp_zero, arith=arith)
+        return [self.mlp_xy(xy).permute(0, 3, 1, 2), self.mlp_yz(yz).permute(0, 3, 1, 2),
+                self.mlp_xz(xz).permute(0, 3, 1, 2)]
+
+
+def _offsets(sizes: Sequence[int], device) -> torch.Tensor:
+    off = [0]
+    for s in sizes:
+        off.append(off[-1] + int(s))
+    return torch.tensor(off, dtype=torch.int64).to(device, non_blocking=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# free functions behind the detector methods
+# ------------------------------------------------------------------------------------------------
+def voxelize_points(points: Sequence[torch.Tensor], pc_range, voxel_size, arith: str = "cuda"):
+    """point_triplane.py:133-161 for a list of per-sample point tensors -> (cropped list, grid_ind list)."""
+    dev = points[0].device
+    sizes = [p.shape[0] for p in points]
+    cat = torch.cat(list(points), dim=0) if len(points) > 1 else points[0]
+    offsets = _offsets(sizes, dev)
+    out_pts, out_idx, out_off = ops.voxelize(cat, offsets, pc_range, voxel_size, arith=arith)
+    bounds = out_off.tolist()
+    cropped = [out_pts[bounds[i]:bounds[i + 1]] for i in range(len(points))]
+    grid_ind = [out_idx[bounds[i]:bounds[i + 1]] for i in range(len(points))]
+    return cropped, grid_ind
+
+
+def sample_points_triplane(triplane: Union[torch.Tensor, Sequence[torch.Tensor]], points: torch.Tensor, lo, vs,
+                           grid_size=None, arith: str = "cuda") -> torch.Tensor:
+    """All five reference variants. Stacked [B,3,C,H,W]: every axis is normalised by
+    triplane.shape[-1] / 2; list of planes: by grid_size[a] / 2. points [B,h,w,3] -> [B,C,h,w];
+    [B,h,w,d,3] -> [B,C,h,w,d]."""
+    if isinstance(triplane, torch.Tensor):
+        half = [triplane.shape[-1] / 2] * 3
+    else:
+        if grid_size is None:
+            raise TriplaneError("list-of-planes triplane needs grid_size")
+        half = [grid_size[a] / 2 for a in range(3)]
+    if points.dim() not in (4, 5) or points.shape[-1] != 3:
+        raise TriplaneError(f"points must be [B,h,w,3] or [B,h,w,d,3], got {tuple(points.shape)}")
+    B = points.shape[0]
+    q = points.reshape(B, -1, 3)
+    if torch.is_grad_enabled() and (any(t.requires_grad for t in ([triplane] if isinstance(triplane, torch.Tensor)
+                                                                  else triplane)) or points.requires_grad):
+        from .autograd import sample3_autograd
+        out = sample3_autograd(triplane, q, lo, vs, half, arith)
+    else:
+        out = ops.sample3(triplane, q, lo, vs, half, arith=arith)
+    return out.view(B, -1, *points.shape[1:-1])
+
+
+def roi(occ_range, voxel_size):
+    """triplane_occ.py:291-318 — bounds into the 200x200x16 GT and the voxel-centre query lattice
+    (host-side constants; built once)."""
+    min_x = int((abs(-50 - occ_range[0]) + 0.5) / voxel_size[0])
+    min_y = int((abs(-50 - occ_range[1]) + 0.5) / voxel_size[1])
+    max_x = int((abs(50 - occ_range[0]) - 0.5) / voxel_size[0])
+    max_y = int((abs(50 - occ_range[1]) - 0.5) / voxel_size[1])
+    X, Y = max_x - min_x + 1, max_y - min_y + 1
+    Z = int((occ_range[5] - occ_range[2]) / voxel_size[2])
+    grid = torch.stack(torch.meshgrid(torch.arange(X, dtype=torch.float32), torch.arange(Y, dtype=torch.float32),
+                                      torch.arange(Z, dtype=torch.float32), indexing="ij"), -1)
+    for a in range(3):
+        grid[..., a] = (grid[..., a] + 0.5) * voxel_size[a] + occ_range[a]
+    return (min_x, min_y, max_x, max_y), grid
+
+
+class TriplaneHotPathMixin:
+    """Mix into the reference detectors (TriplaneMAE, TriplaneOcc, TriplaneElev, PointTriplane,
+    PointTriplaneOcc) ahead of nn.Module to replace their hot-path methods. Attribute names are the
+    reference's: ``triplane_range`` / ``triplane_voxel_size`` when present, else ``pc_range`` /
+    ``voxel_size`` (see _tp_geometry)."""
+
+    tp_arith = "cuda"
+
+    def _tp_geometry(self):
+        # TriplaneOcc / PointTriplaneOcc: triplane_range + triplane_voxel_size; TriplaneElev:
+        # triplane_range + voxel_size (triplane_elev.py:298); TriplaneMAE / PointTriplane: pc_range + voxel_size
+        lo = self.triplane_range if hasattr(self, "triplane_range") else self.pc_range
+        vs = self.triplane_voxel_size if hasattr(self, "triplane_voxel_size") else self.voxel_size
+        return lo, vs
+
+    def voxelize_points(self, points):
+        return voxelize_points(points, self.pc_range, self.voxel_size, self.tp_arith)
+
+    def sample_points_triplane(self, triplane, points):
+        lo, vs = self._tp_geometry()
+        grid_size = None
+        if not isinstance(triplane, torch.Tensor):
+            grid_size = self.point_triplane_projector.grid_size
+        return sample_points_triplane(triplane, points, lo, vs, grid_size, self.tp_arith)
+
+    def roi(self):
+        return roi(self.occ_range, self.voxel_size)
+
+
+def register_with_mmdet() -> bool:
+    """Register PointTriplaneProjector in mmdet's BACKBONES registry (the reference's plugin API,
+    mmdet3d/models/builder.py:5-6) when mmdet is importable. Returns whether it registered."""
+    try:
+        from mmdet.models.builder import BACKBONES  # type: ignore
+    except Exception:
+        return False
+    BACKBONES.register_module(name="PointTriplaneProjector", force=True)(PointTriplaneProjector)
+    return True

@@ -1,0 +1,273 @@
+"""Tensor-level wrappers over the C ABI (include/triplane.h). PyTorch is used for device memory and
+streams only; every arithmetic step runs in libtriplane.so. All functions require CUDA tensors and
+raise (never fall back) otherwise."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from . import _lib as L
+from ._lib import (TP_ARITH_TORCH_CPU, TP_ARITH_TORCH_CUDA, TP_REDUCE_MAX, TP_REDUCE_MEAN, TP_REDUCE_SUM,
+                   TriplaneError)
+
+_REDUCE = {"max": TP_REDUCE_MAX, "mean": TP_REDUCE_MEAN, "sum": TP_REDUCE_SUM}
+_ARITH = {"cuda": TP_ARITH_TORCH_CUDA, "cpu": TP_ARITH_TORCH_CPU, "cuda_nofma": L.TP_ARITH_TORCH_CUDA_NOFMA}
+
+#: count of libtriplane kernel launches issued through this module (bench.py's gpu_launches)
+launch_count = 0
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _need_cuda(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TriplaneError(f"{name}: expected a CUDA tensor (no CPU path exists), got "
+                            f"{type(t).__name__}{'' if not isinstance(t, torch.Tensor) else ' on ' + str(t.device)}")
+    if t.dtype != dtype:
+        raise TriplaneError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def pool_kernels(grid_size, split) -> Tuple[int, int, int]:
+    """int(grid/split), as point_triplane_projector.py:53-58 computes the pooling kernels."""
+    return tuple(int(grid_size[a] / split[a]) for a in range(3))
+
+
+def pooled_sizes(grid_size, pool) -> Tuple[int, int, int]:
+    return tuple((int(grid_size[a]) - int(pool[a])) // int(pool[a]) + 1 for a in range(3))
+
+
+# ------------------------------------------------------------------------------------------------
+# a1
+# ------------------------------------------------------------------------------------------------
+def voxelize(points: torch.Tensor, offsets: torch.Tensor, pc_range, voxel_size, grid_size=(1, 1, 1),
+             ncols: Optional[int] = None, arith: str = "cuda"):
+    """points [N, D] (samples concatenated), offsets [B+1] int64 ->
+    (cropped [N', ncols], grid_ind [N', 3] int32, out_offsets [B+1] int64 on device).
+    One host sync (reading N') — the reference syncs once per sample (point_triplane.py:152)."""
+    global launch_count
+    _need_cuda(points, "points")
+    _need_cuda(offsets, "offsets", torch.int64)
+    if points.dim() != 2 or points.shape[1] < 3:
+        raise TriplaneError(f"points must be [N, >=3], got {tuple(points.shape)}")
+    points = points.contiguous()
+    n, stride = points.shape
+    ncols = stride if ncols is None else ncols
+    batch = offsets.numel() - 1
+    geom = L.make_geom(pc_range, voxel_size, grid_size, (1, 1, 1))
+    lib = L.lib()
+    ws_bytes = lib.tp_voxelize_workspace_bytes(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=points.device)
+    out_pts = torch.empty((n, ncols), dtype=torch.float32, device=points.device)
+    out_idx = torch.empty((n, 3), dtype=torch.int32, device=points.device)
+    out_off = torch.empty(batch + 1, dtype=torch.int64, device=points.device)
+    L.check(lib.tp_voxelize_f32(points.data_ptr(), n, stride, ncols, offsets.data_ptr(), batch, C.byref(geom),
+                                _ARITH[arith], out_pts.data_ptr(), out_idx.data_ptr(), out_off.data_ptr(),
+                                ws.data_ptr(), ws_bytes, _stream(points)), "tp_voxelize_f32")
+    launch_count += 4 if n else 0
+    n_kept = int(out_off[-1].item())
+    return out_pts[:n_kept], out_idx[:n_kept], out_off
+
+
+def voxel_index(points: torch.Tensor, pc_range, voxel_size, arith: str = "cuda"):
+    """Uncompacted crop mask [N] (uint8) and int32 voxel index [N,3] for every raw point."""
+    global launch_count
+    _need_cuda(points, "points")
+    points = points.contiguous()
+    n, stride = points.shape
+    geom = L.make_geom(pc_range, voxel_size, (1, 1, 1), (1, 1, 1))
+    keep = torch.empty(n, dtype=torch.uint8, device=points.device)
+    idx = torch.empty((n, 3), dtype=torch.int32, device=points.device)
+    L.check(L.lib().tp_voxel_index_f32(points.data_ptr(), n, stride, C.byref(geom), _ARITH[arith],
+                                       keep.data_ptr(), idx.data_ptr(), _stream(points)), "tp_voxel_index_f32")
+    launch_count += 1 if n else 0
+    return keep, idx
+
+
+# ------------------------------------------------------------------------------------------------
+# a3
+# ------------------------------------------------------------------------------------------------
+class _EncodeWorkspace:
+    """Per (device, geometry, batch) scratch whose head table is kept clean between calls."""
+    cache = {}
+
+    @classmethod
+    def get(cls, device, geom: L.tp_geom, key, batch: int, n: int, stream: int) -> Tuple[torch.Tensor, int]:
+        lib = L.lib()
+        k = (device.index, key, batch)
+        need = lib.tp_encode_workspace_bytes(C.byref(geom), batch, n)
+        if need < 0:
+            raise TriplaneError("tp_encode_workspace_bytes: bad geometry")
+        ent = cls.cache.get(k)
+        if ent is None or ent[1] < n:
+            cap_n = max(n, 1024) if ent is None else max(n, 2 * ent[1])
+            nbytes = lib.tp_encode_workspace_bytes(C.byref(geom), batch, cap_n)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            L.check(lib.tp_encode_workspace_init(ws.data_ptr(), nbytes, stream), "tp_encode_workspace_init")
+            ent = (ws, cap_n, nbytes)
+            cls.cache[k] = ent
+        return ent[0], ent[2]
+
+
+def encode(feats: torch.Tensor, offsets: torch.Tensor, pc_range, voxel_size, grid_size, split, *,
+           grid_ind: Optional[torch.Tensor] = None, points: Optional[torch.Tensor] = None,
+           reduce: str = "max", clamp_zero: bool = False, want_counts: bool = False, arith: str = "cuda",
+           planes: Sequence[bool] = (True, True, True)):
+    """Fused triplane encode (point_triplane_projector.py:99-115).
+
+    feats [N, C]; offsets [B+1] int64; either grid_ind [N,3] int32 (reference signature) or raw
+    points [N, >=3] (crop + index fused in-kernel). Returns (xy [B,X,Y,Zp*C], yz [B,Y,Z,Xp*C],
+    xz [B,X,Z,Yp*C][, counts int32 [cells]])."""
+    global launch_count
+    _need_cuda(feats, "feats")
+    _need_cuda(offsets, "offsets", torch.int64)
+    if feats.dim() != 2:
+        raise TriplaneError(f"feats must be [N, C], got {tuple(feats.shape)}")
+    if feats.stride(1) != 1 or feats.stride(0) % 4 or feats.data_ptr() % 16:
+        feats = feats.contiguous()
+    n, Cch = feats.shape
+    if (grid_ind is None) == (points is None):
+        raise TriplaneError("encode: pass exactly one of grid_ind / points")
+    if grid_ind is not None:
+        _need_cuda(grid_ind, "grid_ind", torch.int32)
+        grid_ind = grid_ind.contiguous()
+        if tuple(grid_ind.shape) != (n, 3):
+            raise TriplaneError(f"grid_ind must be [{n}, 3], got {tuple(grid_ind.shape)}")
+    else:
+        _need_cuda(points, "points")
+        points = points.contiguous()
+        if points.shape[0] != n or points.shape[1] < 3:
+            raise TriplaneError(f"points must be [{n}, >=3], got {tuple(points.shape)}")
+    batch = offsets.numel() - 1
+    pool = pool_kernels(grid_size, split)
+    P = pooled_sizes(grid_size, pool)
+    X, Y, Z = (int(g) for g in grid_size)
+    geom = L.make_geom(pc_range, voxel_size, grid_size, pool)
+    key = (tuple(float(v) for v in pc_range), tuple(float(v) for v in voxel_size), (X, Y, Z), pool)
+    dev = feats.device
+    stream = _stream(feats)
+    ws, ws_bytes = _EncodeWorkspace.get(dev, geom, key, batch, n, stream)
+    shapes = [(batch, X, Y, P[2] * Cch), (batch, Y, Z, P[0] * Cch), (batch, X, Z, P[1] * Cch)]
+    outs = [torch.empty(s, dtype=torch.float32, device=dev) if use else None for s, use in zip(shapes, planes)]
+    counts = None
+    if want_counts:
+        ncell = batch * (X * Y * P[2] + Y * Z * P[0] + X * Z * P[1])
+        counts = torch.zeros(ncell, dtype=torch.int32, device=dev)
+    L.check(L.lib().tp_encode_f32(feats.data_ptr(), feats.stride(0), Cch, _ptr(grid_ind), _ptr(points),
+                                  0 if points is None else points.shape[1], n, offsets.data_ptr(), batch,
+                                  C.byref(geom), _ARITH[arith], _REDUCE[reduce], int(bool(clamp_zero)),
+                                  _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(counts),
+                                  ws.data_ptr(), ws_bytes, stream), "tp_encode_f32")
+    launch_count += 2 if n else 1
+    return (outs[0], outs[1], outs[2], counts) if want_counts else (outs[0], outs[1], outs[2])
+
+
+def finalize_mean(planes: torch.Tensor, counts: torch.Tensor, channels: int) -> torch.Tensor:
+    """In place: planes[cell, :] /= max(count[cell], 1) — after a point-sharded SUM all-reduce."""
+    global launch_count
+    _need_cuda(planes, "planes")
+    _need_cuda(counts, "counts", torch.int32)
+    if not planes.is_contiguous():
+        raise TriplaneError("finalize_mean: planes must be contiguous")
+    cells = planes.numel() // channels
+    L.check(L.lib().tp_encode_finalize_mean_f32(planes.data_ptr(), counts.data_ptr(), cells, channels,
+                                                _stream(planes)), "tp_encode_finalize_mean_f32")
+    launch_count += 1
+    return planes
+
+
+def voxel_counts(grid_ind: torch.Tensor, offsets: torch.Tensor, grid_size) -> torch.Tensor:
+    """Dense [B,X,Y,Z] int32 histogram of points per voxel (unq_cnt of projector.py:99, densified)."""
+    global launch_count
+    _need_cuda(grid_ind, "grid_ind", torch.int32)
+    _need_cuda(offsets, "offsets", torch.int64)
+    batch = offsets.numel() - 1
+    X, Y, Z = (int(g) for g in grid_size)
+    geom = L.make_geom([0] * 6, (1, 1, 1), grid_size, (1, 1, 1))
+    counts = torch.zeros((batch, X, Y, Z), dtype=torch.int32, device=grid_ind.device)
+    grid_ind = grid_ind.contiguous()
+    L.check(L.lib().tp_voxel_counts_i32(grid_ind.data_ptr(), grid_ind.shape[0], offsets.data_ptr(), batch,
+                                        C.byref(geom), counts.data_ptr(), _stream(grid_ind)), "tp_voxel_counts_i32")
+    launch_count += 1 if grid_ind.shape[0] else 0
+    return counts
+
+
+# ------------------------------------------------------------------------------------------------
+# a4
+# ------------------------------------------------------------------------------------------------
+def _plane_array(planes: Sequence[torch.Tensor]):
+    arr = (L.tp_plane * 3)()
+    for k, p in enumerate(planes):
+        arr[k].data = p.data_ptr()
+        arr[k].batch_stride = p.stride(0)
+        arr[k].H, arr[k].W = p.shape[-2], p.shape[-1]
+    return arr
+
+
+def planes_to_channels_last(planes: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    """NCHW planes (the reference layout; views of the stacked [B,3,C,H,W] are fine) -> contiguous
+    channels-last [B,H,W,C] copies for the gather kernel."""
+    global launch_count
+    out = []
+    for k, p in enumerate(planes):
+        _need_cuda(p, f"plane {k}")
+        if p.dim() != 4:
+            raise TriplaneError(f"plane {k} must be [B,C,H,W], got {tuple(p.shape)}")
+        B, Cc, H, W = p.shape
+        if p.stride(3) != 1 or p.stride(2) != W or p.stride(1) != H * W:
+            p = p.contiguous()
+        dst = torch.empty((B, H, W, Cc), dtype=torch.float32, device=p.device)
+        L.check(L.lib().tp_planes_nchw_to_nhwc_f32(p.data_ptr(), p.stride(0), dst.data_ptr(), B, Cc, H, W,
+                                                   _stream(p)), "tp_planes_nchw_to_nhwc_f32")
+        launch_count += 1
+        out.append(dst)
+    return out
+
+
+def sample3(planes: Union[torch.Tensor, Sequence[torch.Tensor]], queries: torch.Tensor, lo, vs, half, *,
+            arith: str = "cuda", channels_last: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fused 3-plane bilinear sample + sum.
+
+    planes: stacked [B,3,C,H,W] or a list of three NCHW planes [B,C,H_p,W_p] (channels_last=True:
+    already-converted [B,H_p,W_p,C] copies from planes_to_channels_last()). queries [B,Q,3].
+    half[a] = S_a / 2 (triplane_occ.py:337 / point_triplane.py:455-458). Returns [B,C,Q]."""
+    global launch_count
+    if isinstance(planes, torch.Tensor):
+        if planes.dim() != 5 or planes.shape[1] != 3:
+            raise TriplaneError(f"stacked triplane must be [B,3,C,H,W], got {tuple(planes.shape)}")
+        planes = [planes[:, 0], planes[:, 1], planes[:, 2]]
+    if len(planes) != 3:
+        raise TriplaneError("expected three planes")
+    _need_cuda(queries, "queries")
+    if queries.dim() != 3 or queries.shape[-1] != 3:
+        raise TriplaneError(f"queries must be [B,Q,3], got {tuple(queries.shape)}")
+    queries = queries.contiguous()
+    B, Q, _ = queries.shape
+    nhwc = list(planes) if channels_last else planes_to_channels_last(planes)
+    Cc = nhwc[0].shape[-1]
+    for k, p in enumerate(nhwc):
+        _need_cuda(p, f"plane {k}")
+        if p.shape[0] != B or p.shape[-1] != Cc or not p.is_contiguous():
+            raise TriplaneError(f"plane {k}: expected contiguous [B={B},H,W,C={Cc}], got {tuple(p.shape)}")
+    arr = (L.tp_plane * 3)()
+    for k, p in enumerate(nhwc):
+        arr[k].data = p.data_ptr()
+        arr[k].batch_stride = p.stride(0)
+        arr[k].H, arr[k].W = p.shape[1], p.shape[2]
+    sg = L.make_sample_geom(lo, vs, half)
+    if out is None:
+        out = torch.empty((B, Cc, Q), dtype=torch.float32, device=queries.device)
+    elif tuple(out.shape) != (B, Cc, Q) or not out.is_contiguous() or not out.is_cuda:
+        raise TriplaneError("sample3: bad `out`")
+    L.check(L.lib().tp_sample3_nhwc_f32(C.byref(arr), Cc, queries.data_ptr(), Q, B, C.byref(sg), _ARITH[arith],
+                                        out.data_ptr(), _stream(queries)), "tp_sample3_nhwc_f32")
+    launch_count += 1 if Q else 0
+    return out

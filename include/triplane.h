@@ -1,0 +1,194 @@
+/*
+ * triplane.h — C ABI of libtriplane.so: the B200 (sm_100a) triplane hot path.
+ *
+ * The reference (charyyev/efficient_multimodal_perception) has NO FFI for this path: its boundary
+ * is a set of Python methods that call torch / torch_scatter / spconv ops. Each entry point below
+ * names the reference call site (file:line under /root/reference) whose arithmetic it replaces.
+ * The Python modules in efficient_multimodal_perception_b200/ bind these with ctypes and keep the
+ * reference's method names and forward() signatures.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host` or the comment says host;
+ *   - the caller allocates every output and workspace buffer; nothing here allocates device memory;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it and never
+ *     synchronise the device (the *_host entry points are the exception and say so);
+ *   - return value: 0 = ok, <0 = argument error (TP_E_*), >0 = a cudaError_t; tp_last_error()
+ *     returns a thread-local message for the last non-zero return;
+ *   - all arithmetic is fp32 / int32, compiled WITHOUT --use_fast_math; the coordinate chain
+ *     replays the reference's op sequence (see tp_arith).
+ */
+#ifndef TRIPLANE_H_
+#define TRIPLANE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TP_VERSION 1
+
+#if defined(__GNUC__)
+#define TP_API __attribute__((visibility("default")))
+#else
+#define TP_API
+#endif
+
+/* argument errors */
+#define TP_E_NULL      (-1)  /* required pointer is NULL */
+#define TP_E_SHAPE     (-2)  /* size / stride / channel constraint violated */
+#define TP_E_ENUM      (-3)  /* unknown enum value */
+#define TP_E_WORKSPACE (-4)  /* workspace too small */
+
+/*
+ * Which PyTorch device's op sequence the coordinate chain replays. The reference writes
+ *   v = (p - lo) / vs ;  g = v / (S/2) - 1            (triplane_occ.py:333-337, point_triplane.py:451-458)
+ * with Python-float divisors. torch-CUDA evaluates `tensor / python_float` as a multiply by the fp32
+ * reciprocal, torch-CPU as a true division; ATen's grid_sampler un-normalises as
+ * ((g+1)*W-1)/2 on CUDA and (g+1)*(W/2)-0.5 on CPU. Indices differ in rare ulp cases, so the
+ * caller says which one it wants to be bit-compatible with.
+ */
+typedef enum tp_arith {
+  TP_ARITH_TORCH_CUDA = 0, /* x * fp32(1/d); unnormalise ((g+1)*W-1)/2 (fma-contracted as nvcc does) */
+  TP_ARITH_TORCH_CPU  = 1  /* x / d (IEEE);  unnormalise (g+1)*(W/2) - 0.5                           */
+} tp_arith;
+
+typedef enum tp_reduce {
+  TP_REDUCE_MAX  = 0, /* reference: torch_scatter.scatter_max + SparseMaxPool3d (projector.py:104,113-115) */
+  TP_REDUCE_MEAN = 1, /* north-star extension: sum / count per pooled cell                               */
+  TP_REDUCE_SUM  = 2  /* partial sums for the point-sharded multi-GPU mean (divide after the all-reduce)  */
+} tp_reduce;
+
+/* Voxel geometry: pc_range / voxel_size / grid_size of configs/point_triplane.py:8-10. Host struct. */
+typedef struct tp_geom {
+  float lo[3];       /* pc_range[0:3]                                   */
+  float hi[3];       /* pc_range[3:6]                                   */
+  float vs[3];       /* voxel_size                                      */
+  int32_t grid[3];   /* grid_size (X, Y, Z)                             */
+  int32_t pool[3];   /* pooling kernel (kx, ky, kz) = int(grid/split), projector.py:53-58 */
+} tp_geom;
+
+/* One feature plane for decode. */
+typedef struct tp_plane {
+  const float* data;     /* NCHW [B, C, H, W] or NHWC [B, H, W, C] depending on the entry point */
+  int64_t batch_stride;  /* elements between consecutive samples (3*C*H*W for the stacked [B,3,C,H,W]) */
+  int32_t H, W;          /* grid_sample: first coordinate of the pair -> W (last dim), second -> H */
+} tp_plane;
+
+/* Per-axis affine for decode: v_a = (p_a - lo_a) / vs_a ; g_a = v_a / half_a - 1  (half_a = S_a / 2) */
+typedef struct tp_sample_geom {
+  float lo[3];
+  float vs[3];
+  float half[3];
+} tp_sample_geom;
+
+TP_API const char* tp_last_error(void);
+TP_API int tp_version(void);
+/* number of SMs of the current device (grid sizing); <0 on error */
+TP_API int tp_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * a1  voxelize_points — point_triplane.py:133-161 (twin point_triplane_occ.py:132-160)
+ *
+ * points  [n_total, point_stride] fp32, samples concatenated; in_offsets [B+1] int64 (device).
+ * Stable compaction of the points with lo < p < hi (strict, all three axes), copying `ncols`
+ * columns, and idx = int32(trunc((p - lo) (/) vs)) per tp_arith. Order inside a sample is kept
+ * (the reference's boolean-mask indexing). out_offsets [B+1] int64 (device) receives the
+ * compacted sample boundaries; out_offsets[B] = N'.
+ * workspace: tp_voxelize_workspace_bytes(n_total) bytes.
+ * ------------------------------------------------------------------------------------------- */
+TP_API int64_t tp_voxelize_workspace_bytes(int64_t n_total);
+TP_API int tp_voxelize_f32(const float* points, int64_t n_total, int32_t point_stride, int32_t ncols,
+                    const int64_t* in_offsets, int32_t batch,
+                    const tp_geom* geom, int32_t arith,
+                    float* out_points /* [>=N', ncols] */, int32_t* out_idx /* [>=N', 3] */,
+                    int64_t* out_offsets /* [B+1] */,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+
+/* uncompacted variant: keep[n] (uint8) and idx[n,3] for every raw point (idx undefined where !keep) */
+TP_API int tp_voxel_index_f32(const float* points, int64_t n_total, int32_t point_stride,
+                       const tp_geom* geom, int32_t arith,
+                       uint8_t* keep, int32_t* idx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a3  triplane encode — point_triplane_projector.py:99-115
+ *     torch.unique -> torch_scatter.scatter_max -> 3 x SparseMaxPool3d -> .dense()
+ *     -> permute(...).flatten(3), fused: max over all points of a pooled cell, written once.
+ *
+ * feats   [n_total, C] fp32 (row stride feat_stride elements), C % 4 == 0
+ * Either idx [n_total,3] int32 (the reference's grid_ind, batch by offsets) or, when idx == NULL,
+ * xyz points [n_total, point_stride] from which crop + index are computed in-kernel (fused a1).
+ * offsets [B+1] int64 device: sample boundaries.
+ * Outputs, channels-last, exactly the post-permute/flatten layouts of projector.py:113-115:
+ *   out_xy [B, X, Y, Zp*C]   out_yz [B, Y, Z, Xp*C]   out_xz [B, X, Z, Yp*C]
+ * with Xp = (X-kx)/kx+1 etc. Points whose pooled index falls outside the pooled extent are dropped
+ * for that plane (spconv stride/kernel semantics); points with idx outside [0,grid) are dropped.
+ * Empty cells are 0. clamp_zero != 0 -> max(0, .) (spconv native-path ambiguity).
+ * cell_count (optional, may be NULL): int32 [cells] number of points per pooled cell, same cell order
+ * as the three outputs concatenated (xy, yz, xz).
+ * Any of out_xy/out_yz/out_xz may be NULL to skip that plane.
+ * workspace: tp_encode_workspace_bytes(); its `head` region must be all 0xFF bytes before the FIRST
+ * call (tp_encode_workspace_init) and is left clean by every call.
+ * ------------------------------------------------------------------------------------------- */
+TP_API int64_t tp_encode_cells(const tp_geom* geom, int32_t batch, int64_t cells_per_plane[3]);
+TP_API int64_t tp_encode_workspace_bytes(const tp_geom* geom, int32_t batch, int64_t n_total);
+TP_API int tp_encode_workspace_init(void* workspace, int64_t workspace_bytes, void* stream);
+TP_API int tp_encode_f32(const float* feats, int64_t feat_stride, int32_t C,
+                  const int32_t* idx, const float* points, int32_t point_stride,
+                  int64_t n_total, const int64_t* offsets, int32_t batch,
+                  const tp_geom* geom, int32_t arith, int32_t reduce, int32_t clamp_zero,
+                  float* out_xy, float* out_yz, float* out_xz, int32_t* cell_count,
+                  void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Divide partial SUM planes by counts (after a point-sharded all-reduce): out[cell,:] /= max(cnt,1). */
+TP_API int tp_encode_finalize_mean_f32(float* planes, const int32_t* cell_count, int64_t cells, int32_t C,
+                                void* stream);
+
+/* unq_cnt of projector.py:99 as a dense grid: counts [B, X, Y, Z] int32 += 1 per in-range point.
+ * counts must be zeroed by the caller. */
+TP_API int tp_voxel_counts_i32(const int32_t* idx, int64_t n_total, const int64_t* offsets, int32_t batch,
+                        const tp_geom* geom, int32_t* counts, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a4  sample_points_triplane — triplane.py:490-514, triplane_occ.py:321-348, triplane_elev.py:286-313,
+ *     point_triplane.py:439-466, point_triplane_occ.py:407-440:
+ *     normalise + 3 x F.grid_sample(bilinear, zeros, align_corners=False) + (xy + yz) + xz, fused.
+ *
+ * planes[3]: (x,y)->plane 0, (y,z)->plane 1, (x,z)->plane 2; first coordinate of each pair -> W.
+ * queries [B, Q, 3] fp32; out [B, C, Q] fp32 (the reference's channel-major result).
+ * tp_planes_nchw_to_nhwc_f32 converts a reference-layout plane [B,C,H,W] to the channels-last
+ * [B,H,W,C] copy the gather kernel reads with 16-byte loads. tp_sample3_nchw_f32 does both
+ * (nhwc_workspace >= sum_p B*C*H_p*W_p floats).
+ * ------------------------------------------------------------------------------------------- */
+TP_API int tp_planes_nchw_to_nhwc_f32(const float* src, int64_t src_batch_stride, float* dst,
+                               int32_t batch, int32_t C, int32_t H, int32_t W, void* stream);
+TP_API int tp_sample3_nhwc_f32(const tp_plane planes_nhwc[3], int32_t C,
+                        const float* queries, int64_t Q, int32_t batch,
+                        const tp_sample_geom* sg, int32_t arith,
+                        float* out, void* stream);
+TP_API int tp_sample3_nchw_f32(const tp_plane planes_nchw[3], int32_t C,
+                        const float* queries, int64_t Q, int32_t batch,
+                        const tp_sample_geom* sg, int32_t arith,
+                        float* out, float* nhwc_workspace, int64_t nhwc_workspace_floats,
+                        void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-buffer entry points (what a non-PyTorch caller binds; bench.py's `e2e` leg).
+ * All pointers are HOST memory (pinned recommended). They allocate a per-thread cached device
+ * arena, copy in, run the kernels above, copy out and synchronise the internal stream.
+ * ------------------------------------------------------------------------------------------- */
+TP_API int tp_sample3_host_f32(const float* planes_nchw_host[3], const int32_t HW[6] /* H0,W0,H1,W1,H2,W2 */,
+                        const int64_t plane_batch_stride[3], int32_t C,
+                        const float* queries_host, int64_t Q, int32_t batch,
+                        const tp_sample_geom* sg, int32_t arith, float* out_host);
+TP_API int tp_encode_host_f32(const float* feats_host, int32_t C, const float* points_host,
+                       int32_t point_stride, int64_t n_total, const int64_t* offsets_host,
+                       int32_t batch, const tp_geom* geom, int32_t arith, int32_t reduce,
+                       int32_t clamp_zero, float* out_xy_host, float* out_yz_host, float* out_xz_host);
+/* free the cached arena of the calling thread */
+TP_API void tp_host_arena_release(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRIPLANE_H_ */

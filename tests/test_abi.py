@@ -1,0 +1,83 @@
+"""CPU: libtriplane.so loads, exports every TP_API symbol of include/triplane.h, and rejects bad
+arguments before touching a device (no compute calls here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from efficient_multimodal_perception_b200 import _lib as L
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "triplane.h")).read()
+    return re.findall(r"TP_API\s+[\w\s\*]+?\b(tp_\w+)\s*\(", text)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.lib()
+    syms = header_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in triplane.h but not exported"
+    assert set(syms) == set(L.SIGNATURES), "ctypes SIGNATURES out of sync with include/triplane.h"
+    assert lib.tp_version() == 1
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(L.tp_geom) == 9 * 4 + 6 * 4
+    assert C.sizeof(L.tp_plane) == 24
+    assert C.sizeof(L.tp_sample_geom) == 36
+
+
+def test_argument_errors_are_reported_without_a_device():
+    lib = L.lib()
+    sg = L.make_sample_geom([0, 0, 0], [1, 1, 1], [1, 1, 1])
+    planes = (L.tp_plane * 3)()
+    rc = lib.tp_sample3_nhwc_f32(C.byref(planes), 32, None, 10, 1, C.byref(sg), 0, None, None)
+    assert rc == -1 and b"null" in lib.tp_last_error()
+    rc = lib.tp_sample3_nhwc_f32(C.byref(planes), 30, 1, 10, 1, C.byref(sg), 0, 1, None)
+    assert rc == -2 and b"multiple of 4" in lib.tp_last_error()
+    geom = L.make_geom([-1, -1, -1, 1, 1, 1], (0.0, 1, 1), (4, 4, 4), (1, 1, 1))
+    rc = lib.tp_voxel_index_f32(1, 10, 3, C.byref(geom), 0, 1, 1, None)
+    assert rc == -2 and b"geometry" in lib.tp_last_error()
+    geom = L.make_geom([-1, -1, -1, 1, 1, 1], (1, 1, 1), (4, 4, 4), (1, 1, 1))
+    rc = lib.tp_voxel_index_f32(1, 10, 3, C.byref(geom), 7, 1, 1, None)
+    assert rc == -3
+    rc = lib.tp_encode_f32(16, 8, 8, None, None, 0, 5, 1, 1, C.byref(geom), 0, 0, 0, None, None, None, None, 16,
+                           1 << 30, None)
+    assert rc == -1  # neither idx nor points
+    rc = lib.tp_encode_f32(16, 8, 8, 16, None, 0, 5, 1, 1, C.byref(geom), 0, 0, 0, None, None, None, None, 16, 8,
+                           None)
+    assert rc == -4 and b"workspace" in lib.tp_last_error()
+
+
+def test_cell_and_workspace_sizes():
+    lib = L.lib()
+    geom = L.make_geom([-25, -25, -5, 25, 25, 3], (0.4, 0.4, 0.1), (128, 128, 80), (5, 5, 4))
+    cells = (C.c_int64 * 3)()
+    total = lib.tp_encode_cells(C.byref(geom), 1, C.byref(cells))
+    # 327 680 + 256 000 + 256 000 = 839 680 pooled cells per sample at geometry A
+    assert list(cells) == [327680, 256000, 256000] and total == 839680
+    geom_b = L.make_geom([-50, -50, -5, 50, 50, 3], (0.5, 0.5, 0.5), (200, 200, 16), (8, 8, 1))
+    assert lib.tp_encode_cells(C.byref(geom_b), 2, C.byref(cells)) == 2 * 800000
+    assert lib.tp_encode_workspace_bytes(C.byref(geom), 1, 1000) >= 839680 * 4 + 12000
+    assert lib.tp_voxelize_workspace_bytes(0) > 0
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+    from efficient_multimodal_perception_b200 import TriplaneError, ops
+    with pytest.raises(TriplaneError, match="CUDA tensor"):
+        ops.sample3(torch.zeros(1, 3, 4, 8, 8), torch.zeros(1, 5, 3), [0] * 3, [1] * 3, [4] * 3)
+    with pytest.raises(TriplaneError, match="CUDA tensor"):
+        ops.voxel_index(torch.zeros(5, 3), [0] * 6, [1] * 3)
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from efficient_multimodal_perception_b200 import TriplaneError
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "LIB_PATH", "/nonexistent/libtriplane.so")
+    with pytest.raises(TriplaneError, match="no CPU/PyTorch fallback"):
+        L.lib()

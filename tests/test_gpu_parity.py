@@ -1,0 +1,376 @@
+"""GPU parity: libtriplane (through the C ABI) vs the reference-generated goldens, the CPU oracle and
+torch-CUDA's own ops. Bars: bit-exact for crop mask, indices, counts, scatter-max;
+normwise max|a-b| <= 1e-5 * max|b| for bilinear sampling and scatter-mean."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden, normwise
+from efficient_multimodal_perception_b200 import (PointTriplaneProjector, ops, sample_points_triplane, synth,
+                                                  voxelize_points)
+from oracle import triplane_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-5  # normwise, north star "within 1e-5 relative for fp32 scatter-mean and bilinear sampling"
+
+
+def cu(t):
+    return t.to(DEV)
+
+
+# ---------------------------------------------------------------------------------------------
+# a1 voxelize
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["voxelize_A", "voxelize_B"])
+def test_voxelize_golden_bit_exact_cpu_arith(name):
+    """arith='cpu' (true division) must reproduce the reference run on torch-CPU bit for bit,
+    including the rows on / one ulp around the crop bounds, NaN and inf rows and an empty sample."""
+    g = load_golden(name)
+    pts = [cu(g.t(f"points{i}")) for i in range(3)]
+    cropped, ind = voxelize_points(pts, g["pc_range"].tolist(), g["voxel_size"].tolist(), arith="cpu")
+    for i in range(3):
+        assert torch.equal(cropped[i].cpu(), g.t(f"cropped{i}"))
+        assert torch.equal(ind[i].cpu(), g.t(f"ind{i}"))
+        assert ind[i].dtype == torch.int32
+
+
+def test_voxelize_matches_torch_cuda_bit_exact():
+    """arith='cuda' vs the reference's expression evaluated by torch on the same GPU (multiply by the
+    fp32 reciprocal); 350k points = the S5 sample size."""
+    G = synth.GEOM_A
+    pts = cu(synth.multi_sweep(10, 35000, seed=1005))
+    rng, vs = G["pc_range"], G["voxel_size"]
+    mask = ((pts[:, 0] > rng[0]) & (pts[:, 0] < rng[3]) & (pts[:, 1] > rng[1]) & (pts[:, 1] < rng[4])
+            & (pts[:, 2] > rng[2]) & (pts[:, 2] < rng[5]))
+    ref_pts = pts[mask]
+    vi = torch.zeros((ref_pts.shape[0], 3), device=DEV)
+    for a in range(3):
+        vi[:, a] = (ref_pts[:, a] - rng[a]) / vs[a]
+    ref_ind = vi.type(torch.int)
+    cropped, ind = voxelize_points([pts], rng, vs, arith="cuda")
+    assert torch.equal(cropped[0], ref_pts)
+    assert torch.equal(ind[0], ref_ind)
+    keep, idx = ops.voxel_index(pts, rng, vs, arith="cuda")
+    assert torch.equal(keep.bool(), mask)
+    assert torch.equal(idx[mask], ref_ind)
+
+
+def test_voxelize_config_sweep_and_batch_offsets():
+    g = load_golden("voxelize_S1")
+    pts = synth.lidar_sweep(int(g["n"]), seed=int(g["seed"]))
+    batch = [cu(pts), cu(pts[:0]), cu(pts[5000:9000]), cu(pts[:1])]
+    cropped, ind = voxelize_points(batch, g["pc_range"].tolist(), g["voxel_size"].tolist(), arith="cpu")
+    assert cropped[0].shape[0] == int(g["n_kept"])
+    assert torch.equal(ind[0].cpu().to(torch.int16), g.t("ind"))
+    assert torch.equal(cropped[0].cpu().double().sum(0), g.t("cropped_checksum"))
+    assert cropped[1].shape[0] == 0
+    ref = O.voxelize_points([pts[5000:9000], pts[:1]], g["pc_range"].tolist(), g["voxel_size"].tolist())
+    assert torch.equal(cropped[2].cpu(), ref[0][0]) and torch.equal(ind[2].cpu(), ref[1][0])
+    assert torch.equal(cropped[3].cpu(), ref[0][1])
+
+
+# ---------------------------------------------------------------------------------------------
+# a3 encode
+# ---------------------------------------------------------------------------------------------
+def _rand_encode_case(n_per, grid, C, seed, hot=False):
+    g = torch.Generator().manual_seed(seed)
+    inds, feats = [], []
+    for n in n_per:
+        if hot:  # many points per cell: long lists
+            ind = torch.stack([torch.randint(0, max(1, grid[a] // 8), (n,), generator=g) for a in range(3)], 1)
+        else:
+            ind = torch.stack([torch.randint(0, grid[a], (n,), generator=g) for a in range(3)], 1)
+        inds.append(ind.int())
+        feats.append(torch.randn(n, C, generator=g))
+    return inds, torch.cat(feats)
+
+
+@pytest.mark.parametrize("grid,split,C,n_per,hot", [
+    ([16, 16, 8], [4, 4, 2], 8, (300, 200), False),
+    ([13, 13, 9], [4, 4, 2], 12, (400, 0, 250), False),      # ragged: idx 12 falls off the pooled extent
+    ([128, 128, 80], [25, 25, 20], 128, (28000,), False),    # geometry A, one sweep
+    ([200, 200, 16], [25, 25, 16], 128, (9000, 11000), False),  # geometry B
+    ([32, 32, 16], [4, 4, 4], 32, (20000,), True),           # ~150 points per cell
+    ([16, 16, 8], [4, 4, 2], 132, (500,), False),            # C not a multiple of 128: 2 float4 per lane
+])
+def test_encode_max_bit_exact_vs_oracle(grid, split, C, n_per, hot):
+    inds, feats = _rand_encode_case(n_per, grid, C, seed=sum(n_per) + C, hot=hot)
+    B = len(n_per)
+    ref = O.encode_pooled(feats, O.cat_indices(inds), grid, split, B)
+    off = cu(synth.batch_offsets(n_per))
+    for rep in range(2):  # second call proves the head table was left clean
+        xy, yz, xz, cnt = ops.encode(cu(feats), off, [0] * 6, (1, 1, 1), grid, split,
+                                     grid_ind=cu(torch.cat(inds)), want_counts=True)
+        assert torch.equal(xy.cpu(), ref[0]) and torch.equal(yz.cpu(), ref[1]) and torch.equal(xz.cpu(), ref[2])
+        ref_cnt = torch.cat(O.cell_counts(O.cat_indices(inds), grid, split, B))
+        assert torch.equal(cnt.cpu(), ref_cnt)
+
+
+def test_encode_negative_features_and_clamp_zero():
+    grid, split = [16, 16, 8], [4, 4, 2]
+    inds, feats = _rand_encode_case((700,), grid, 16, seed=5)
+    feats = -feats.abs() - 0.5
+    off = cu(synth.batch_offsets([700]))
+    ref = O.encode_pooled(feats, O.cat_indices(inds), grid, split, 1)
+    out = ops.encode(cu(feats), off, [0] * 6, (1, 1, 1), grid, split, grid_ind=cu(inds[0]))
+    assert torch.equal(out[0].cpu(), ref[0]) and float(out[0].max()) <= 0 and float(out[0].min()) < 0
+    out = ops.encode(cu(feats), off, [0] * 6, (1, 1, 1), grid, split, grid_ind=cu(inds[0]), clamp_zero=True)
+    assert float(out[0].abs().max()) == 0 and float(out[1].abs().max()) == 0
+
+
+def test_encode_out_of_grid_indices_are_dropped():
+    """z index 80 (one ulp below the upper bound) is outside spatial_shape: dropped."""
+    grid, split = [128, 128, 80], [25, 25, 20]
+    ind = torch.tensor([[3, 4, 80], [3, 4, 79], [125, 4, 5], [-1, 0, 0], [127, 127, 0]], dtype=torch.int32)
+    feats = torch.arange(5 * 8, dtype=torch.float32).view(5, 8) + 1
+    ref = O.encode_pooled(feats, O.cat_indices([ind]), grid, split, 1)
+    out = ops.encode(cu(feats), cu(synth.batch_offsets([5])), [0] * 6, (1, 1, 1), grid, split, grid_ind=cu(ind))
+    for a, b in zip(out, ref[:3]):
+        assert torch.equal(a.cpu(), b)
+    # x index 125..127: kept by pool_xy, outside the 25 pooled cells of pool_yz
+    assert float(out[0][0, 125, 4].abs().sum()) > 0 and float(out[0][0, 127, 127].abs().sum()) > 0
+    assert float(out[1].abs().sum()) == float(ref[1].abs().sum())
+
+
+def test_encode_fused_crop_index_equals_two_step():
+    """idx == NULL path: crop + voxel index inside the link kernel == voxelize_points then encode."""
+    G = synth.GEOM_A
+    raw = [synth.lidar_sweep(20000, seed=71), synth.lidar_sweep(15000, seed=72)]
+    feats = torch.randn(35000, 32, generator=torch.Generator().manual_seed(73))
+    off = cu(synth.batch_offsets([20000, 15000]))
+    for arith in ("cuda", "cpu"):
+        fused = ops.encode(cu(feats), off, G["pc_range"], G["voxel_size"], G["grid_size"], G["split"],
+                           points=cu(torch.cat(raw)[:, :3].contiguous()), arith=arith)
+        cropped, ind = voxelize_points([cu(r) for r in raw], G["pc_range"], G["voxel_size"], arith=arith)
+        keep, _ = ops.voxel_index(cu(torch.cat(raw)), G["pc_range"], G["voxel_size"], arith=arith)
+        f2 = cu(feats)[keep.bool()]
+        off2 = cu(synth.batch_offsets([c.shape[0] for c in cropped]))
+        two = ops.encode(f2, off2, [0] * 6, (1, 1, 1), G["grid_size"], G["split"], grid_ind=torch.cat(ind))
+        for a, b in zip(fused, two):
+            assert torch.equal(a, b)
+    # and against the CPU oracle end to end (arith='cpu' == torch-CPU indices)
+    cr, gi = O.voxelize_points(raw, G["pc_range"], G["voxel_size"])
+    mask = torch.cat([(r[:, 0] > -25) & (r[:, 0] < 25) & (r[:, 1] > -25) & (r[:, 1] < 25) & (r[:, 2] > -5) & (r[:, 2] < 3)
+                      for r in raw])
+    ref = O.encode_pooled(feats[mask], O.cat_indices(gi), G["grid_size"], G["split"], 2)
+    for a, b in zip(fused, ref[:3]):
+        assert torch.equal(a.cpu(), b)
+
+
+@pytest.mark.parametrize("hot", [False, True])
+def test_encode_mean_within_tolerance(hot):
+    grid, split, C = [32, 32, 16], [4, 4, 4], 32
+    inds, feats = _rand_encode_case((6000, 5000), grid, C, seed=17, hot=hot)
+    ref = O.encode_pooled(feats.double(), O.cat_indices(inds), grid, split, 2, reduce="mean")
+    off = cu(synth.batch_offsets([6000, 5000]))
+    out = ops.encode(cu(feats), off, [0] * 6, (1, 1, 1), grid, split, grid_ind=cu(torch.cat(inds)), reduce="mean")
+    for a, b in zip(out, ref[:3]):
+        assert normwise(a.cpu(), b) <= TOL
+    # SUM + counts + finalize == MEAN (the point-sharded multi-GPU path)
+    xy, yz, xz, cnt = ops.encode(cu(feats), off, [0] * 6, (1, 1, 1), grid, split, grid_ind=cu(torch.cat(inds)),
+                                 reduce="sum", want_counts=True)
+    n0, n1 = xy.numel() // C, yz.numel() // C
+    ops.finalize_mean(xy, cnt[:n0], C)
+    ops.finalize_mean(yz, cnt[n0:n0 + n1], C)
+    ops.finalize_mean(xz, cnt[n0 + n1:], C)
+    for a, b in zip((xy, yz, xz), out):
+        assert torch.equal(a, b)
+    # deterministic across runs (sorted accumulation for <= 32 points per cell)
+    if not hot:
+        again = ops.encode(cu(feats), off, [0] * 6, (1, 1, 1), grid, split, grid_ind=cu(torch.cat(inds)), reduce="mean")
+        assert all(torch.equal(a, b) for a, b in zip(out, again))
+
+
+def test_voxel_counts_match_unique():
+    grid = [16, 16, 8]
+    inds, _ = _rand_encode_case((3000, 2000), grid, 4, seed=23)
+    cat = O.cat_indices(inds)
+    unq, cnt = torch.unique(cat, return_counts=True, dim=0)
+    dense = ops.voxel_counts(cu(torch.cat(inds)), cu(synth.batch_offsets([3000, 2000])), grid).cpu()
+    assert int(dense.sum()) == 5000
+    got = dense[unq[:, 0].long(), unq[:, 1].long(), unq[:, 2].long(), unq[:, 3].long()]
+    assert torch.equal(got.long(), cnt) and int((dense > 0).sum()) == unq.shape[0]
+
+
+@pytest.mark.parametrize("name", ["projector_small", "projector_ragged"])
+def test_projector_forward_vs_reference_golden(name):
+    """The drop-in module with the reference's state_dict vs the reference class's forward."""
+    g = load_golden(name)
+    ns = int(g["nsamples"])
+    m = PointTriplaneProjector(g["grid"].tolist(), in_channels=5, out_channels=int(g["C"]),
+                               base_channels=int(g["C"]), split=g["split"].tolist())
+    m.load_state_dict({k[3:]: g.t(k) for k in g if k.startswith("sd.")})
+    m = m.to(DEV).eval()
+    with torch.no_grad():
+        out = m([cu(g.t(f"points{i}")) for i in range(ns)], [cu(g.t(f"ind{i}")) for i in range(ns)],
+                [cu(g.t(f"cam{i}")) for i in range(ns)])
+    # the Linear layers run in cuBLAS here and MKL in the golden: tolerance, not bits
+    for a, key in zip(out, ("tpv_xy", "tpv_yz", "tpv_xz")):
+        assert a.shape == g[key].shape
+        assert normwise(a.cpu(), g.t(key)) < 1e-4
+    # the kernel itself on the golden's features: bit-exact vs the oracle's dense tensors
+    feats = g.t("feats")
+    inds = [g.t(f"ind{i}") for i in range(ns)]
+    ref = O.encode_pooled(feats, O.cat_indices(inds), g["grid"].tolist(), g["split"].tolist(), ns)
+    got = ops.encode(cu(feats), cu(synth.batch_offsets([i.shape[0] for i in inds])), [0] * 6, (1, 1, 1),
+                     g["grid"].tolist(), g["split"].tolist(), grid_ind=cu(torch.cat(inds)))
+    for a, b in zip(got, ref[:3]):
+        assert torch.equal(a.cpu(), b)
+
+
+# ---------------------------------------------------------------------------------------------
+# a4 decode
+# ---------------------------------------------------------------------------------------------
+def _torch_cuda_sample(planes, q, lo, vs, half):
+    """The reference's op sequence evaluated by torch on the GPU: [B,Q,3] -> [B,C,Q]."""
+    v = torch.zeros_like(q)
+    for a in range(3):
+        v[..., a] = (q[..., a] - lo[a]) / vs[a]
+    for a in range(3):
+        v[..., a] = v[..., a] / half[a] - 1
+    v = v[:, None]
+    xy = F.grid_sample(planes[0], v[..., [0, 1]], mode="bilinear", padding_mode="zeros", align_corners=False)
+    yz = F.grid_sample(planes[1], v[..., [1, 2]], mode="bilinear", padding_mode="zeros", align_corners=False)
+    xz = F.grid_sample(planes[2], v[..., [0, 2]], mode="bilinear", padding_mode="zeros", align_corners=False)
+    return (xy + yz + xz)[:, :, 0]
+
+
+@pytest.mark.parametrize("name", ["sample_stacked4d", "sample_stacked5d_TriplaneOcc", "sample_stacked5d_TriplaneElev"])
+@pytest.mark.parametrize("arith", ["cuda", "cpu"])
+def test_sample_stacked_vs_reference_golden(name, arith):
+    g = load_golden(name)
+    tri = synth.triplane_stacked(int(g["batch"]), int(g["channels"]), int(g["size"]), seed=int(g["seed"]))
+    out = sample_points_triplane(cu(tri), cu(g.t("points")), g["lo"].tolist(), g["vs"].tolist(), arith=arith)
+    assert out.shape == g["out"].shape
+    assert normwise(out.cpu(), g.t("out")) <= TOL
+
+
+@pytest.mark.parametrize("name", ["sample_list4d", "sample_list5d"])
+def test_sample_list_vs_reference_golden(name):
+    g = load_golden(name)
+    grid = g["grid"].tolist()
+    planes = synth.triplane_list(int(g["batch"]), int(g["channels"]), grid, seed=int(g["seed"]))
+    out = sample_points_triplane([cu(p) for p in planes], cu(g.t("points")), g["lo"].tolist(), g["vs"].tolist(),
+                                 grid_size=grid)
+    assert out.shape == g["out"].shape
+    assert normwise(out.cpu(), g.t("out")) <= TOL
+
+
+def test_sample_config_exact_occ_decode():
+    """configs/triplane_occ.py shapes: C=32, 3x128x128, the 99x99x16 roi() lattice."""
+    c = load_golden("sample_occ_config")
+    tri = cu(synth.triplane_stacked(1, 32, 128, seed=int(c["seed"])))
+    ref3d = cu(synth.roi_lattice())[None]
+    out = sample_points_triplane(tri, ref3d, c["lo"].tolist(), c["vs"].tolist())
+    assert out.shape == (1, 32, 99, 99, 16)
+    flat = out.reshape(1, 32, -1).cpu()
+    assert normwise(flat[:, :, :: int(c["stride"])], c.t("out_strided")) <= TOL
+    assert normwise(flat.double().sum(-1), c.t("out_sum")) <= 1e-6
+
+
+@pytest.mark.parametrize("C,grid", [(32, None), (96, [128, 128, 80]), (4, None), (36, [20, 24, 12])])
+def test_sample_vs_torch_cuda_grid_sample(C, grid):
+    """Same GPU, same op chain: report the bitwise-equal fraction, assert the normwise bar and that we
+    are no further from fp64 truth than torch's own fp32 result."""
+    lo, vs = [-25.0, -25.0, -5.0], (0.4, 0.4, 0.1)
+    B, Q = 2, 50000
+    if grid is None:
+        tri = cu(synth.triplane_stacked(B, C, 128, seed=C))
+        planes, half = [tri[:, 0], tri[:, 1], tri[:, 2]], [64.0] * 3
+        arg = tri
+    else:
+        vs = tuple(50.0 / grid[0] for _ in range(2)) + (8.0 / grid[2],)
+        planes = [cu(p) for p in synth.triplane_list(B, C, grid, seed=C)]
+        half, arg = [grid[a] / 2 for a in range(3)], planes
+    q = torch.stack([synth.uniform_queries(Q, seed=40 + b) for b in range(B)])
+    q[:, :5000] *= 1.2  # out-of-range share
+    q = cu(q)
+    ref = _torch_cuda_sample(planes, q, lo, vs, half)
+    out = ops.sample3(arg, q, lo, vs, half)
+    assert normwise(out, ref) <= TOL
+    same = float((out == ref).float().mean())
+    print(f"\n[sample C={C}] bitwise-equal to torch-CUDA grid_sample: {same:.6f}")
+    out_nofma = ops.sample3(arg, q, lo, vs, half, arith="cuda_nofma")
+    print(f"[sample C={C}] no-fma variant bitwise-equal: {float((out_nofma == ref).float().mean()):.6f}")
+    f64 = _torch_cuda_sample([p.double() for p in planes], q.double(), lo, vs, half)
+    assert normwise(out, f64) <= max(TOL, 1.05 * normwise(ref, f64))
+
+
+def test_sample_edge_cases():
+    lo, vs, half = [-25.0, -25.0, -5.0], (0.4, 0.4, 0.1), [64.0] * 3
+    tri = cu(synth.triplane_stacked(1, 8, 128, seed=3))
+    # Q = 0
+    out = ops.sample3(tri, torch.zeros(1, 0, 3, device=DEV), lo, vs, half)
+    assert out.shape == (1, 8, 0)
+    # ragged Q (not a multiple of 32), all far outside -> exact zeros
+    q = torch.full((1, 77, 3), 1e6, device=DEV)
+    assert float(ops.sample3(tri, q, lo, vs, half).abs().max()) == 0
+    # constant planes, interior queries -> 3 * constant (partition of unity)
+    ones = torch.ones(1, 3, 8, 128, 128, device=DEV)
+    qi = cu(synth.uniform_queries(1000, seed=8)) * 0.9
+    qi[..., 2] = qi[..., 2].clamp(-4.5, 2.0)
+    out = ops.sample3(ones, qi[None], lo, vs, half)
+    assert float((out - 3).abs().max()) < 1e-5
+    # linearity
+    t2 = cu(synth.triplane_stacked(1, 8, 128, seed=4))
+    a, b = ops.sample3(tri, qi[None], lo, vs, half), ops.sample3(t2, qi[None], lo, vs, half)
+    ab = ops.sample3(tri + t2, qi[None], lo, vs, half)
+    assert normwise(ab, a + b) < 1e-5
+    # NaN query -> NaN result, like grid_sample
+    qn = qi[None, :4].clone()
+    qn[0, 0, 0] = float("nan")
+    assert torch.isnan(ops.sample3(tri, qn, lo, vs, half)[0, :, 0]).all()
+
+
+def test_sample_baseline_size_640k():
+    """BASELINE.json config[1]: 640k queries. Checked against torch-CUDA on the same inputs plus the
+    size-independent property that out-of-plane queries are exactly zero."""
+    lo, vs, half = [-25.0, -25.0, -5.0], (0.4, 0.4, 0.1), [64.0] * 3
+    tri = cu(synth.triplane_stacked(1, 32, 128, seed=1002))
+    lat = cu(synth.occ_gt_lattice().reshape(1, -1, 3))
+    out = ops.sample3(tri, lat, lo, vs, half)
+    ref = _torch_cuda_sample([tri[:, 0], tri[:, 1], tri[:, 2]], lat, lo, vs, half)
+    assert out.shape == (1, 32, 640000) and normwise(out, ref) <= TOL
+    far = (lat[0, :, :2].abs() > 25.3).any(1)
+    assert float(out[0][:, far].abs().max()) == 0 and int(far.sum()) > 400000
+    rnd = cu(synth.uniform_queries(640000, seed=1002))[None]
+    out = ops.sample3(tri, rnd, lo, vs, half)
+    ref = _torch_cuda_sample([tri[:, 0], tri[:, 1], tri[:, 2]], rnd, lo, vs, half)
+    assert normwise(out, ref) <= TOL
+
+
+def test_host_buffer_entry_points():
+    """tp_sample3_host_f32 / tp_encode_host_f32 (what a non-PyTorch caller binds)."""
+    import ctypes as C
+    from efficient_multimodal_perception_b200 import _lib as L
+    lib = L.lib()
+    lo, vs = [-25.0, -25.0, -5.0], (0.4, 0.4, 0.1)
+    tri = synth.triplane_stacked(2, 8, 128, seed=3).contiguous()
+    q = torch.stack([synth.uniform_queries(3000, seed=s) for s in (1, 2)]).contiguous()
+    out = torch.empty(2, 8, 3000)
+    ptrs = (C.c_void_p * 3)(*[tri[:, k].data_ptr() for k in range(3)])
+    hw = (C.c_int32 * 6)(128, 128, 128, 128, 128, 128)
+    bs = (C.c_int64 * 3)(*[tri.stride(0)] * 3)
+    sg = L.make_sample_geom(lo, vs, [64.0] * 3)
+    L.check(lib.tp_sample3_host_f32(C.byref(ptrs), C.byref(hw), C.byref(bs), 8, q.data_ptr(), 3000, 2,
+                                    C.byref(sg), 1, out.data_ptr()), "tp_sample3_host_f32")
+    ref = O.sample_points_triplane_stacked(tri, q[:, None], lo, vs)[:, :, 0]
+    assert normwise(out, ref) <= TOL
+    G = synth.GEOM_A
+    raw = synth.lidar_sweep(5000, seed=4)[:, :3].contiguous()
+    feats = torch.randn(5000, 16, generator=torch.Generator().manual_seed(5))
+    geom = L.make_geom(G["pc_range"], G["voxel_size"], G["grid_size"], (5, 5, 4))
+    outs = [torch.empty(1, 128, 128, 20 * 16), torch.empty(1, 128, 80, 25 * 16), torch.empty(1, 128, 80, 25 * 16)]
+    off = torch.tensor([0, 5000], dtype=torch.int64)
+    for _ in range(2):
+        L.check(lib.tp_encode_host_f32(feats.data_ptr(), 16, raw.data_ptr(), 3, 5000, off.data_ptr(), 1,
+                                       C.byref(geom), 1, 0, 0, outs[0].data_ptr(), outs[1].data_ptr(),
+                                       outs[2].data_ptr()), "tp_encode_host_f32")
+    cr, gi = O.voxelize_points([raw], G["pc_range"], G["voxel_size"])
+    mask = (raw[:, 0].abs() < 25) & (raw[:, 1].abs() < 25) & (raw[:, 2] > -5) & (raw[:, 2] < 3)
+    ref = O.encode_pooled(feats[mask], O.cat_indices(gi), G["grid_size"], G["split"], 1)
+    for a, b in zip(outs, ref[:3]):
+        assert torch.equal(a, b)
+    lib.tp_host_arena_release()

@@ -208,9 +208,30 @@ def bench_decode_device(args, dev, barrier, sampler):
         launch(i)
     torch.cuda.synchronize()
     k_avg, k_med, k_min = kernel_time_ms(launch, reps)
+    # the other query sets of SURVEY 8(d) S2, gather kernel only, same rotation of plane / output sets
+    variants = {}
+    for kind in ("lattice640k", "uniform640k", "roi"):
+        if kind == args.queries:
+            continue
+        qv = decode_queries(kind)
+        qs = [qv.roll(s * 1013, 1).to(dev) for s in range(nsets)]
+        outs = [sets.sets[s][2][:, :, :qv.shape[1]].contiguous() for s in range(nsets)]
+
+        def launch_v(i):
+            ops.sample3(nhwc[i % nsets], qs[i % nsets], OCC_LO, OCC_VS, OCC_HALF, channels_last=True,
+                        out=outs[i % nsets])
+
+        for i in range(8):
+            launch_v(i)
+        torch.cuda.synchronize()
+        va, vm, vmin = kernel_time_ms(launch_v, min(reps, 200))
+        vb = decode_bytes(qv.shape[1])
+        variants[kind] = {"Q": qv.shape[1], "kernel_ms_avg": va, "kernel_ms_median": vm, "queries_per_s": qv.shape[1] / (va * 1e-3),
+                          "algorithmic_bytes": vb, "achieved_gbs": vb / (va * 1e-3) / 1e9}
+        del qs, outs
     sampler.active.clear()
     return dict(Q=Q, nsets=nsets, ms_total=ms, kernel_ms_avg=k_avg, kernel_ms_med=k_med, kernel_ms_min=k_min,
-                launches=args.steps * 4, sets=sets)
+                launches=args.steps * 4, sets=sets, variants=variants)
 
 
 def bench_decode_e2e(args, Q_host, barrier):
@@ -266,7 +287,11 @@ def bench_encode_device(args, dev, barrier, sampler):
         outs = step()
     steps = max(10, min(args.steps, 200))
     sampler.active.set()
-    ms = time_region(lambda: [step() for _ in range(steps)], barrier)
+    def run():
+        for _ in range(steps):
+            step()  # outputs are dropped each step: the caching allocator hands the same blocks back
+
+    ms = time_region(run, barrier)
     sampler.active.clear()
     bytes_alg = n * 12 + inside * 4 * Cc + 4 * Cc * cells
     return dict(n=n, inside=inside, cells=cells, steps=steps, ms_per_step=ms / steps, bytes=bytes_alg,
@@ -342,7 +367,11 @@ def run_b200(args):
             dec["sets"].step(0)
             torch.cuda.synchronize()
             scale = float(ref.abs().max())
-            parity = {"device_vs_oracle_normwise": float((out0.cpu() - ref[:, :, 0]).abs().max()) / scale,
+            out_cpu_arith = dec["sets"].ops.sample3(tri0, q0, OCC_LO, OCC_VS, OCC_HALF, arith="cpu")
+            parity = {"note": "oracle = torch-CPU op chain; arith='cpu' replays it, the timed arith='cuda' replays "
+                              "torch-CUDA's (x * fp32(1/vs)) and is checked bitwise-level against torch-CUDA in tests/",
+                      "device_cpu_arith_vs_oracle_normwise": float((out_cpu_arith.cpu() - ref[:, :, 0]).abs().max()) / scale,
+                      "device_vs_oracle_normwise": float((out0.cpu() - ref[:, :, 0]).abs().max()) / scale,
                       "e2e_vs_oracle_normwise": float((e2e["out"] - ref[:, :, 0]).abs().max()) / scale, "bar": 1e-5}
         line = {
             "metric": "triplane decode queries/s (3-plane bilinear sample + sum, triplane_occ occupancy decode)",
@@ -367,6 +396,7 @@ def run_b200(args):
                     "steps": e2e["steps"], "api": "tp_sample3_host_f32 (C ABI, pinned host buffers; H2D planes+queries, "
                                                   "D2H full result, synchronised every step)"},
             "gpu_launches": dec["launches"],
+            "variants_kernel_only": {k: dict(v, frac=v["achieved_gbs"] / peak) for k, v in dec["variants"].items()},
             "clocks": clocks,
             "parity": parity,
             "encode": {"metric": "triplane encode points/s (fused crop+index+scatter-max into dense pooled planes)",

@@ -10,6 +10,8 @@
 // L2-resident 4 B/cell table and exactly one write of every output byte. max over the points of a
 // voxel followed by max over the voxels of a pooling window == max over the points of the pooled
 // cell, so the intermediate voxel tensor never exists. No floating-point atomics are issued.
+#include <atomic>
+
 #include "tp_common.cuh"
 
 namespace tp {
@@ -95,114 +97,136 @@ __device__ __forceinline__ float4 add4(float4 a, float4 b) {
 }
 
 // ---- pass 2: materialise ------------------------------------------------------------------------
-// Work unit = 32 consecutive cells of one (sample, plane); units are ordered sample-major
+// Work unit = kUnitCells consecutive cells of one (sample, plane); units are ordered sample-major
 // (xy, yz, xz of sample 0, then sample 1, ...) so the three planes of a sample re-read its feature
-// rows while they are still L2-resident. VPL = float4 per lane per cell (C <= 128*VPL).
+// rows while they are still L2-resident. Warps pull units from a global counter: a unit with
+// occupied cells costs one dependent load chain per point, an empty unit is 4 KB of streaming
+// stores, so a static split leaves the few dense units as a long tail (ncu, profiles/).
+// VPL = float4 per lane per cell (C <= 128*VPL).
+constexpr int kUnitCells = 8;
+constexpr int kUnitsPerGrab = 4;
+constexpr int kEncSchedSlots = 256;
+__device__ unsigned long long g_enc_sched[kEncSchedSlots][2];  // [next unit, finished warps]
+
 template <int REDUCE, int VPL>
 __global__ void __launch_bounds__(256)
 encode_materialize_kernel(const EncodeParams P, int64_t units_per_sample0, int64_t units_per_sample1,
-                          int64_t units_per_sample2) {
+                          int64_t units_per_sample2, int sched_slot) {
   const int lane = threadIdx.x & 31;
   const int64_t ups[3] = {units_per_sample0, units_per_sample1, units_per_sample2};
   const int64_t ups_all = ups[0] + ups[1] + ups[2];
   const int64_t total = ups_all * P.batch;
-  const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int C4 = P.C4;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  unsigned long long* sched = g_enc_sched[sched_slot];
 
-  for (int64_t u = gwarp; u < total; u += nwarp) {
-    const int64_t b = u / ups_all;
-    int64_t r = u - b * ups_all;
-    int k = 0;
-    if (r >= ups[0]) { r -= ups[0]; k = 1; if (r >= ups[1]) { r -= ups[1]; k = 2; } }
-    const int64_t cps = P.cells_per_sample[k];
-    const int64_t c0 = r * 32;  // first cell of the unit inside the sample
-    const int ncell = (int)min((int64_t)32, cps - c0);
-    int32_t* hp = P.head + P.head_base[k] + b * cps + c0;
-    int h = -1;
-    if (lane < ncell) {
-      h = hp[lane];
-      if (h >= 0) hp[lane] = -1;  // leave the table clean for the next call
-    }
-    float4* o = reinterpret_cast<float4*>(P.out[k]) + (b * cps + c0) * C4;
-    const int32_t* nxt = P.next + (int64_t)k * P.n;
-    const unsigned occ = __ballot_sync(0xffffffffu, h >= 0);
-    int mycount = 0;
+  for (;;) {
+    unsigned long long g = 0;
+    if (lane == 0) g = atomicAdd(&sched[0], (unsigned long long)kUnitsPerGrab);
+    const int64_t u0 = (int64_t)__shfl_sync(0xffffffffu, g, 0);
+    if (u0 >= total) break;
+    const int64_t u1 = min(total, u0 + kUnitsPerGrab);
+    for (int64_t u = u0; u < u1; ++u) {
+      const int64_t b = u / ups_all;
+      int64_t r = u - b * ups_all;
+      int k = 0;
+      if (r >= ups[0]) { r -= ups[0]; k = 1; if (r >= ups[1]) { r -= ups[1]; k = 2; } }
+      const int64_t cps = P.cells_per_sample[k];
+      const int64_t c0 = r * kUnitCells;  // first cell of the unit inside the sample
+      const int ncell = (int)min((int64_t)kUnitCells, cps - c0);
+      int32_t* hp = P.head + P.head_base[k] + b * cps + c0;
+      int h = -1;
+      if (lane < ncell) {
+        h = hp[lane];
+        if (h >= 0) hp[lane] = -1;  // leave the table clean for the next call
+      }
+      float4* o = reinterpret_cast<float4*>(P.out[k]) + (b * cps + c0) * C4;
+      const int32_t* nxt = P.next + (int64_t)k * P.n;
+      const unsigned occ = __ballot_sync(0xffffffffu, h >= 0);
+      int mycount = 0;
 
-    if (occ == 0) {  // common case: 32 empty cells = ncell*C4 contiguous float4 of zeros
-      const int64_t nvec = (int64_t)ncell * C4;
-      for (int64_t v = lane; v < nvec; v += 32) st_cs_f4(o + v, zero);
-    } else {
-      for (int j = 0; j < ncell; ++j) {
-        int p = __shfl_sync(0xffffffffu, h, j);
-        float4 acc[VPL];
+      if (occ == 0) {  // common case: ncell*C4 contiguous float4 of zeros
+        const int nvec = ncell * C4;
+        for (int v = lane; v < nvec; v += 32) st_cs_f4(o + v, zero);
+      } else {
+        for (int j = 0; j < ncell; ++j) {
+          int p = __shfl_sync(0xffffffffu, h, j);
+          float4 acc[VPL];
 #pragma unroll
-        for (int t = 0; t < VPL; ++t) acc[t] = zero;
-        int cnt = 0;
-        if (p >= 0) {
-          if (REDUCE == TP_REDUCE_MAX) {
-            bool first = true;
-            while (p >= 0) {
-              const float4* f = reinterpret_cast<const float4*>(P.feats + (int64_t)p * P.feat_stride);
-              const int pn = __ldg(nxt + p);
-#pragma unroll
-              for (int t = 0; t < VPL; ++t) {
-                const int v = lane + 32 * t;
-                if (v < C4) {
-                  float4 x = __ldg(f + v);
-                  acc[t] = first ? x : max4(acc[t], x);
-                }
-              }
-              first = false;
-              ++cnt;
-              p = pn;
-            }
-            if (P.clamp_zero) {
-#pragma unroll
-              for (int t = 0; t < VPL; ++t) acc[t] = max4(acc[t], zero);
-            }
-          } else {
-            // SUM / MEAN: accumulate in ascending point order inside each run of <= 32 list
-            // entries so the result does not depend on the (racy) insertion order for the
-            // common case of <= 32 points per cell.
-            while (p >= 0) {
-              int mine = 0x7fffffff;
-              int m = 0;
-              for (; m < 32 && p >= 0; ++m) {
-                if (lane == m) mine = p;
-                p = __ldg(nxt + p);
-              }
-              for (int s = 0; s < m; ++s) {
-                const int id = __reduce_min_sync(0xffffffffu, (unsigned)mine);
-                if (mine == id) mine = 0x7fffffff;
-                const float4* f = reinterpret_cast<const float4*>(P.feats + (int64_t)id * P.feat_stride);
+          for (int t = 0; t < VPL; ++t) acc[t] = zero;
+          int cnt = 0;
+          if (p >= 0) {
+            if (REDUCE == TP_REDUCE_MAX) {
+              bool first = true;
+              while (p >= 0) {
+                const float4* f = reinterpret_cast<const float4*>(P.feats + (int64_t)p * P.feat_stride);
+                const int pn = __ldg(nxt + p);
 #pragma unroll
                 for (int t = 0; t < VPL; ++t) {
                   const int v = lane + 32 * t;
-                  if (v < C4) acc[t] = add4(acc[t], __ldg(f + v));
+                  if (v < C4) {
+                    float4 x = __ldg(f + v);
+                    acc[t] = first ? x : max4(acc[t], x);
+                  }
                 }
+                first = false;
+                ++cnt;
+                p = pn;
               }
-              cnt += m;
-            }
-            if (REDUCE == TP_REDUCE_MEAN) {
-              const float d = (float)cnt;
+              if (P.clamp_zero) {
 #pragma unroll
-              for (int t = 0; t < VPL; ++t)
-                acc[t] = make_float4(__fdiv_rn(acc[t].x, d), __fdiv_rn(acc[t].y, d),
-                                     __fdiv_rn(acc[t].z, d), __fdiv_rn(acc[t].w, d));
+                for (int t = 0; t < VPL; ++t) acc[t] = max4(acc[t], zero);
+              }
+            } else {
+              // SUM / MEAN: accumulate in ascending point order inside each run of <= 32 list
+              // entries so the result does not depend on the (racy) insertion order for the
+              // common case of <= 32 points per cell.
+              while (p >= 0) {
+                int mine = 0x7fffffff;
+                int m = 0;
+                for (; m < 32 && p >= 0; ++m) {
+                  if (lane == m) mine = p;
+                  p = __ldg(nxt + p);
+                }
+                for (int s = 0; s < m; ++s) {
+                  const int id = __reduce_min_sync(0xffffffffu, (unsigned)mine);
+                  if (mine == id) mine = 0x7fffffff;
+                  const float4* f = reinterpret_cast<const float4*>(P.feats + (int64_t)id * P.feat_stride);
+#pragma unroll
+                  for (int t = 0; t < VPL; ++t) {
+                    const int v = lane + 32 * t;
+                    if (v < C4) acc[t] = add4(acc[t], __ldg(f + v));
+                  }
+                }
+                cnt += m;
+              }
+              if (REDUCE == TP_REDUCE_MEAN) {
+                const float d = (float)cnt;
+#pragma unroll
+                for (int t = 0; t < VPL; ++t)
+                  acc[t] = make_float4(__fdiv_rn(acc[t].x, d), __fdiv_rn(acc[t].y, d),
+                                       __fdiv_rn(acc[t].z, d), __fdiv_rn(acc[t].w, d));
+              }
             }
           }
-        }
-        if (lane == j) mycount = cnt;
+          if (lane == j) mycount = cnt;
 #pragma unroll
-        for (int t = 0; t < VPL; ++t) {
-          const int v = lane + 32 * t;
-          if (v < C4) st_cs_f4(o + (int64_t)j * C4 + v, acc[t]);
+          for (int t = 0; t < VPL; ++t) {
+            const int v = lane + 32 * t;
+            if (v < C4) st_cs_f4(o + (int64_t)j * C4 + v, acc[t]);
+          }
         }
       }
+      if (P.cell_count && lane < ncell) P.cell_count[P.count_base[k] + b * cps + c0 + lane] = mycount;
     }
-    if (P.cell_count && lane < ncell) P.cell_count[P.count_base[k] + b * cps + c0 + lane] = mycount;
+  }
+  if (lane == 0) {  // last warp out resets the scheduler slot
+    __threadfence();
+    if (atomicAdd(&sched[1], 1ull) == (unsigned long long)gridDim.x * (blockDim.x >> 5) - 1) {
+      sched[0] = 0;
+      sched[1] = 0;
+      __threadfence();
+    }
   }
 }
 
@@ -342,14 +366,16 @@ extern "C" int tp_encode_f32(const float* feats, int64_t feat_stride, int32_t C,
     TP_LAUNCH_CHECK("encode_link_kernel");
   }
   int64_t ups[3];
-  for (int k = 0; k < 3; ++k) ups[k] = P.out[k] ? (cps[k] + 31) / 32 : 0;
+  for (int k = 0; k < 3; ++k) ups[k] = P.out[k] ? (cps[k] + kUnitCells - 1) / kUnitCells : 0;
   const int64_t units = (ups[0] + ups[1] + ups[2]) * batch;
   if (units == 0) return 0;
-  const int64_t ctas = (units + 7) / 8;
-  const int64_t cap = (int64_t)kSMs * 8 * 4;  // 8 resident CTAs/SM x 4 waves, then grid-stride
+  const int64_t ctas = (units + 8 * kUnitsPerGrab - 1) / (8 * kUnitsPerGrab);
+  const int64_t cap = (int64_t)kSMs * 8;  // persistent: 8 CTAs x 8 warps resident per SM
   const int grid = (int)(ctas < cap ? ctas : cap);
   const int vpl = (P.C4 + 31) / 32;
-#define TP_MAT(R, V) encode_materialize_kernel<R, V><<<grid, 256, 0, s>>>(P, ups[0], ups[1], ups[2])
+  static std::atomic<unsigned> next_slot{0};
+  const int slot = (int)(next_slot.fetch_add(1) % kEncSchedSlots);
+#define TP_MAT(R, V) encode_materialize_kernel<R, V><<<grid, 256, 0, s>>>(P, ups[0], ups[1], ups[2], slot)
 #define TP_MAT_V(R)                                                              \
   switch (vpl) { case 1: TP_MAT(R, 1); break; case 2: TP_MAT(R, 2); break;        \
                  case 3: TP_MAT(R, 3); break; default: TP_MAT(R, 4); break; }

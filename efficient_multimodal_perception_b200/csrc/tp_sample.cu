@@ -9,6 +9,8 @@
 // (8 lanes x 16 B per 32 channels => every warp-wide LDG.128 touches 4 fully used 128-B lines);
 // the result is transposed through shared memory so the reference's channel-major [B,C,Q] output
 // is written as 128-B coalesced rows.
+#include <atomic>
+
 #include "tp_common.cuh"
 
 namespace tp {
@@ -38,11 +40,17 @@ __device__ __forceinline__ float unnormalize(float g, float size) {
 }
 
 constexpr int kWarpsPerCta = 4;
-constexpr int kParamWords = 32 * 16 + 16;  // 16 words per query + 4-word skew per 8-query group
-constexpr int kTileStride = 33;            // [32 channels][32 queries] padded: conflict-free both ways
-constexpr int kTileWords = 32 * kTileStride;
+constexpr int kParamStride = 20;  // words per query: 16 used; 20 keeps 8-lane STS.128 phases conflict-free
+constexpr int kParamWords = 32 * kParamStride + 16;  // + 4-word skew per 8-query group (LDS.128 side)
+constexpr int kTileWords = 32 * 32;  // [32 channels][32 queries], column XOR-swizzled by (channel >> 2) & 7
 
-__device__ __forceinline__ int param_base(int qi) { return qi * 16 + (qi >> 3) * 4; }
+__device__ __forceinline__ int param_base(int qi) { return qi * kParamStride + (qi >> 3) * 4; }
+
+// Dynamic tile scheduler state: a ring of (next tile, finished warps) pairs; the host picks a slot
+// per launch, the last warp of a launch resets it. In-range and out-of-range tiles differ ~5x in
+// cost, so a static split leaves SMs idle.
+constexpr int kSchedSlots = 1024;
+__device__ unsigned int g_sched[kSchedSlots][2];  // [next tile, finished warps]
 
 // per-query setup for one plane: 4 weights, nw pixel index, 4-bit in-bounds mask
 template <int ARITH>
@@ -70,29 +78,70 @@ __device__ __forceinline__ void plane_setup(float gx, float gy, int W, int H, fl
   base = mask ? (y0 * W + x0) : 0;
 }
 
-template <int ARITH>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
-sample3_kernel(const SampleParams P) {
+// ATen accumulates out_acc += val * w for nw, ne, sw, se in that order (fma-contracted by nvcc),
+// starting from 0 and skipping out-of-bounds taps.
+__device__ __forceinline__ float4 fma4(float4 v, float w, float4 a) {
+  return make_float4(__fmaf_rn(v.x, w, a.x), __fmaf_rn(v.y, w, a.y), __fmaf_rn(v.z, w, a.z),
+                     __fmaf_rn(v.w, w, a.w));
+}
+__device__ __forceinline__ float4 mul4(float4 v, float w) {  // == fma(v, w, +0) bit for bit
+  return make_float4(__fmaf_rn(v.x, w, 0.f), __fmaf_rn(v.y, w, 0.f), __fmaf_rn(v.z, w, 0.f),
+                     __fmaf_rn(v.w, w, 0.f));
+}
+
+// One plane, one query, this lane's 4 channels. C4 = C/4 is a compile-time constant in the
+// specialised kernels so the x-neighbour is an immediate offset and only the row stride needs a
+// second 64-bit pointer.
+template <bool MASKED>
+__device__ __forceinline__ float4 plane_taps(const float4* __restrict__ pl, int off, int C4, int WC4,
+                                             float4 w, int mk) {
+  const float4* t0 = pl + off;
+  const float4* t1 = t0 + WC4;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!MASKED) {
+    const float4 v00 = __ldg(t0), v01 = __ldg(t0 + C4), v10 = __ldg(t1), v11 = __ldg(t1 + C4);
+    return fma4(v11, w.w, fma4(v10, w.z, fma4(v01, w.y, mul4(v00, w.x))));
+  }
+  float4 a = z;
+  if (mk & 1) a = fma4(__ldg(t0), w.x, a);
+  if (mk & 2) a = fma4(__ldg(t0 + C4), w.y, a);
+  if (mk & 4) a = fma4(__ldg(t1), w.z, a);
+  if (mk & 8) a = fma4(__ldg(t1 + C4), w.w, a);
+  return a;
+}
+
+// C4T: C/4 known at compile time (8, 24, 32 for the reference's C = 32, 96, 128) or 0 = runtime.
+template <int ARITH, int C4T>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 8)
+sample3_kernel(const SampleParams P, const int sched_slot) {
   __shared__ __align__(16) float s_param[kWarpsPerCta][kParamWords];
-  __shared__ float s_tile[kWarpsPerCta][kTileWords];
+  __shared__ __align__(16) float s_tile[kWarpsPerCta][kTileWords];
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int sub = lane >> 3, l8 = lane & 7;
   float* sp = s_param[warp];
   float* st = s_tile[warp];
-  const int C = P.C;
-  const int nchunk = (C + 31) >> 5;
-  const int64_t gwarp = (int64_t)blockIdx.x * kWarpsPerCta + warp;
-  const int64_t nwarp = (int64_t)gridDim.x * kWarpsPerCta;
+  const int C4 = C4T ? C4T : (P.C >> 2);
+  const int C = C4 * 4;
+  const int nchunk = (C4 + 7) >> 3;
+  const int WC4_0 = P.W[0] * C4, WC4_1 = P.W[1] * C4, WC4_2 = P.W[2] * C4;
+  unsigned int* sched = g_sched[sched_slot];
+  const bool q_vec4 = ((P.Q & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0);
 
-  for (int64_t tile = gwarp; tile < P.tiles; tile += nwarp) {
+  for (;;) {
+    // warp-granular dynamic scheduling: no CTA barrier, in-range and out-of-range tiles balance out
+    unsigned int t32 = 0;
+    if (lane == 0) t32 = atomicAdd(&sched[0], 1u);
+    const int64_t tile = __shfl_sync(0xffffffffu, t32, 0);
+    if (tile >= P.tiles) break;
     const int b = (int)(tile / P.tiles_per_sample);
     const int64_t q0 = (tile - (int64_t)b * P.tiles_per_sample) * 32;
     const int64_t q = q0 + lane;
     const bool qvalid = q < P.Q;
 
     // ---- per-query coordinate chain (one lane per query) ---------------------------------
+    int anymask = 0;
     {
       float4 w[3];
       int base[3], mask[3];
@@ -120,74 +169,93 @@ sample3_kernel(const SampleParams P) {
           mask[k] = 0;
         }
       }
+      anymask = mask[0] | (mask[1] << 4) | (mask[2] << 8);
       float4* dst = reinterpret_cast<float4*>(sp + param_base(lane));
       dst[0] = w[0];
       dst[1] = w[1];
       dst[2] = w[2];
-      dst[3] = make_float4(__int_as_float(base[0]), __int_as_float(base[1]),
-                           __int_as_float(base[2]),
-                           __int_as_float(mask[0] | (mask[1] << 4) | (mask[2] << 8)));
+      // tap offsets in float4 units (base * C/4 < 2^29, checked on the host)
+      dst[3] = make_float4(__int_as_float(base[0] * C4), __int_as_float(base[1] * C4),
+                           __int_as_float(base[2] * C4), __int_as_float(anymask));
     }
+    const bool tile_empty = __all_sync(0xffffffffu, anymask == 0);
+    const bool tile_full = __all_sync(0xffffffffu, anymask == 0xfff);
     __syncwarp();
 
-    const float* pl0 = P.plane[0] + (int64_t)b * P.bstride[0];
-    const float* pl1 = P.plane[1] + (int64_t)b * P.bstride[1];
-    const float* pl2 = P.plane[2] + (int64_t)b * P.bstride[2];
+    const float4* pl0 = reinterpret_cast<const float4*>(P.plane[0] + (int64_t)b * P.bstride[0]) + l8;
+    const float4* pl1 = reinterpret_cast<const float4*>(P.plane[1] + (int64_t)b * P.bstride[1]) + l8;
+    const float4* pl2 = reinterpret_cast<const float4*>(P.plane[2] + (int64_t)b * P.bstride[2]) + l8;
 
     for (int ch = 0; ch < nchunk; ++ch) {
-      const int c4 = ch * 32 + l8 * 4;  // first of this lane's 4 channels
-      const bool cvalid = c4 < C;       // C % 4 == 0
-#pragma unroll 2
-      for (int pass = 0; pass < 8; ++pass) {
-        const int qi = sub * 8 + pass;  // 8 consecutive queries per 8-lane group
-        const float4* prm = reinterpret_cast<const float4*>(sp + param_base(qi));
-        const float4 w0 = prm[0], w1 = prm[1], w2 = prm[2], bm = prm[3];
-        const int m = cvalid ? __float_as_int(bm.w) : 0;
-        float4 acc[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const float* pl = k == 0 ? pl0 : (k == 1 ? pl1 : pl2);
-          const int Wk = P.W[k];
-          const int base = __float_as_int(k == 0 ? bm.x : (k == 1 ? bm.y : bm.z));
-          const float4 w = k == 0 ? w0 : (k == 1 ? w1 : w2);
-          const int mk = (m >> (4 * k)) & 15;
-          const float* t00 = pl + (int64_t)base * C + c4;
-          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-          float4 v00 = z, v01 = z, v10 = z, v11 = z;
-          if (mk & 1) v00 = __ldg(reinterpret_cast<const float4*>(t00));
-          if (mk & 2) v01 = __ldg(reinterpret_cast<const float4*>(t00 + C));
-          if (mk & 4) v10 = __ldg(reinterpret_cast<const float4*>(t00 + (int64_t)Wk * C));
-          if (mk & 8) v11 = __ldg(reinterpret_cast<const float4*>(t00 + (int64_t)(Wk + 1) * C));
-          // ATen accumulates out_acc += val * w for nw, ne, sw, se in that order, skipping
-          // out-of-bounds taps (fma-contracted). Skipped taps must not contribute -0/NaN.
-          float4 a = z;
-          if (mk & 1) { a.x = __fmaf_rn(v00.x, w.x, a.x); a.y = __fmaf_rn(v00.y, w.x, a.y); a.z = __fmaf_rn(v00.z, w.x, a.z); a.w = __fmaf_rn(v00.w, w.x, a.w); }
-          if (mk & 2) { a.x = __fmaf_rn(v01.x, w.y, a.x); a.y = __fmaf_rn(v01.y, w.y, a.y); a.z = __fmaf_rn(v01.z, w.y, a.z); a.w = __fmaf_rn(v01.w, w.y, a.w); }
-          if (mk & 4) { a.x = __fmaf_rn(v10.x, w.z, a.x); a.y = __fmaf_rn(v10.y, w.z, a.y); a.z = __fmaf_rn(v10.z, w.z, a.z); a.w = __fmaf_rn(v10.w, w.z, a.w); }
-          if (mk & 8) { a.x = __fmaf_rn(v11.x, w.w, a.x); a.y = __fmaf_rn(v11.y, w.w, a.y); a.z = __fmaf_rn(v11.z, w.w, a.z); a.w = __fmaf_rn(v11.w, w.w, a.w); }
-          acc[k] = a;
+      const int cmax = min(32, C - ch * 32);
+      float* orow = P.out + ((int64_t)b * C + ch * 32) * P.Q + q0;
+      if (tile_empty) {
+        // every query of the tile misses all three planes: zeros, no gathers, no staging
+        if (q_vec4) {
+          const int r0 = lane >> 3, c4q = (lane & 7) * 4;
+          if (q0 + c4q < P.Q) {
+            for (int c = r0; c < cmax; c += 4)
+              st_cs_f4(reinterpret_cast<float4*>(orow + (int64_t)c * P.Q + c4q), make_float4(0.f, 0.f, 0.f, 0.f));
+          }
+        } else if (qvalid) {
+          for (int c = 0; c < cmax; ++c) st_cs_f1(orow + (int64_t)c * P.Q + lane, 0.f);
         }
-        // (xy + yz) + xz  (triplane_occ.py:345)
-        float4 r;
-        r.x = __fadd_rn(__fadd_rn(acc[0].x, acc[1].x), acc[2].x);
-        r.y = __fadd_rn(__fadd_rn(acc[0].y, acc[1].y), acc[2].y);
-        r.z = __fadd_rn(__fadd_rn(acc[0].z, acc[1].z), acc[2].z);
-        r.w = __fadd_rn(__fadd_rn(acc[0].w, acc[1].w), acc[2].w);
-        float* t = st + (l8 * 4) * kTileStride + qi;
-        t[0] = r.x;
-        t[kTileStride] = r.y;
-        t[2 * kTileStride] = r.z;
-        t[3 * kTileStride] = r.w;
+        continue;
+      }
+      const int choff = ch * 8;
+      const bool chunk_full = cmax == 32;  // warp-uniform; partial chunks only when C % 32 != 0
+      float* tcol = st + (l8 * 4) * 32;
+      if (tile_full && chunk_full) {
+#pragma unroll
+        for (int pass = 0; pass < 8; ++pass) {
+          const int qi = sub * 8 + pass;  // 8 consecutive queries per 8-lane group
+          const float4* prm = reinterpret_cast<const float4*>(sp + param_base(qi));
+          const float4 w0 = prm[0], w1 = prm[1], w2 = prm[2], bm = prm[3];
+          const float4 a0 = plane_taps<false>(pl0 + choff, __float_as_int(bm.x), C4, WC4_0, w0, 15);
+          const float4 a1 = plane_taps<false>(pl1 + choff, __float_as_int(bm.y), C4, WC4_1, w1, 15);
+          const float4 a2 = plane_taps<false>(pl2 + choff, __float_as_int(bm.z), C4, WC4_2, w2, 15);
+          float* t = tcol + (qi ^ l8);
+          t[0] = __fadd_rn(__fadd_rn(a0.x, a1.x), a2.x);  // (xy + yz) + xz  (triplane_occ.py:345)
+          t[32] = __fadd_rn(__fadd_rn(a0.y, a1.y), a2.y);
+          t[64] = __fadd_rn(__fadd_rn(a0.z, a1.z), a2.z);
+          t[96] = __fadd_rn(__fadd_rn(a0.w, a1.w), a2.w);
+        }
+      } else {
+        const bool cvalid = ch * 32 + l8 * 4 < C;  // C % 4 == 0
+#pragma unroll 2
+        for (int pass = 0; pass < 8; ++pass) {
+          const int qi = sub * 8 + pass;
+          const float4* prm = reinterpret_cast<const float4*>(sp + param_base(qi));
+          const float4 w0 = prm[0], w1 = prm[1], w2 = prm[2], bm = prm[3];
+          const int m = cvalid ? __float_as_int(bm.w) : 0;
+          const float4 a0 = plane_taps<true>(pl0 + choff, __float_as_int(bm.x), C4, WC4_0, w0, m & 15);
+          const float4 a1 = plane_taps<true>(pl1 + choff, __float_as_int(bm.y), C4, WC4_1, w1, (m >> 4) & 15);
+          const float4 a2 = plane_taps<true>(pl2 + choff, __float_as_int(bm.z), C4, WC4_2, w2, (m >> 8) & 15);
+          float* t = tcol + (qi ^ l8);
+          t[0] = __fadd_rn(__fadd_rn(a0.x, a1.x), a2.x);
+          t[32] = __fadd_rn(__fadd_rn(a0.y, a1.y), a2.y);
+          t[64] = __fadd_rn(__fadd_rn(a0.z, a1.z), a2.z);
+          t[96] = __fadd_rn(__fadd_rn(a0.w, a1.w), a2.w);
+        }
       }
       __syncwarp();
       // ---- coalesced write of the [32 channels][32 queries] tile -------------------------
       if (qvalid) {
-        float* o = P.out + ((int64_t)b * C + ch * 32) * P.Q + q;
-        const int cmax = min(32, C - ch * 32);
+        float* o = orow + lane;
+        const int64_t Qs = P.Q;
 #pragma unroll 8
-        for (int c = 0; c < cmax; ++c) st_cs_f1(o + (int64_t)c * P.Q, st[c * kTileStride + lane]);
+        for (int c = 0; c < cmax; ++c, o += Qs) st_cs_f1(o, st[c * 32 + (lane ^ ((c >> 2) & 7))]);
       }
       __syncwarp();
+    }
+  }
+  // last warp out resets the scheduler slot for the next launch that draws it
+  if (lane == 0) {
+    __threadfence();
+    if (atomicAdd(&sched[1], 1u) == gridDim.x * kWarpsPerCta - 1) {
+      sched[0] = 0;
+      sched[1] = 0;
+      __threadfence();
     }
   }
 }
@@ -235,15 +303,16 @@ extern "C" int tp_planes_nchw_to_nhwc_f32(const float* src, int64_t src_batch_st
 extern "C" int tp_sample3_nhwc_f32(const tp_plane planes[3], int32_t C, const float* queries,
                                    int64_t Q, int32_t batch, const tp_sample_geom* sg,
                                    int32_t arith, float* out, void* stream) {
-  if (!planes || !queries || !out || !sg) return fail(TP_E_NULL, "tp_sample3_nhwc_f32: null argument");
   if (C <= 0 || (C & 3)) return fail(TP_E_SHAPE, "tp_sample3_nhwc_f32: C=%d must be a positive multiple of 4", C);
   if (batch <= 0 || Q < 0) return fail(TP_E_SHAPE, "tp_sample3_nhwc_f32: bad B=%d Q=%lld", batch, (long long)Q);
   if (Q == 0) return 0;
+  if (!planes || !queries || !out || !sg) return fail(TP_E_NULL, "tp_sample3_nhwc_f32: null argument");
   SampleParams P;
   for (int k = 0; k < 3; ++k) {
     if (!planes[k].data) return fail(TP_E_NULL, "tp_sample3_nhwc_f32: plane %d is null", k);
     if (planes[k].H <= 0 || planes[k].W <= 0 ||
-        (int64_t)planes[k].H * planes[k].W * C >= (int64_t)1 << 31)
+        (int64_t)planes[k].H * planes[k].W * C >= (int64_t)1 << 31 || planes[k].H >= (1 << 20) ||
+        planes[k].W >= (1 << 20))
       return fail(TP_E_SHAPE, "tp_sample3_nhwc_f32: plane %d H=%d W=%d unsupported", k, planes[k].H, planes[k].W);
     if ((uintptr_t)planes[k].data & 15 || (planes[k].batch_stride & 3))
       return fail(TP_E_SHAPE, "tp_sample3_nhwc_f32: plane %d not 16-byte aligned", k);
@@ -263,16 +332,25 @@ extern "C" int tp_sample3_nhwc_f32(const tp_plane planes[3], int32_t C, const fl
   P.C = C;
   P.tiles_per_sample = (Q + 31) / 32;
   P.tiles = P.tiles_per_sample * batch;
+  if (P.tiles + kWarpsPerCta >= ((int64_t)1 << 32)) return fail(TP_E_SHAPE, "tp_sample3_nhwc_f32: too many queries");
   const int64_t ctas_needed = (P.tiles + kWarpsPerCta - 1) / kWarpsPerCta;
-  const int64_t cap = (int64_t)kSMs * 16;  // persistent beyond 16 CTAs/SM worth of tiles
+  const int64_t cap = (int64_t)kSMs * 8;  // persistent: 8 resident CTAs per SM pull tiles dynamically
   const int grid = (int)(ctas_needed < cap ? ctas_needed : cap);
+  static std::atomic<unsigned> next_slot{0};
+  const int slot = (int)(next_slot.fetch_add(1) % kSchedSlots);
   cudaStream_t s = (cudaStream_t)stream;
+#define TP_SAMPLE(A, C4T) sample3_kernel<A, C4T><<<grid, kWarpsPerCta * 32, 0, s>>>(P, slot)
+#define TP_SAMPLE_C(A)                                                   \
+  switch (C) { case 32: TP_SAMPLE(A, 8); break; case 96: TP_SAMPLE(A, 24); break; \
+               case 128: TP_SAMPLE(A, 32); break; default: TP_SAMPLE(A, 0); break; }
   switch (arith) {
-    case TP_ARITH_TORCH_CUDA: sample3_kernel<TP_ARITH_TORCH_CUDA><<<grid, kWarpsPerCta * 32, 0, s>>>(P); break;
-    case TP_ARITH_TORCH_CPU:  sample3_kernel<TP_ARITH_TORCH_CPU><<<grid, kWarpsPerCta * 32, 0, s>>>(P); break;
-    case 2:                   sample3_kernel<2><<<grid, kWarpsPerCta * 32, 0, s>>>(P); break;
+    case TP_ARITH_TORCH_CUDA: TP_SAMPLE_C(TP_ARITH_TORCH_CUDA) break;
+    case TP_ARITH_TORCH_CPU:  TP_SAMPLE_C(TP_ARITH_TORCH_CPU) break;
+    case 2:                   TP_SAMPLE(2, 0); break;
     default: return fail(TP_E_ENUM, "tp_sample3_nhwc_f32: unknown arith %d", arith);
   }
+#undef TP_SAMPLE_C
+#undef TP_SAMPLE
   TP_LAUNCH_CHECK("sample3_kernel");
   return 0;
 }

@@ -176,7 +176,8 @@ def test_encode_mean_within_tolerance(hot):
     ops.finalize_mean(yz, cnt[n0:n0 + n1], C)
     ops.finalize_mean(xz, cnt[n0 + n1:], C)
     for a, b in zip((xy, yz, xz), out):
-        assert torch.equal(a, b)
+        # > 32 points per cell: accumulation order follows the (racy) list order -> last-ulp differences
+        assert torch.equal(a, b) if not hot else normwise(a, b) <= TOL
     # deterministic across runs (sorted accumulation for <= 32 points per cell)
     if not hot:
         again = ops.encode(cu(feats), off, [0] * 6, (1, 1, 1), grid, split, grid_ind=cu(torch.cat(inds)), reduce="mean")
@@ -244,7 +245,11 @@ def test_sample_stacked_vs_reference_golden(name, arith):
     tri = synth.triplane_stacked(int(g["batch"]), int(g["channels"]), int(g["size"]), seed=int(g["seed"]))
     out = sample_points_triplane(cu(tri), cu(g.t("points")), g["lo"].tolist(), g["vs"].tolist(), arith=arith)
     assert out.shape == g["out"].shape
-    assert normwise(out.cpu(), g.t("out")) <= TOL
+    # The goldens were produced by the reference on torch-CPU: arith='cpu' replays that op chain and
+    # must meet the bar. arith='cuda' replays torch-CUDA's chain (x * fp32(1/d) instead of x / d), which
+    # torch itself puts ~1.4e-5 (normwise) away from its own CPU result; its 1e-5 bar is checked against
+    # torch-CUDA in test_sample_vs_torch_cuda_grid_sample.
+    assert normwise(out.cpu(), g.t("out")) <= (TOL if arith == "cpu" else 5 * TOL)
 
 
 @pytest.mark.parametrize("name", ["sample_list4d", "sample_list5d"])
@@ -253,7 +258,7 @@ def test_sample_list_vs_reference_golden(name):
     grid = g["grid"].tolist()
     planes = synth.triplane_list(int(g["batch"]), int(g["channels"]), grid, seed=int(g["seed"]))
     out = sample_points_triplane([cu(p) for p in planes], cu(g.t("points")), g["lo"].tolist(), g["vs"].tolist(),
-                                 grid_size=grid)
+                                 grid_size=grid, arith="cpu")
     assert out.shape == g["out"].shape
     assert normwise(out.cpu(), g.t("out")) <= TOL
 
@@ -263,7 +268,7 @@ def test_sample_config_exact_occ_decode():
     c = load_golden("sample_occ_config")
     tri = cu(synth.triplane_stacked(1, 32, 128, seed=int(c["seed"])))
     ref3d = cu(synth.roi_lattice())[None]
-    out = sample_points_triplane(tri, ref3d, c["lo"].tolist(), c["vs"].tolist())
+    out = sample_points_triplane(tri, ref3d, c["lo"].tolist(), c["vs"].tolist(), arith="cpu")
     assert out.shape == (1, 32, 99, 99, 16)
     flat = out.reshape(1, 32, -1).cpu()
     assert normwise(flat[:, :, :: int(c["stride"])], c.t("out_strided")) <= TOL
@@ -333,8 +338,13 @@ def test_sample_baseline_size_640k():
     out = ops.sample3(tri, lat, lo, vs, half)
     ref = _torch_cuda_sample([tri[:, 0], tri[:, 1], tri[:, 2]], lat, lo, vs, half)
     assert out.shape == (1, 32, 640000) and normwise(out, ref) <= TOL
-    far = (lat[0, :, :2].abs() > 25.3).any(1)
-    assert float(out[0][:, far].abs().max()) == 0 and int(far.sum()) > 400000
+    # a query misses all three planes only if BOTH x and y are outside (z is always inside here);
+    # the 128-px planes span [-25, 26.2] m, half a pixel of bilinear support beyond that
+    xy = lat[0, :, :2]
+    far = ((xy < -25.5) | (xy > 26.5)).all(1)
+    assert float(out[0][:, far].abs().max()) == 0 and int(far.sum()) > 300000
+    inside = (xy.abs() < 24.7).all(1)
+    assert int(inside.sum()) > 150000 and bool((out[0][:, inside].abs().sum(0) > 0).all())
     rnd = cu(synth.uniform_queries(640000, seed=1002))[None]
     out = ops.sample3(tri, rnd, lo, vs, half)
     ref = _torch_cuda_sample([tri[:, 0], tri[:, 1], tri[:, 2]], rnd, lo, vs, half)

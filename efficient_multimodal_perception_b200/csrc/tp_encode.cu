@@ -1,230 +1,462 @@
-// a3: triplane encode. One pass links every point into the (pooled cell -> points) lists of the three
-// planes with a single 4-byte atomicExch per (point, plane); a second pass streams over the dense
-// channels-last outputs ONCE, writing zeros for empty cells and the gathered max / mean for
-// occupied ones.
+// a3: triplane encode — tile-binned scatter-reduce in shared memory, dense output written once by TMA.
 //
 // Replaces point_triplane_projector.py:99-115:
 //   torch.unique(dim=0) -> torch_scatter.scatter_max -> 3 x spconv.SparseMaxPool3d -> .dense()
 //   -> permute(...).flatten(3)
-// (a sort, three hash builds and ~6 passes over 430 MB per sample) with N'x3 integer atomics on an
-// L2-resident 4 B/cell table and exactly one write of every output byte. max over the points of a
-// voxel followed by max over the voxels of a pooling window == max over the points of the pooled
-// cell, so the intermediate voxel tensor never exists. No floating-point atomics are issued.
+// (a sort, three hash builds and ~6 passes over 430 MB per sample). max over the points of a voxel
+// followed by max over the voxels of a pooling window == max over the points of the pooled cell, so
+// the intermediate voxel tensor never exists.
+//
+// The three channels-last outputs are cut into TILES of consecutive cells (16 KB of output each).
+//   1. count:  every point computes its crop / voxel index / three pooled cells (fused a1) and
+//              bumps the point counter of the three tiles it lands in (int32 atomics, L2-resident).
+//   2. scan:   exclusive scan of the per-tile counters -> CSR offsets.
+//   3. fill:   every point writes (point id, cell inside tile) into its slot of each tile's list.
+//   4. reduce: persistent 4-warp CTAs (about ten per SM) pull tiles from a global counter. An empty
+//              tile is 16 KB of streaming zero stores. An occupied tile is reduced in the CTA's
+//              shared-memory tile buffer — its point rows are gathered with independent 16-byte loads
+//              (ids come from the CSR list: no pointer chasing) and folded in with shared-memory
+//              atomics (max on order-preserving integer keys, or fp32 add) — finalised in place and
+//              written with ONE bulk-async (TMA) store. Every output byte is written exactly once;
+//              there are no global floating-point atomics.
+// An earlier design (per-cell linked lists walked by one warp) is in git history; its ncu summary
+// (profiles/r01_encode_v1_linkedlist_ncu.txt) shows the dependent-load chains this one removes.
 #include <atomic>
+#include <cstdlib>
 
 #include "tp_common.cuh"
 
 namespace tp {
 
+constexpr int kTileFloats = 4096;  // 16 KB of output per tile
+constexpr int kMaxCpt = 256;       // cells per tile is capped (small C): bounds the per-buffer counters
+constexpr int kRedThreads = 128;   // small CTAs, ~10 resident per SM: that many tile chains in flight
+constexpr int kRedCtasPerSm = 10;
+constexpr int kGrab = 4;           // tiles taken per scheduler atomic
+constexpr int kHeavy = 48;         // tiles with at least this many points are reduced first
+
 struct EncodeParams {
   GeomDev g;
   int batch;
   int C, C4;
+  int cpt;  // cells per tile = largest power of two <= min(kTileFloats / C, kMaxCpt)
   int64_t n;
-  // plane k: cells per sample, and the dims (D0, D1, P) of out_k [B, D0, D1, P*C]
   int64_t cells_per_sample[3];
-  int64_t head_base[3];  // offset of plane k's head entries (sample-major inside the plane)
+  int64_t tiles_per_sample[3];  // 0 for a skipped plane
+  int64_t tiles_all;            // sum over planes
+  int64_t tiles_total;          // * batch
   const int32_t* idx;
   const float* points;
   int point_stride;
   const int64_t* offsets;
   const float* feats;
   int64_t feat_stride;
-  int32_t* head;
-  int32_t* next;  // [3][n]
+  int32_t* tile_cnt;    // [tiles_total]   zero on entry, zero on exit
+  int32_t* tile_start;  // [tiles_total + 1]
+  int32_t* heavy;       // [1 + tiles_total]: count, then the tiles with >= kHeavy points (scan pass)
+  int32_t* rank;        // [3][n]
+  int2* entries;        // [3n] (point id, cell inside tile)
   float* out[3];
   int32_t* cell_count;  // optional, order xy | yz | xz, each [B, cells_per_sample]
   int64_t count_base[3];
   int clamp_zero;
 };
 
-// ---- pass 1: link ----------------------------------------------------------------------------
+// tile order: sample-major, then plane, then position — the three planes of a sample are reduced
+// close together in time so their feature rows are re-read from L2, not HBM.
+__device__ __forceinline__ int64_t tile_index(const EncodeParams& P, int64_t b, int k, int64_t cell) {
+  int64_t t = b * P.tiles_all + cell / P.cpt;
+  if (k >= 1) t += P.tiles_per_sample[0];
+  if (k >= 2) t += P.tiles_per_sample[1];
+  return t;
+}
+
+// crop + voxel index + the three pooled cells of point i; cell[k] = -1 where the point does not
+// contribute (outside the crop / grid, plane skipped, or beyond the pooled extent).
+template <int ARITH>
+__device__ __forceinline__ int64_t point_cells(const EncodeParams& P, int64_t i, int64_t cell[3]) {
+  const GeomDev& g = P.g;
+  cell[0] = cell[1] = cell[2] = -1;
+  int ix, iy, iz;
+  bool keep;
+  if (P.idx) {
+    ix = __ldg(P.idx + i * 3);
+    iy = __ldg(P.idx + i * 3 + 1);
+    iz = __ldg(P.idx + i * 3 + 2);
+    keep = true;
+  } else {
+    const float* p = P.points + i * P.point_stride;
+    keep = tp_crop_index<ARITH>(g, __ldg(p), __ldg(p + 1), __ldg(p + 2), ix, iy, iz);
+  }
+  // spconv would index out of bounds for idx outside the grid; we drop the point.
+  keep = keep & (ix >= 0) & (ix < g.grid[0]) & (iy >= 0) & (iy < g.grid[1]) & (iz >= 0) &
+         (iz < g.grid[2]);
+  if (!keep) return -1;
+  const int px = ix / g.pool[0], py = iy / g.pool[1], pz = iz / g.pool[2];
+  // xy: [B, X, Y, Zp]  (pool_xy(...).dense().permute(0,2,3,4,1), projector.py:113)
+  if (P.out[0] && pz < g.pooled[2]) cell[0] = ((int64_t)ix * g.grid[1] + iy) * g.pooled[2] + pz;
+  // yz: [B, Y, Z, Xp]  (permute(0,3,4,2,1), projector.py:114)
+  if (P.out[1] && px < g.pooled[0]) cell[1] = ((int64_t)iy * g.grid[2] + iz) * g.pooled[0] + px;
+  // xz: [B, X, Z, Yp]  (permute(0,2,4,3,1), projector.py:115)
+  if (P.out[2] && py < g.pooled[1]) cell[2] = ((int64_t)ix * g.grid[2] + iz) * g.pooled[1] + py;
+  return tp_find_batch(P.offsets, P.batch, i);
+}
+
+// ---- pass 1: count ---------------------------------------------------------------------------
 template <int ARITH>
 __global__ void __launch_bounds__(256)
-encode_link_kernel(const EncodeParams P) {
-  const GeomDev& g = P.g;
+encode_count_kernel(const EncodeParams P) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n;
        i += (int64_t)gridDim.x * blockDim.x) {
-    int ix, iy, iz;
-    bool keep;
-    if (P.idx) {
-      ix = __ldg(P.idx + i * 3);
-      iy = __ldg(P.idx + i * 3 + 1);
-      iz = __ldg(P.idx + i * 3 + 2);
-      keep = true;
-    } else {
-      const float* p = P.points + i * P.point_stride;
-      keep = tp_crop_index<ARITH>(g, __ldg(p), __ldg(p + 1), __ldg(p + 2), ix, iy, iz);
-    }
-    // spconv would index out of bounds for idx outside the grid; we drop the point.
-    keep = keep & (ix >= 0) & (ix < g.grid[0]) & (iy >= 0) & (iy < g.grid[1]) & (iz >= 0) &
-           (iz < g.grid[2]);
-    if (!keep) continue;
-    const int64_t b = tp_find_batch(P.offsets, P.batch, i);
-    const int px = ix / g.pool[0], py = iy / g.pool[1], pz = iz / g.pool[2];
-    // plane xy: [B, X, Y, Zp]   (pool_xy(...).dense().permute(0,2,3,4,1), projector.py:113)
-    if (P.out[0] && pz < g.pooled[2]) {
-      int64_t cell = P.head_base[0] + b * P.cells_per_sample[0] +
-                     ((int64_t)ix * g.grid[1] + iy) * g.pooled[2] + pz;
-      P.next[i] = atomicExch(P.head + cell, (int)i);
-    }
-    // plane yz: [B, Y, Z, Xp]   (permute(0,3,4,2,1), projector.py:114)
-    if (P.out[1] && px < g.pooled[0]) {
-      int64_t cell = P.head_base[1] + b * P.cells_per_sample[1] +
-                     ((int64_t)iy * g.grid[2] + iz) * g.pooled[0] + px;
-      P.next[P.n + i] = atomicExch(P.head + cell, (int)i);
-    }
-    // plane xz: [B, X, Z, Yp]   (permute(0,2,4,3,1), projector.py:115)
-    if (P.out[2] && py < g.pooled[1]) {
-      int64_t cell = P.head_base[2] + b * P.cells_per_sample[2] +
-                     ((int64_t)ix * g.grid[2] + iz) * g.pooled[1] + py;
-      P.next[2 * P.n + i] = atomicExch(P.head + cell, (int)i);
+    int64_t cell[3];
+    const int64_t b = point_cells<ARITH>(P, i, cell);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      int r = -1;
+      if (b >= 0 && cell[k] >= 0) r = atomicAdd(P.tile_cnt + tile_index(P, b, k, cell[k]), 1);
+      P.rank[(int64_t)k * P.n + i] = r;
     }
   }
 }
 
-__device__ __forceinline__ float max_nan(float a, float b) {
-  float r;
-  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+// ---- pass 2: exclusive scan of tile counters (one CTA, 8192 counters per iteration) -----------
+__global__ void __launch_bounds__(1024)
+encode_scan_kernel(const int32_t* __restrict__ cnt, int32_t* __restrict__ start, int32_t* __restrict__ heavy,
+                   int64_t T) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  __shared__ int s_hc;  // heavy tiles found so far
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) { s_carry = 0; s_hc = 0; }
+  __syncthreads();
+  for (int64_t base = 0; base < T; base += 8192) {
+    const int64_t i0 = base + (int64_t)tid * 8;
+    int v[8];
+    if (i0 + 8 <= T) {  // the counter array is 256-byte aligned: two 16-byte loads
+      const int4 a = *reinterpret_cast<const int4*>(cnt + i0);
+      const int4 b = *reinterpret_cast<const int4*>(cnt + i0 + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (i0 + j < T) ? cnt[i0 + j] : 0;
+    }
+    int sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sum += v[j];
+      if (v[j] >= kHeavy) heavy[1 + atomicAdd(&s_hc, 1)] = (int)(i0 + j);
+    }
+    int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = s_warp[lane], wi = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, wi, d);
+        if (lane >= d) wi += t;
+      }
+      s_warp[lane] = wi - w;
+    }
+    __syncthreads();
+    int run = s_carry + s_warp[warp] + incl - sum;
+    int o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o[j] = run; run += v[j]; }
+    if (i0 + 8 <= T) {
+      *reinterpret_cast<int4*>(start + i0) = make_int4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<int4*>(start + i0 + 4) = make_int4(o[4], o[5], o[6], o[7]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (i0 + j < T) start[i0 + j] = o[j];
+    }
+    __syncthreads();
+    if (tid == 1023) s_carry = run;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    start[T] = s_carry;
+    heavy[0] = s_hc;
+  }
+}
+
+// ---- pass 3: fill ------------------------------------------------------------------------------
+template <int ARITH>
+__global__ void __launch_bounds__(256)
+encode_fill_kernel(const EncodeParams P) {
+  unsigned long long pol_keep;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t cell[3];
+    const int64_t b = point_cells<ARITH>(P, i, cell);
+    if (b < 0) continue;
+    // Pull this point's feature row into L2 now, with evict_last priority: the reduce pass gathers it
+    // up to three times while the dense output streams through L2, and a gather that misses waits in
+    // the DRAM queues behind ~6 TB/s of writes.
+    if ((cell[0] & cell[1] & cell[2]) >= 0 || cell[0] >= 0 || cell[1] >= 0 || cell[2] >= 0) {
+      const char* row = reinterpret_cast<const char*>(P.feats + i * P.feat_stride);
+      for (int o = 0; o < P.C * 4; o += 128)
+        asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(row + o));
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (cell[k] < 0) continue;
+      const int64_t t = tile_index(P, b, k, cell[k]);
+      const int slot = P.tile_start[t] + P.rank[(int64_t)k * P.n + i];
+      // keep the CSR list in L2 while the dense output streams through it
+      asm volatile("st.global.L2::cache_hint.v2.s32 [%0], {%1,%2}, %3;" ::"l"(P.entries + slot), "r"((int)i),
+                   "r"((int)(cell[k] % P.cpt)), "l"(pol_keep)
+                   : "memory");
+    }
+  }
+}
+
+// ---- pass 4: reduce + write ---------------------------------------------------------------------
+// order-preserving float <-> uint32 (max on keys == max on floats; +NaN is the largest key, so a NaN
+// feature propagates like torch.amax; -0 < +0)
+__device__ __forceinline__ unsigned f2key(float f) {
+  unsigned u = __float_as_uint(f);
+  return u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float key2f(unsigned k) {
+  return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu));
+}
+
+// L2 policies: the dense output is written once and never re-read by this kernel (evict_first), the
+// point rows and CSR entries are re-read by up to three planes while 430 MB of output streams past
+// them (evict_last) — without the hints the rows are evicted between planes and every gather waits in
+// the DRAM queue behind the writes (ncu: lts hit rate 5 %, profiles/r01_encode_v1_linkedlist_ncu.txt).
+__device__ __forceinline__ unsigned long long policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long policy_evict_last() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ld_keep_f4(const float4* p, unsigned long long pol) {
+  float4 r;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p), "l"(pol));
   return r;
 }
-__device__ __forceinline__ float4 max4(float4 a, float4 b) {
-  return make_float4(max_nan(a.x, b.x), max_nan(a.y, b.y), max_nan(a.z, b.z), max_nan(a.w, b.w));
+__device__ __forceinline__ void st_stream_f4(float4* p, float4 v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w), "l"(pol)
+               : "memory");
 }
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes, unsigned long long pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
+               "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes), "l"(pol)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read0() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 __device__ __forceinline__ float4 add4(float4 a, float4 b) {
-  return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z),
-                     __fadd_rn(a.w, b.w));
+  return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
 }
 
-// ---- pass 2: materialise ------------------------------------------------------------------------
-// Work unit = kUnitCells consecutive cells of one (sample, plane); units are ordered sample-major
-// (xy, yz, xz of sample 0, then sample 1, ...) so the three planes of a sample re-read its feature
-// rows while they are still L2-resident. Warps pull units from a global counter: a unit with
-// occupied cells costs one dependent load chain per point, an empty unit is 4 KB of streaming
-// stores, so a static split leaves the few dense units as a long tail (ncu, profiles/).
-// VPL = float4 per lane per cell (C <= 128*VPL).
-constexpr int kUnitCells = 8;
-constexpr int kUnitsPerGrab = 4;
 constexpr int kEncSchedSlots = 256;
-__device__ unsigned long long g_enc_sched[kEncSchedSlots][2];  // [next unit, finished warps]
+__device__ unsigned long long g_enc_sched[kEncSchedSlots][4];  // [next tile, finished CTAs, next phase-1 window, -]
 
-template <int REDUCE, int VPL>
-__global__ void __launch_bounds__(256)
-encode_materialize_kernel(const EncodeParams P, int64_t units_per_sample0, int64_t units_per_sample1,
-                          int64_t units_per_sample2, int sched_slot) {
-  const int lane = threadIdx.x & 31;
-  const int64_t ups[3] = {units_per_sample0, units_per_sample1, units_per_sample2};
-  const int64_t ups_all = ups[0] + ups[1] + ups[2];
-  const int64_t total = ups_all * P.batch;
-  const int C4 = P.C4;
-  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+// Persistent small CTAs (4 warps, one 16 KB tile buffer each, ~10 per SM). The chain per tile is
+// metadata -> CSR entries -> point rows, three dependent global loads (~3 us); the stream of dense
+// output needs a 16 KB tile per SM every ~0.4 us, so many independent tile chains must be in flight
+// per SM — measured: 3 CTAs/SM with 32 KB tiles 117 us, one 16-warp CTA per SM 210 us (profiles/).
+template <int REDUCE>
+__global__ void __launch_bounds__(kRedThreads, kRedCtasPerSm)
+encode_reduce_kernel(const EncodeParams P, int sched_slot) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* s_work = reinterpret_cast<float*>(smem_raw);           // kTileFloats, zero outside touched cells
+  int* s_cnt = reinterpret_cast<int*>(s_work + kTileFloats);    // kMaxCpt: points per cell of the tile
+  __shared__ long long s_t0;
+  __shared__ int s_npts[kGrab], s_start[kGrab];
+  __shared__ int s_heavy[1][3];  // phase 1: (tile, points, CSR start)
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kRedThreads / 32;
+  const int C = P.C, C4 = P.C4, cpt = P.cpt;
   unsigned long long* sched = g_enc_sched[sched_slot];
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const unsigned long long pol_out = policy_evict_first(), pol_in = policy_evict_last();
 
-  for (;;) {
-    unsigned long long g = 0;
-    if (lane == 0) g = atomicAdd(&sched[0], (unsigned long long)kUnitsPerGrab);
-    const int64_t u0 = (int64_t)__shfl_sync(0xffffffffu, g, 0);
-    if (u0 >= total) break;
-    const int64_t u1 = min(total, u0 + kUnitsPerGrab);
-    for (int64_t u = u0; u < u1; ++u) {
-      const int64_t b = u / ups_all;
-      int64_t r = u - b * ups_all;
-      int k = 0;
-      if (r >= ups[0]) { r -= ups[0]; k = 1; if (r >= ups[1]) { r -= ups[1]; k = 2; } }
-      const int64_t cps = P.cells_per_sample[k];
-      const int64_t c0 = r * kUnitCells;  // first cell of the unit inside the sample
-      const int ncell = (int)min((int64_t)kUnitCells, cps - c0);
-      int32_t* hp = P.head + P.head_base[k] + b * cps + c0;
-      int h = -1;
-      if (lane < ncell) {
-        h = hp[lane];
-        if (h >= 0) hp[lane] = -1;  // leave the table clean for the next call
+  // the tile buffer starts zeroed and is returned to all-zero before each reuse by clearing only the
+  // cells the previous tile touched (their counters are still set): a sparse tile costs O(points).
+  for (int i = tid; i < kTileFloats / 4; i += kRedThreads) reinterpret_cast<float4*>(s_work)[i] = zero4;
+  for (int i = tid; i < kMaxCpt; i += kRedThreads) s_cnt[i] = 0;
+  bool in_flight = false;  // thread 0: a bulk store may still be reading s_work
+
+  // One tile: empty -> 16 KB of streaming zero stores; occupied -> reduce in shared memory, one TMA store.
+  auto process_tile = [&](const int64_t t, const int npts, const int start) {
+    const int64_t b = t / P.tiles_all;
+    int64_t r = t - b * P.tiles_all;
+    int k = 0;
+    if (r >= P.tiles_per_sample[0]) { r -= P.tiles_per_sample[0]; k = 1;
+      if (r >= P.tiles_per_sample[1]) { r -= P.tiles_per_sample[1]; k = 2; } }
+    const int64_t cps = P.cells_per_sample[k];
+    const int64_t c0 = r * cpt;
+    const int ncell = (int)min((int64_t)cpt, cps - c0);
+    float* gdst = P.out[k] + (b * cps + c0) * C;
+    int32_t* gcount = P.cell_count ? P.cell_count + P.count_base[k] + b * cps + c0 : nullptr;
+
+    if (npts == 0) {
+      float4* g4 = reinterpret_cast<float4*>(gdst);
+      const int nvec = ncell * C4;
+#pragma unroll 4
+      for (int i = tid; i < nvec; i += kRedThreads) st_stream_f4(g4 + i, zero4, pol_out);
+      if (gcount) for (int c = tid; c < ncell; c += kRedThreads) gcount[c] = 0;
+      return;
+    }
+    if (tid == 0 && in_flight) { bulk_wait_read0(); in_flight = false; }
+    __syncthreads();
+    for (int c = warp; c < cpt; c += kWarps) {  // rows are warp-owned here: no barrier before the reset
+      if (s_cnt[c] > 0) {
+        for (int v = lane; v < C4; v += 32) reinterpret_cast<float4*>(s_work + c * C)[v] = zero4;
+        __syncwarp();
+        if (lane == 0) s_cnt[c] = 0;
       }
-      float4* o = reinterpret_cast<float4*>(P.out[k]) + (b * cps + c0) * C4;
-      const int32_t* nxt = P.next + (int64_t)k * P.n;
-      const unsigned occ = __ballot_sync(0xffffffffu, h >= 0);
-      int mycount = 0;
-
-      if (occ == 0) {  // common case: ncell*C4 contiguous float4 of zeros
-        const int nvec = ncell * C4;
-        for (int v = lane; v < nvec; v += 32) st_cs_f4(o + v, zero);
-      } else {
-        for (int j = 0; j < ncell; ++j) {
-          int p = __shfl_sync(0xffffffffu, h, j);
-          float4 acc[VPL];
+    }
+    __syncthreads();
+    const int2* ent = P.entries + start;
+    for (int e0 = warp * 4; e0 < npts; e0 += kWarps * 4) {
+      int2 en[4];
 #pragma unroll
-          for (int t = 0; t < VPL; ++t) acc[t] = zero;
-          int cnt = 0;
-          if (p >= 0) {
-            if (REDUCE == TP_REDUCE_MAX) {
-              bool first = true;
-              while (p >= 0) {
-                const float4* f = reinterpret_cast<const float4*>(P.feats + (int64_t)p * P.feat_stride);
-                const int pn = __ldg(nxt + p);
+      for (int j = 0; j < 4; ++j) en[j] = (e0 + j < npts) ? __ldg(ent + e0 + j) : make_int2(-1, 0);
+      for (int v = lane; v < C4; v += 32) {
+        float4 x[4];
 #pragma unroll
-                for (int t = 0; t < VPL; ++t) {
-                  const int v = lane + 32 * t;
-                  if (v < C4) {
-                    float4 x = __ldg(f + v);
-                    acc[t] = first ? x : max4(acc[t], x);
-                  }
-                }
-                first = false;
-                ++cnt;
-                p = pn;
-              }
-              if (P.clamp_zero) {
+        for (int j = 0; j < 4; ++j)
+          if (en[j].x >= 0)
+            x[j] = ld_keep_f4(reinterpret_cast<const float4*>(P.feats + (int64_t)en[j].x * P.feat_stride) + v, pol_in);
 #pragma unroll
-                for (int t = 0; t < VPL; ++t) acc[t] = max4(acc[t], zero);
-              }
-            } else {
-              // SUM / MEAN: accumulate in ascending point order inside each run of <= 32 list
-              // entries so the result does not depend on the (racy) insertion order for the
-              // common case of <= 32 points per cell.
-              while (p >= 0) {
-                int mine = 0x7fffffff;
-                int m = 0;
-                for (; m < 32 && p >= 0; ++m) {
-                  if (lane == m) mine = p;
-                  p = __ldg(nxt + p);
-                }
-                for (int s = 0; s < m; ++s) {
-                  const int id = __reduce_min_sync(0xffffffffu, (unsigned)mine);
-                  if (mine == id) mine = 0x7fffffff;
-                  const float4* f = reinterpret_cast<const float4*>(P.feats + (int64_t)id * P.feat_stride);
-#pragma unroll
-                  for (int t = 0; t < VPL; ++t) {
-                    const int v = lane + 32 * t;
-                    if (v < C4) acc[t] = add4(acc[t], __ldg(f + v));
-                  }
-                }
-                cnt += m;
-              }
-              if (REDUCE == TP_REDUCE_MEAN) {
-                const float d = (float)cnt;
-#pragma unroll
-                for (int t = 0; t < VPL; ++t)
-                  acc[t] = make_float4(__fdiv_rn(acc[t].x, d), __fdiv_rn(acc[t].y, d),
-                                       __fdiv_rn(acc[t].z, d), __fdiv_rn(acc[t].w, d));
-              }
-            }
-          }
-          if (lane == j) mycount = cnt;
-#pragma unroll
-          for (int t = 0; t < VPL; ++t) {
-            const int v = lane + 32 * t;
-            if (v < C4) st_cs_f4(o + (int64_t)j * C4 + v, acc[t]);
+        for (int j = 0; j < 4; ++j) {
+          if (en[j].x < 0) continue;
+          float* w = s_work + en[j].y * C + v * 4;
+          if (REDUCE == TP_REDUCE_MAX) {
+            unsigned* wk = reinterpret_cast<unsigned*>(w);
+            atomicMax(wk + 0, f2key(x[j].x));
+            atomicMax(wk + 1, f2key(x[j].y));
+            atomicMax(wk + 2, f2key(x[j].z));
+            atomicMax(wk + 3, f2key(x[j].w));
+          } else {
+            atomicAdd(w + 0, x[j].x);
+            atomicAdd(w + 1, x[j].y);
+            atomicAdd(w + 2, x[j].z);
+            atomicAdd(w + 3, x[j].w);
           }
         }
       }
-      if (P.cell_count && lane < ncell) P.cell_count[P.count_base[k] + b * cps + c0 + lane] = mycount;
+      if (lane < 4 && en[lane].x >= 0) atomicAdd(s_cnt + en[lane].y, 1);
+    }
+    __syncthreads();
+    // finalise touched cells in place: keys -> floats, or sum -> mean
+    for (int c = warp; c < ncell; c += kWarps) {
+      const int cnt = s_cnt[c];
+      if (cnt > 0 && REDUCE != TP_REDUCE_SUM) {
+        float4* row = reinterpret_cast<float4*>(s_work + c * C);
+        for (int v = lane; v < C4; v += 32) {
+          if (REDUCE == TP_REDUCE_MAX) {
+            const uint4 kk = *reinterpret_cast<const uint4*>(row + v);
+            float4 o = make_float4(key2f(kk.x), key2f(kk.y), key2f(kk.z), key2f(kk.w));
+            if (P.clamp_zero) o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
+            row[v] = o;
+          } else {
+            const float4 o = row[v];
+            const float d = (float)cnt;
+            row[v] = make_float4(__fdiv_rn(o.x, d), __fdiv_rn(o.y, d), __fdiv_rn(o.z, d), __fdiv_rn(o.w, d));
+          }
+        }
+      }
+      if (gcount && lane == 0) gcount[c] = cnt;
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) { bulk_store(gdst, s_work, (unsigned)ncell * (unsigned)C * 4u, pol_out); in_flight = true; }
+  };
+
+  // ---- phase 1: longest tiles first. A tile that collects hundreds of points (the ground plane
+  // folds onto one z row of the yz / xz planes) is a ~50 us chain of gathers for one CTA; started
+  // last it is the tail of the kernel, started first it hides under the streaming of the rest. The
+  // scan pass listed them; CTAs pop them one at a time.
+  const int nheavy = P.heavy[0];
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) {
+      const long long i = (long long)atomicAdd(&sched[2], 1ull);
+      s_t0 = i;
+      if (i < nheavy) {
+        const int t = P.heavy[1 + i];
+        s_heavy[0][0] = t;
+        s_heavy[0][1] = P.tile_cnt[t];  // stays >= kHeavy until the last CTA cleans up: phase 2 of
+        s_heavy[0][2] = P.tile_start[t];  // other CTAs may already be running and must keep skipping it
+      }
+    }
+    __syncthreads();
+    if (s_t0 >= nheavy) break;
+    process_tile(s_heavy[0][0], s_heavy[0][1], s_heavy[0][2]);
+  }
+
+  // ---- phase 2: everything else, in order -----------------------------------------------------
+  for (;;) {
+    __syncthreads();
+    if (tid < kGrab) {
+      long long t0 = 0;
+      if (tid == 0) t0 = (long long)atomicAdd(&sched[0], (unsigned long long)kGrab);
+      t0 = __shfl_sync((1u << kGrab) - 1u, t0, 0);
+      if (tid == 0) s_t0 = t0;
+      const long long t = t0 + tid;
+      int np = 0, st = 0;
+      if (t < P.tiles_total) {
+        np = P.tile_cnt[t];
+        if (np > 0 && np < kHeavy) {
+          st = P.tile_start[t];
+          P.tile_cnt[t] = 0;  // leave the counters clean for the next call
+        }
+      }
+      s_npts[tid] = np;
+      s_start[tid] = st;
+    }
+    __syncthreads();
+    const int64_t t0 = s_t0;
+    if (t0 >= P.tiles_total) break;
+#pragma unroll 1
+    for (int gi = 0; gi < kGrab; ++gi) {
+      const int64_t t = t0 + gi;
+      if (t >= P.tiles_total) break;
+      if (s_npts[gi] >= kHeavy) continue;  // phase 1's
+      process_tile(t, s_npts[gi], s_start[gi]);
     }
   }
-  if (lane == 0) {  // last warp out resets the scheduler slot
+  __syncthreads();
+  if (tid == 0) {
+    bulk_wait0();  // shared memory must outlive the bulk stores that read it
     __threadfence();
-    if (atomicAdd(&sched[1], 1ull) == (unsigned long long)gridDim.x * (blockDim.x >> 5) - 1) {
+    s_t0 = (atomicAdd(&sched[1], 1ull) == (unsigned long long)gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_t0) {  // last CTA out: leave the heavy tiles' counters and the scheduler slot clean
+    for (int i = tid; i < nheavy; i += kRedThreads) P.tile_cnt[P.heavy[1 + i]] = 0;
+    __syncthreads();
+    if (tid == 0) {
       sched[0] = 0;
       sched[1] = 0;
+      sched[2] = 0;
       __threadfence();
     }
   }
@@ -290,19 +522,57 @@ extern "C" int64_t tp_encode_cells(const tp_geom* geom, int32_t batch, int64_t c
   return tot;
 }
 
-static int64_t head_bytes(const tp_geom* geom, int32_t batch) {
-  int64_t cells = tp_encode_cells(geom, batch, nullptr);
-  return (cells * 4 + 255) / 256 * 256;
+static int cells_per_tile(int C) {
+  int c = 1;
+  while (c * 2 * C <= kTileFloats && c * 2 <= kMaxCpt) c *= 2;
+  return c;
 }
 
+struct EncodeLayout {
+  int64_t tiles_per_sample[3], tiles_all, tiles_total;
+  int64_t off_cnt, off_start, off_heavy, off_rank, off_ent, bytes;
+};
+
+static EncodeLayout encode_layout(const GeomDev& g, int batch, int64_t n, int C, const bool use[3]) {
+  EncodeLayout L;
+  int64_t cps[3];
+  plane_cells(g, cps);
+  const int cpt = cells_per_tile(C);
+  L.tiles_all = 0;
+  for (int k = 0; k < 3; ++k) {
+    L.tiles_per_sample[k] = use[k] ? (cps[k] + cpt - 1) / cpt : 0;
+    L.tiles_all += L.tiles_per_sample[k];
+  }
+  L.tiles_total = L.tiles_all * batch;
+  // region offsets do not depend on C or on which planes are used (sized for the most tiles, C = 512,
+  // all planes), so the "tile counters are zero between calls" invariant survives a change of C
+  int64_t tmax = 0;
+  const int cpt_min = cells_per_tile(512);
+  for (int k = 0; k < 3; ++k) tmax += (cps[k] + cpt_min - 1) / cpt_min;
+  tmax *= batch;
+  auto pad = [](int64_t b) { return (b + 255) / 256 * 256; };
+  L.off_cnt = 0;
+  L.off_start = L.off_cnt + pad(tmax * 4);
+  L.off_heavy = L.off_start + pad((tmax + 1) * 4);
+  L.off_rank = L.off_heavy + pad((tmax + 1) * 4);
+  L.off_ent = L.off_rank + pad(3 * n * 4);
+  L.bytes = L.off_ent + pad(3 * n * 8);
+  return L;
+}
+
+// workspace is sized for all three planes and the smallest tile (C = 4 would give the fewest,
+// largest tiles; C = 512 the most), so one workspace serves every C.
 extern "C" int64_t tp_encode_workspace_bytes(const tp_geom* geom, int32_t batch, int64_t n_total) {
   if (!geom || batch <= 0 || n_total < 0) return -1;
-  return head_bytes(geom, batch) + (3 * n_total * 4 + 255) / 256 * 256;
+  const bool all[3] = {true, true, true};
+  return encode_layout(make_geom_dev(*geom), batch, n_total, 512, all).bytes;
 }
 
+// The tile counters (the first region of the workspace) must be zero before the first call; every
+// call leaves them zero.
 extern "C" int tp_encode_workspace_init(void* workspace, int64_t workspace_bytes, void* stream) {
   if (!workspace) return fail(TP_E_NULL, "tp_encode_workspace_init: null workspace");
-  TP_CUDA(cudaMemsetAsync(workspace, 0xFF, (size_t)workspace_bytes, (cudaStream_t)stream));
+  TP_CUDA(cudaMemsetAsync(workspace, 0, (size_t)workspace_bytes, (cudaStream_t)stream));
   return 0;
 }
 
@@ -314,7 +584,7 @@ extern "C" int tp_encode_f32(const float* feats, int64_t feat_stride, int32_t C,
                              int64_t workspace_bytes, void* stream) {
   if (int rc = check_geom_e(geom, "tp_encode_f32")) return rc;
   if (C <= 0 || (C & 3) || C > 512) return fail(TP_E_SHAPE, "tp_encode_f32: C=%d must be a multiple of 4 in [4,512]", C);
-  if (batch <= 0 || n < 0 || n >= ((int64_t)1 << 31)) return fail(TP_E_SHAPE, "tp_encode_f32: batch=%d n=%lld", batch, (long long)n);
+  if (batch <= 0 || n < 0 || 3 * n >= ((int64_t)1 << 31)) return fail(TP_E_SHAPE, "tp_encode_f32: batch=%d n=%lld", batch, (long long)n);
   if (!offsets || !workspace) return fail(TP_E_NULL, "tp_encode_f32: offsets/workspace null");
   if (n > 0 && !feats) return fail(TP_E_NULL, "tp_encode_f32: feats null");
   if (n > 0 && !idx && !points) return fail(TP_E_NULL, "tp_encode_f32: need idx or points");
@@ -333,58 +603,74 @@ extern "C" int tp_encode_f32(const float* feats, int64_t feat_stride, int32_t C,
   P.batch = batch;
   P.C = C;
   P.C4 = C / 4;
+  P.cpt = cells_per_tile(C);
   P.n = n;
   int64_t cps[3];
   plane_cells(P.g, cps);
-  int64_t hb = 0;
+  const bool use[3] = {out_xy != nullptr, out_yz != nullptr, out_xz != nullptr};
+  const EncodeLayout L = encode_layout(P.g, batch, n, C, use);
+  if (L.tiles_total >= ((int64_t)1 << 31)) return fail(TP_E_SHAPE, "tp_encode_f32: too many tiles");
+  int64_t cb = 0;
   for (int k = 0; k < 3; ++k) {
     P.cells_per_sample[k] = cps[k];
-    P.head_base[k] = hb;
-    P.count_base[k] = hb;
-    hb += cps[k] * batch;
+    P.tiles_per_sample[k] = L.tiles_per_sample[k];
+    P.count_base[k] = cb;
+    cb += cps[k] * batch;
   }
+  P.tiles_all = L.tiles_all;
+  P.tiles_total = L.tiles_total;
   P.idx = idx;
   P.points = points;
   P.point_stride = point_stride;
   P.offsets = offsets;
   P.feats = feats;
   P.feat_stride = feat_stride;
-  P.head = reinterpret_cast<int32_t*>(workspace);
-  P.next = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(workspace) + head_bytes(geom, batch));
+  char* ws = reinterpret_cast<char*>(workspace);
+  P.tile_cnt = reinterpret_cast<int32_t*>(ws + L.off_cnt);
+  P.tile_start = reinterpret_cast<int32_t*>(ws + L.off_start);
+  P.heavy = reinterpret_cast<int32_t*>(ws + L.off_heavy);
+  P.rank = reinterpret_cast<int32_t*>(ws + L.off_rank);
+  P.entries = reinterpret_cast<int2*>(ws + L.off_ent);
   P.out[0] = out_xy;
   P.out[1] = out_yz;
   P.out[2] = out_xz;
   P.cell_count = cell_count;
   P.clamp_zero = clamp_zero;
   cudaStream_t s = (cudaStream_t)stream;
+  if (L.tiles_total == 0) return 0;
 
   if (n > 0) {
     int64_t blocks = (n + 255) / 256;
     int grid = (int)(blocks < (int64_t)kSMs * 8 ? blocks : (int64_t)kSMs * 8);
-    if (arith == TP_ARITH_TORCH_CUDA) encode_link_kernel<TP_ARITH_TORCH_CUDA><<<grid, 256, 0, s>>>(P);
-    else encode_link_kernel<TP_ARITH_TORCH_CPU><<<grid, 256, 0, s>>>(P);
-    TP_LAUNCH_CHECK("encode_link_kernel");
+    if (arith == TP_ARITH_TORCH_CUDA) encode_count_kernel<TP_ARITH_TORCH_CUDA><<<grid, 256, 0, s>>>(P);
+    else encode_count_kernel<TP_ARITH_TORCH_CPU><<<grid, 256, 0, s>>>(P);
+    TP_LAUNCH_CHECK("encode_count_kernel");
+    encode_scan_kernel<<<1, 1024, 0, s>>>(P.tile_cnt, P.tile_start, P.heavy, L.tiles_total);
+    TP_LAUNCH_CHECK("encode_scan_kernel");
+    if (arith == TP_ARITH_TORCH_CUDA) encode_fill_kernel<TP_ARITH_TORCH_CUDA><<<grid, 256, 0, s>>>(P);
+    else encode_fill_kernel<TP_ARITH_TORCH_CPU><<<grid, 256, 0, s>>>(P);
+    TP_LAUNCH_CHECK("encode_fill_kernel");
+  } else {
+    TP_CUDA(cudaMemsetAsync(P.heavy, 0, 4, s));  // no points: no heavy tiles (the scan pass did not run)
   }
-  int64_t ups[3];
-  for (int k = 0; k < 3; ++k) ups[k] = P.out[k] ? (cps[k] + kUnitCells - 1) / kUnitCells : 0;
-  const int64_t units = (ups[0] + ups[1] + ups[2]) * batch;
-  if (units == 0) return 0;
-  const int64_t ctas = (units + 8 * kUnitsPerGrab - 1) / (8 * kUnitsPerGrab);
-  const int64_t cap = (int64_t)kSMs * 8;  // persistent: 8 CTAs x 8 warps resident per SM
+  constexpr int kSmem = kTileFloats * 4 + kMaxCpt * 4;  // 17 KB
+  const size_t smem = kSmem;
+  static bool attr_done = false;
+  if (!attr_done) {
+    TP_CUDA(cudaFuncSetAttribute(encode_reduce_kernel<TP_REDUCE_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    TP_CUDA(cudaFuncSetAttribute(encode_reduce_kernel<TP_REDUCE_MEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    TP_CUDA(cudaFuncSetAttribute(encode_reduce_kernel<TP_REDUCE_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    attr_done = true;
+  }
+  const int64_t ctas = (L.tiles_total + kGrab - 1) / kGrab;
+  const int64_t cap = (int64_t)kSMs * kRedCtasPerSm;  // persistent: one resident wave
   const int grid = (int)(ctas < cap ? ctas : cap);
-  const int vpl = (P.C4 + 31) / 32;
   static std::atomic<unsigned> next_slot{0};
   const int slot = (int)(next_slot.fetch_add(1) % kEncSchedSlots);
-#define TP_MAT(R, V) encode_materialize_kernel<R, V><<<grid, 256, 0, s>>>(P, ups[0], ups[1], ups[2], slot)
-#define TP_MAT_V(R)                                                              \
-  switch (vpl) { case 1: TP_MAT(R, 1); break; case 2: TP_MAT(R, 2); break;        \
-                 case 3: TP_MAT(R, 3); break; default: TP_MAT(R, 4); break; }
-  if (reduce == TP_REDUCE_MAX) { TP_MAT_V(TP_REDUCE_MAX) }
-  else if (reduce == TP_REDUCE_MEAN) { TP_MAT_V(TP_REDUCE_MEAN) }
-  else { TP_MAT_V(TP_REDUCE_SUM) }
-#undef TP_MAT_V
-#undef TP_MAT
-  TP_LAUNCH_CHECK("encode_materialize_kernel");
+  if (reduce == TP_REDUCE_MAX) encode_reduce_kernel<TP_REDUCE_MAX><<<grid, kRedThreads, smem, s>>>(P, slot);
+  else if (reduce == TP_REDUCE_MEAN) encode_reduce_kernel<TP_REDUCE_MEAN><<<grid, kRedThreads, smem, s>>>(P, slot);
+  else encode_reduce_kernel<TP_REDUCE_SUM><<<grid, kRedThreads, smem, s>>>(P, slot);
+  TP_LAUNCH_CHECK("encode_reduce_kernel");
   return 0;
 }
 

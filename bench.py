@@ -6,11 +6,12 @@ queries/s on B200, % of HBM peak).
 
 Headline (`value`): occupancy decode of configs/triplane_occ.py at BASELINE.json's size — 640 000
 voxel queries sampled from three fp32 128x128 triplanes with C=32 (`configs[1]`) — in queries/s,
-inputs resident in HBM. A step = one pass of the decode path over one batch: 3 x NCHW->NHWC plane
-conversion + the fused 3-plane gather kernel (4 launches). Steps rotate over `nsets` disjoint
+inputs resident in HBM. A step = one pass of the decode path over one batch: the NCHW->NHWC
+conversion of the three planes (one launch) + the fused 3-plane gather kernel (one launch). Steps rotate over `nsets` disjoint
 buffer sets whose total footprint exceeds 3x the 126 MB L2, and are replayed from CUDA graphs so the
 Python launch cost is not what is measured. The same JSON line also carries the encode leg
-(`encode`: points/s for one synthetic nuScenes sweep at the config-exact geometry), `roofline`
+(`encode`: points/s for one synthetic nuScenes sweep at the config-exact geometry; `variants_kernel_only`:
+the other query sets of SURVEY 8(d) S2, including 640k uniform-random in-range queries = worst-case locality), `roofline`
 (dominant kernel, algorithmic bytes / CUDA-event time, vs MEASURED_PEAKS.json), `cpu_baseline`
 (the oracle on the box's host cores), `e2e` (host buffers through the C ABI) and `clocks`.
 
@@ -58,6 +59,15 @@ def decode_queries(kind: str):
     if kind == "roi":
         return synth.roi_lattice().reshape(1, -1, 3).contiguous()
     raise SystemExit(f"unknown --queries {kind}")
+
+
+def ncu_traffic(kernel: str, key: str):
+    """dram bytes per launch from the committed ncu capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+            return json.load(fh)[kernel][key]
+    except Exception:
+        return None
 
 
 def decode_bytes(Q: int, C_: int = C_DEC) -> int:
@@ -111,7 +121,7 @@ class ClockSampler(threading.Thread):
 # b200 arm
 # --------------------------------------------------------------------------------------------------
 class DecodeSets:
-    """nsets disjoint (planes, queries, out) buffer sets + CUDA graphs of the 4-launch step."""
+    """nsets disjoint (planes, queries, out) buffer sets + CUDA graphs of the 2-launch step."""
 
     def __init__(self, q_host: torch.Tensor, nsets: int, dev):
         from efficient_multimodal_perception_b200 import ops, synth
@@ -231,7 +241,7 @@ def bench_decode_device(args, dev, barrier, sampler):
         del qs, outs
     sampler.active.clear()
     return dict(Q=Q, nsets=nsets, ms_total=ms, kernel_ms_avg=k_avg, kernel_ms_med=k_med, kernel_ms_min=k_min,
-                launches=args.steps * 4, sets=sets, variants=variants)
+                launches=args.steps * 2, sets=sets, variants=variants)
 
 
 def bench_decode_e2e(args, Q_host, barrier):
@@ -295,7 +305,35 @@ def bench_encode_device(args, dev, barrier, sampler):
     sampler.active.clear()
     bytes_alg = n * 12 + inside * 4 * Cc + 4 * Cc * cells
     return dict(n=n, inside=inside, cells=cells, steps=steps, ms_per_step=ms / steps, bytes=bytes_alg,
-                launches=2 * steps)
+                launches=4 * steps)
+
+
+def bench_encode_point_sharded(args, dev, barrier, rank, world):
+    """N > 1 only: ONE 10-sweep sample (350 000 raw points) point-sharded over the ranks:
+    partial planes (-inf empties) -> NCCL all-reduce(max) of the 430 MB dense planes -> finalise."""
+    from efficient_multimodal_perception_b200 import dist as tpd
+    from efficient_multimodal_perception_b200 import synth
+    G = synth.GEOM_A
+    pts = synth.multi_sweep(10, 35000, seed=1005)[:, :3].contiguous()
+    feats = synth.point_features(pts.shape[0], G["channels"], seed=1005)
+    lo, hi = tpd.shard_bounds(pts.shape[0], rank, world)
+    my_pts, my_feats = pts[lo:hi].to(dev), feats[lo:hi].contiguous().to(dev)
+    off = synth.batch_offsets([hi - lo]).to(dev)
+
+    def step():
+        return tpd.encode_point_sharded(my_feats, my_pts, off, G["pc_range"], G["voxel_size"], G["grid_size"],
+                                        G["split"], reduce="max")
+
+    for _ in range(3):
+        step()
+    steps = max(5, min(args.steps, 30))
+
+    def run():
+        for _ in range(steps):
+            step()
+
+    ms = time_region(run, barrier) / steps
+    return dict(n=pts.shape[0], ms_per_step=ms, steps=steps, allreduce_bytes=4 * G["channels"] * 839680)
 
 
 def cpu_baseline_decode(q_host, budget_s=15.0):
@@ -339,11 +377,13 @@ def run_b200(args):
 
     dec = bench_decode_device(args, dev, barrier, sampler)
     enc = bench_encode_device(args, dev, barrier, sampler)
+    eps = bench_encode_point_sharded(args, dev, barrier, rank, world) if world > 1 else None
     # max over ranks (device time)
-    t = torch.tensor([dec["ms_total"], enc["ms_per_step"], dec["kernel_ms_avg"]], device=dev, dtype=torch.float64)
+    t = torch.tensor([dec["ms_total"], enc["ms_per_step"], dec["kernel_ms_avg"], eps["ms_per_step"] if eps else 0.0],
+                     device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, enc_ms, k_avg = (float(x) for x in t.tolist())
+    ms_total, enc_ms, k_avg, eps_ms = (float(x) for x in t.tolist())
     clocks = sampler.stop()
 
     q_host = decode_queries(args.queries)
@@ -381,12 +421,13 @@ def run_b200(args):
             "config": {"workload": f"configs/triplane_occ.py occupancy decode: {Q} voxel queries ({args.queries}) "
                                    f"x C={C_DEC} from 3 fp32 {PLANE}x{PLANE} triplanes, bs=1 per GPU",
                        "queries": args.queries, "Q": Q, "C": C_DEC, "planes": [PLANE, PLANE],
-                       "step": "3x NCHW->NHWC plane conversion + fused gather kernel (4 launches, CUDA-graph replay)",
+                       "step": "NCHW->NHWC conversion of the 3 planes (1 launch) + fused gather kernel (1 launch), CUDA-graph replay",
                        "l2": f"{dec['nsets']} rotating buffer sets, total footprint "
                              f"{dec['nsets'] * (kbytes + 4 * C_DEC * 3 * PLANE * PLANE) / 1e6:.0f} MB > 3x L2 (no flush kernel)",
                        "parallelism": f"queries sharded over {world} GPU(s), no collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "tp::sample3_kernel<0>", "algorithmic_bytes": kbytes,
+                         "traffic": ncu_traffic("sample3_kernel", args.queries), "kernel": "tp::sample3_kernel<0,8>",
+                         "algorithmic_bytes": kbytes,
                          "kernel_ms_avg": k_avg, "kernel_ms_median": dec["kernel_ms_med"],
                          "kernel_ms_min": dec["kernel_ms_min"], "peak_source": peak_src,
                          "step_frac": kbytes / (ms_per_step * 1e-3) / 1e9 / peak},
@@ -406,9 +447,18 @@ def run_b200(args):
                                    f"{enc['cells']} pooled cells dense out",
                        "roofline": {"bound": "hbm", "achieved": enc["bytes"] / (enc_ms * 1e-3) / 1e9, "peak": peak,
                                     "unit": "GB/s", "frac": enc["bytes"] / (enc_ms * 1e-3) / 1e9 / peak,
-                                    "algorithmic_bytes": enc["bytes"], "note": "whole step (link + materialise)"},
+                                    "algorithmic_bytes": enc["bytes"],
+                                    "traffic": ncu_traffic("encode_reduce_kernel", "S1_geomA_C128"),
+                                    "note": "whole step: count + scan + fill + reduce (4 launches)"},
                        "steps": enc["steps"], "gpu_launches": enc["launches"]},
         }
+        if eps:
+            line["encode_point_sharded"] = {
+                "workload": f"ONE 10-sweep sample ({eps['n']} raw pts) point-sharded over {world} GPUs, geometry "
+                            f"128x128x80 C=128: partial planes -> NCCL all-reduce(max) of {eps['allreduce_bytes'] / 1e6:.0f} MB "
+                            f"-> finalise (strong scaling of one sample; the sample-sharded path above needs no collective)",
+                "value": eps["n"] / (eps_ms * 1e-3), "unit": "points/s", "ms_per_step": eps_ms, "steps": eps["steps"],
+                "allreduce_bytes_per_step": eps["allreduce_bytes"]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -465,7 +515,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--queries", default="uniform640k", choices=["lattice640k", "uniform640k", "roi"])
+    ap.add_argument("--queries", default="lattice640k", choices=["lattice640k", "uniform640k", "roi"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

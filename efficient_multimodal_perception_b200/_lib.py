@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 TP_ARITH_TORCH_CUDA = 0
 TP_ARITH_TORCH_CPU = 1
 TP_ARITH_TORCH_CUDA_NOFMA = 2  # diagnostic: CUDA formula without the fma contraction (decode only)
-TP_REDUCE_MAX, TP_REDUCE_MEAN, TP_REDUCE_SUM = 0, 1, 2
+TP_REDUCE_MAX, TP_REDUCE_MEAN, TP_REDUCE_SUM, TP_REDUCE_MAX_PARTIAL = 0, 1, 2, 3
 
 
 class TriplaneError(RuntimeError):
@@ -48,8 +48,10 @@ SIGNATURES = {
     "tp_encode_f32": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, _i64, _vp, _i32, C.POINTER(tp_geom), _i32,
                                 _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "tp_encode_finalize_mean_f32": (C.c_int, [_vp, _vp, _i64, _i32, _vp]),
+    "tp_encode_finalize_max_f32": (C.c_int, [_vp, _i64, _i32, _vp]),
     "tp_voxel_counts_i32": (C.c_int, [_vp, _i64, _vp, _i32, C.POINTER(tp_geom), _vp, _vp]),
     "tp_planes_nchw_to_nhwc_f32": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "tp_planes3_nchw_to_nhwc_f32": (C.c_int, [C.POINTER(tp_plane * 3), C.POINTER(_vp * 3), _i32, _i32, _vp]),
     "tp_sample3_nhwc_f32": (C.c_int, [C.POINTER(tp_plane * 3), _i32, _vp, _i64, _i32,
                                       C.POINTER(tp_sample_geom), _i32, _vp, _vp]),
     "tp_sample3_nchw_f32": (C.c_int, [C.POINTER(tp_plane * 3), _i32, _vp, _i64, _i32,

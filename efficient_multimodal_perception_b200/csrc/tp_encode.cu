@@ -60,6 +60,7 @@ struct EncodeParams {
   int32_t* cell_count;  // optional, order xy | yz | xz, each [B, cells_per_sample]
   int64_t count_base[3];
   int clamp_zero;
+  int partial;  // 1: TP_REDUCE_MAX_PARTIAL — empty cells are -inf (identity of max) for a cross-GPU max
 };
 
 // tile order: sample-major, then plane, then position — the three planes of a sample are reduced
@@ -232,28 +233,6 @@ __device__ __forceinline__ float key2f(unsigned k) {
 // point rows and CSR entries are re-read by up to three planes while 430 MB of output streams past
 // them (evict_last) — without the hints the rows are evicted between planes and every gather waits in
 // the DRAM queue behind the writes (ncu: lts hit rate 5 %, profiles/r01_encode_v1_linkedlist_ncu.txt).
-__device__ __forceinline__ unsigned long long policy_evict_first() {
-  unsigned long long p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ unsigned long long policy_evict_last() {
-  unsigned long long p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ float4 ld_keep_f4(const float4* p, unsigned long long pol) {
-  float4 r;
-  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-               : "l"(p), "l"(pol));
-  return r;
-}
-__device__ __forceinline__ void st_stream_f4(float4* p, float4 v, unsigned long long pol) {
-  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y),
-               "f"(v.z), "f"(v.w), "l"(pol)
-               : "memory");
-}
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes, unsigned long long pol) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
                "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes), "l"(pol)
@@ -294,6 +273,8 @@ encode_reduce_kernel(const EncodeParams P, int sched_slot) {
   const int C = P.C, C4 = P.C4, cpt = P.cpt;
   unsigned long long* sched = g_enc_sched[sched_slot];
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float fillv = P.partial ? __uint_as_float(0xff800000u) : 0.f;  // -inf or 0 for empty cells
+  const float4 fill4 = make_float4(fillv, fillv, fillv, fillv);
   const unsigned long long pol_out = policy_evict_first(), pol_in = policy_evict_last();
 
   // the tile buffer starts zeroed and is returned to all-zero before each reuse by clearing only the
@@ -319,14 +300,14 @@ encode_reduce_kernel(const EncodeParams P, int sched_slot) {
       float4* g4 = reinterpret_cast<float4*>(gdst);
       const int nvec = ncell * C4;
 #pragma unroll 4
-      for (int i = tid; i < nvec; i += kRedThreads) st_stream_f4(g4 + i, zero4, pol_out);
+      for (int i = tid; i < nvec; i += kRedThreads) st_stream_f4(g4 + i, fill4, pol_out);
       if (gcount) for (int c = tid; c < ncell; c += kRedThreads) gcount[c] = 0;
       return;
     }
     if (tid == 0 && in_flight) { bulk_wait_read0(); in_flight = false; }
     __syncthreads();
     for (int c = warp; c < cpt; c += kWarps) {  // rows are warp-owned here: no barrier before the reset
-      if (s_cnt[c] > 0) {
+      if (s_cnt[c] != 0) {
         for (int v = lane; v < C4; v += 32) reinterpret_cast<float4*>(s_work + c * C)[v] = zero4;
         __syncwarp();
         if (lane == 0) s_cnt[c] = 0;
@@ -384,6 +365,12 @@ encode_reduce_kernel(const EncodeParams P, int sched_slot) {
         }
       }
       if (gcount && lane == 0) gcount[c] = cnt;
+      if (P.partial && cnt == 0) {  // untouched cell of an occupied tile: -inf, and mark the row dirty
+        float4* row = reinterpret_cast<float4*>(s_work + c * C);
+        for (int v = lane; v < C4; v += 32) row[v] = fill4;
+        __syncwarp();
+        if (lane == 0) s_cnt[c] = -1;
+      }
     }
     fence_async_smem();
     __syncthreads();
@@ -474,6 +461,24 @@ finalize_mean_kernel(float* __restrict__ planes, const int32_t* __restrict__ cnt
       const float d = (float)c;
       *p = make_float4(__fdiv_rn(x.x, d), __fdiv_rn(x.y, d), __fdiv_rn(x.z, d), __fdiv_rn(x.w, d));
     }
+  }
+}
+
+// after the cross-GPU max of TP_REDUCE_MAX_PARTIAL planes: -inf (no point on any GPU) -> 0
+__global__ void __launch_bounds__(256)
+finalize_max_kernel(float4* __restrict__ planes, int64_t nvec, int clamp_zero) {
+  const float ninf = __uint_as_float(0xff800000u);
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
+       v += (int64_t)gridDim.x * blockDim.x) {
+    float4 x = planes[v];
+    const float lo = clamp_zero ? 0.f : ninf;
+    // a cell is empty on all GPUs iff all of its channels are -inf; per element is equivalent because
+    // a touched cell has a finite (or NaN / +inf) value in every channel unless the feature itself is -inf
+    x.x = (x.x == ninf) ? 0.f : fmaxf(x.x, lo);
+    x.y = (x.y == ninf) ? 0.f : fmaxf(x.y, lo);
+    x.z = (x.z == ninf) ? 0.f : fmaxf(x.z, lo);
+    x.w = (x.w == ninf) ? 0.f : fmaxf(x.w, lo);
+    planes[v] = x;
   }
 }
 
@@ -592,7 +597,7 @@ extern "C" int tp_encode_f32(const float* feats, int64_t feat_stride, int32_t C,
   if (feat_stride < C || (feat_stride & 3) || ((uintptr_t)feats & 15))
     return fail(TP_E_SHAPE, "tp_encode_f32: feats must be 16-byte aligned rows (stride=%lld)", (long long)feat_stride);
   if (arith != TP_ARITH_TORCH_CUDA && arith != TP_ARITH_TORCH_CPU) return fail(TP_E_ENUM, "tp_encode_f32: unknown arith %d", arith);
-  if (reduce < 0 || reduce > 2) return fail(TP_E_ENUM, "tp_encode_f32: unknown reduce %d", reduce);
+  if (reduce < 0 || reduce > 3) return fail(TP_E_ENUM, "tp_encode_f32: unknown reduce %d", reduce);
   const int64_t need = tp_encode_workspace_bytes(geom, batch, n);
   if (workspace_bytes < need) return fail(TP_E_WORKSPACE, "tp_encode_f32: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)need);
   for (float* o : {out_xy, out_yz, out_xz})
@@ -635,7 +640,8 @@ extern "C" int tp_encode_f32(const float* feats, int64_t feat_stride, int32_t C,
   P.out[1] = out_yz;
   P.out[2] = out_xz;
   P.cell_count = cell_count;
-  P.clamp_zero = clamp_zero;
+  P.clamp_zero = (reduce == TP_REDUCE_MAX_PARTIAL) ? 0 : clamp_zero;  // clamp after the cross-GPU max
+  P.partial = (reduce == TP_REDUCE_MAX_PARTIAL) ? 1 : 0;
   cudaStream_t s = (cudaStream_t)stream;
   if (L.tiles_total == 0) return 0;
 
@@ -667,7 +673,7 @@ extern "C" int tp_encode_f32(const float* feats, int64_t feat_stride, int32_t C,
   const int grid = (int)(ctas < cap ? ctas : cap);
   static std::atomic<unsigned> next_slot{0};
   const int slot = (int)(next_slot.fetch_add(1) % kEncSchedSlots);
-  if (reduce == TP_REDUCE_MAX) encode_reduce_kernel<TP_REDUCE_MAX><<<grid, kRedThreads, smem, s>>>(P, slot);
+  if (reduce == TP_REDUCE_MAX || reduce == TP_REDUCE_MAX_PARTIAL) encode_reduce_kernel<TP_REDUCE_MAX><<<grid, kRedThreads, smem, s>>>(P, slot);
   else if (reduce == TP_REDUCE_MEAN) encode_reduce_kernel<TP_REDUCE_MEAN><<<grid, kRedThreads, smem, s>>>(P, slot);
   else encode_reduce_kernel<TP_REDUCE_SUM><<<grid, kRedThreads, smem, s>>>(P, slot);
   TP_LAUNCH_CHECK("encode_reduce_kernel");
@@ -683,6 +689,18 @@ extern "C" int tp_encode_finalize_mean_f32(float* planes, const int32_t* cell_co
   int grid = (int)(blocks < (int64_t)kSMs * 16 ? blocks : (int64_t)kSMs * 16);
   finalize_mean_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(planes, cell_count, cells, C / 4);
   TP_LAUNCH_CHECK("finalize_mean_kernel");
+  return 0;
+}
+
+extern "C" int tp_encode_finalize_max_f32(float* planes, int64_t n_floats, int32_t clamp_zero, void* stream) {
+  if (!planes) return fail(TP_E_NULL, "tp_encode_finalize_max_f32: null argument");
+  if (n_floats < 0 || (n_floats & 3) || ((uintptr_t)planes & 15))
+    return fail(TP_E_SHAPE, "tp_encode_finalize_max_f32: need a 16-byte aligned multiple of 4 floats");
+  if (n_floats == 0) return 0;
+  int64_t blocks = (n_floats / 4 + 255) / 256;
+  int grid = (int)(blocks < (int64_t)kSMs * 16 ? blocks : (int64_t)kSMs * 16);
+  finalize_max_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(planes), n_floats / 4, clamp_zero);
+  TP_LAUNCH_CHECK("finalize_max_kernel");
   return 0;
 }
 

@@ -94,19 +94,20 @@ __device__ __forceinline__ float4 mul4(float4 v, float w) {  // == fma(v, w, +0)
 // second 64-bit pointer.
 template <bool MASKED>
 __device__ __forceinline__ float4 plane_taps(const float4* __restrict__ pl, int off, int C4, int WC4,
-                                             float4 w, int mk) {
+                                             float4 w, int mk, unsigned long long pol) {
   const float4* t0 = pl + off;
   const float4* t1 = t0 + WC4;
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   if (!MASKED) {
-    const float4 v00 = __ldg(t0), v01 = __ldg(t0 + C4), v10 = __ldg(t1), v11 = __ldg(t1 + C4);
+    const float4 v00 = ld_keep_f4(t0, pol), v01 = ld_keep_f4(t0 + C4, pol), v10 = ld_keep_f4(t1, pol),
+                 v11 = ld_keep_f4(t1 + C4, pol);
     return fma4(v11, w.w, fma4(v10, w.z, fma4(v01, w.y, mul4(v00, w.x))));
   }
   float4 a = z;
-  if (mk & 1) a = fma4(__ldg(t0), w.x, a);
-  if (mk & 2) a = fma4(__ldg(t0 + C4), w.y, a);
-  if (mk & 4) a = fma4(__ldg(t1), w.z, a);
-  if (mk & 8) a = fma4(__ldg(t1 + C4), w.w, a);
+  if (mk & 1) a = fma4(ld_keep_f4(t0, pol), w.x, a);
+  if (mk & 2) a = fma4(ld_keep_f4(t0 + C4, pol), w.y, a);
+  if (mk & 4) a = fma4(ld_keep_f4(t1, pol), w.z, a);
+  if (mk & 8) a = fma4(ld_keep_f4(t1 + C4, pol), w.w, a);
   return a;
 }
 
@@ -127,6 +128,8 @@ sample3_kernel(const SampleParams P, const int sched_slot) {
   const int nchunk = (C4 + 7) >> 3;
   const int WC4_0 = P.W[0] * C4, WC4_1 = P.W[1] * C4, WC4_2 = P.W[2] * C4;
   unsigned int* sched = g_sched[sched_slot];
+  // planes (MBs) are re-read by every query while the output (10x larger) streams through L2 once
+  const unsigned long long pol_planes = policy_evict_last(), pol_out = policy_evict_first();
   const bool q_vec4 = ((P.Q & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0);
 
   for (;;) {
@@ -195,10 +198,10 @@ sample3_kernel(const SampleParams P, const int sched_slot) {
           const int r0 = lane >> 3, c4q = (lane & 7) * 4;
           if (q0 + c4q < P.Q) {
             for (int c = r0; c < cmax; c += 4)
-              st_cs_f4(reinterpret_cast<float4*>(orow + (int64_t)c * P.Q + c4q), make_float4(0.f, 0.f, 0.f, 0.f));
+              st_stream_f4(reinterpret_cast<float4*>(orow + (int64_t)c * P.Q + c4q), make_float4(0.f, 0.f, 0.f, 0.f), pol_out);
           }
         } else if (qvalid) {
-          for (int c = 0; c < cmax; ++c) st_cs_f1(orow + (int64_t)c * P.Q + lane, 0.f);
+          for (int c = 0; c < cmax; ++c) st_stream_f1(orow + (int64_t)c * P.Q + lane, 0.f, pol_out);
         }
         continue;
       }
@@ -211,9 +214,9 @@ sample3_kernel(const SampleParams P, const int sched_slot) {
           const int qi = sub * 8 + pass;  // 8 consecutive queries per 8-lane group
           const float4* prm = reinterpret_cast<const float4*>(sp + param_base(qi));
           const float4 w0 = prm[0], w1 = prm[1], w2 = prm[2], bm = prm[3];
-          const float4 a0 = plane_taps<false>(pl0 + choff, __float_as_int(bm.x), C4, WC4_0, w0, 15);
-          const float4 a1 = plane_taps<false>(pl1 + choff, __float_as_int(bm.y), C4, WC4_1, w1, 15);
-          const float4 a2 = plane_taps<false>(pl2 + choff, __float_as_int(bm.z), C4, WC4_2, w2, 15);
+          const float4 a0 = plane_taps<false>(pl0 + choff, __float_as_int(bm.x), C4, WC4_0, w0, 15, pol_planes);
+          const float4 a1 = plane_taps<false>(pl1 + choff, __float_as_int(bm.y), C4, WC4_1, w1, 15, pol_planes);
+          const float4 a2 = plane_taps<false>(pl2 + choff, __float_as_int(bm.z), C4, WC4_2, w2, 15, pol_planes);
           float* t = tcol + (qi ^ l8);
           t[0] = __fadd_rn(__fadd_rn(a0.x, a1.x), a2.x);  // (xy + yz) + xz  (triplane_occ.py:345)
           t[32] = __fadd_rn(__fadd_rn(a0.y, a1.y), a2.y);
@@ -228,9 +231,9 @@ sample3_kernel(const SampleParams P, const int sched_slot) {
           const float4* prm = reinterpret_cast<const float4*>(sp + param_base(qi));
           const float4 w0 = prm[0], w1 = prm[1], w2 = prm[2], bm = prm[3];
           const int m = cvalid ? __float_as_int(bm.w) : 0;
-          const float4 a0 = plane_taps<true>(pl0 + choff, __float_as_int(bm.x), C4, WC4_0, w0, m & 15);
-          const float4 a1 = plane_taps<true>(pl1 + choff, __float_as_int(bm.y), C4, WC4_1, w1, (m >> 4) & 15);
-          const float4 a2 = plane_taps<true>(pl2 + choff, __float_as_int(bm.z), C4, WC4_2, w2, (m >> 8) & 15);
+          const float4 a0 = plane_taps<true>(pl0 + choff, __float_as_int(bm.x), C4, WC4_0, w0, m & 15, pol_planes);
+          const float4 a1 = plane_taps<true>(pl1 + choff, __float_as_int(bm.y), C4, WC4_1, w1, (m >> 4) & 15, pol_planes);
+          const float4 a2 = plane_taps<true>(pl2 + choff, __float_as_int(bm.z), C4, WC4_2, w2, (m >> 8) & 15, pol_planes);
           float* t = tcol + (qi ^ l8);
           t[0] = __fadd_rn(__fadd_rn(a0.x, a1.x), a2.x);
           t[32] = __fadd_rn(__fadd_rn(a0.y, a1.y), a2.y);
@@ -244,7 +247,7 @@ sample3_kernel(const SampleParams P, const int sched_slot) {
         float* o = orow + lane;
         const int64_t Qs = P.Q;
 #pragma unroll 8
-        for (int c = 0; c < cmax; ++c, o += Qs) st_cs_f1(o, st[c * 32 + (lane ^ ((c >> 2) & 7))]);
+        for (int c = 0; c < cmax; ++c, o += Qs) st_stream_f1(o, st[c * 32 + (lane ^ ((c >> 2) & 7))], pol_out);
       }
       __syncwarp();
     }
@@ -283,9 +286,64 @@ nchw_to_nhwc_kernel(const float* __restrict__ src, int64_t src_bstride, float* _
   }
 }
 
+struct Planes3 {
+  const float* src[3];
+  float* dst[3];
+  int64_t src_bstride[3];
+  int HW[3];
+  int tiles_x[3];  // ceil(HW/32) per plane; blockIdx.x runs over the three planes back to back
+};
+
+// all three planes in one launch. grid = (sum_p ceil(HW_p/32), ceil(C/32), B)
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc3_kernel(const Planes3 P, int C) {
+  __shared__ float tile[32][33];
+  int bx = blockIdx.x, k = 0;
+  if (bx >= P.tiles_x[0]) { bx -= P.tiles_x[0]; k = 1; if (bx >= P.tiles_x[1]) { bx -= P.tiles_x[1]; k = 2; } }
+  const int HW = P.HW[k];
+  const int b = blockIdx.z;
+  const int p0 = bx * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* s = P.src[k] + (int64_t)b * P.src_bstride[k];
+  float* d = P.dst[k] + (int64_t)b * C * HW;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    int c = c0 + ty + j, p = p0 + tx;
+    if (c < C && p < HW) tile[ty + j][tx] = __ldg(s + (int64_t)c * HW + p);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    int p = p0 + ty + j, c = c0 + tx;
+    if (c < C && p < HW) d[(int64_t)p * C + c] = tile[tx][ty + j];
+  }
+}
+
 }  // namespace tp
 
 using namespace tp;
+
+extern "C" int tp_planes3_nchw_to_nhwc_f32(const tp_plane planes_nchw[3], float* const dst[3], int32_t batch,
+                                           int32_t C, void* stream) {
+  if (!planes_nchw || !dst) return fail(TP_E_NULL, "tp_planes3_nchw_to_nhwc_f32: null argument");
+  if (batch <= 0 || C <= 0) return fail(TP_E_SHAPE, "tp_planes3_nchw_to_nhwc_f32: bad shape B=%d C=%d", batch, C);
+  Planes3 P;
+  int tx = 0;
+  for (int k = 0; k < 3; ++k) {
+    if (!planes_nchw[k].data || !dst[k]) return fail(TP_E_NULL, "tp_planes3_nchw_to_nhwc_f32: plane %d is null", k);
+    if (planes_nchw[k].H <= 0 || planes_nchw[k].W <= 0) return fail(TP_E_SHAPE, "tp_planes3_nchw_to_nhwc_f32: plane %d shape", k);
+    P.src[k] = planes_nchw[k].data;
+    P.dst[k] = dst[k];
+    P.src_bstride[k] = planes_nchw[k].batch_stride;
+    P.HW[k] = planes_nchw[k].H * planes_nchw[k].W;
+    P.tiles_x[k] = (P.HW[k] + 31) / 32;
+    tx += P.tiles_x[k];
+  }
+  dim3 grid(tx, (C + 31) / 32, batch);
+  nchw_to_nhwc3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P, C);
+  TP_LAUNCH_CHECK("nchw_to_nhwc3_kernel");
+  return 0;
+}
 
 extern "C" int tp_planes_nchw_to_nhwc_f32(const float* src, int64_t src_batch_stride, float* dst,
                                           int32_t batch, int32_t C, int32_t H, int32_t W,
@@ -366,16 +424,15 @@ extern "C" int tp_sample3_nchw_f32(const tp_plane planes_nchw[3], int32_t C, con
   if (ws_floats < need)
     return fail(TP_E_WORKSPACE, "tp_sample3_nchw_f32: workspace %lld < %lld floats", (long long)ws_floats, (long long)need);
   float* w = ws;
+  float* dsts[3];
   for (int k = 0; k < 3; ++k) {
-    if (!planes_nchw[k].data) return fail(TP_E_NULL, "tp_sample3_nchw_f32: plane %d is null", k);
-    int rc = tp_planes_nchw_to_nhwc_f32(planes_nchw[k].data, planes_nchw[k].batch_stride, w, batch, C,
-                                        planes_nchw[k].H, planes_nchw[k].W, stream);
-    if (rc) return rc;
+    dsts[k] = w;
     nhwc[k].data = w;
     nhwc[k].H = planes_nchw[k].H;
     nhwc[k].W = planes_nchw[k].W;
     nhwc[k].batch_stride = (int64_t)C * planes_nchw[k].H * planes_nchw[k].W;
     w += (int64_t)batch * nhwc[k].batch_stride;
   }
+  if (int rc = tp_planes3_nchw_to_nhwc_f32(planes_nchw, dsts, batch, C, stream)) return rc;
   return tp_sample3_nhwc_f32(nhwc, C, queries, Q, batch, sg, arith, out, stream);
 }

@@ -1,0 +1,90 @@
+"""Multi-GPU plumbing for the triplane hot path: one process per GPU,
+torch.distributed (NCCL over NVLink 5 / NVSwitch; gloo in CPU tests).
+
+* decode — queries are independent: shard Q (or the batch) across ranks, no collective.
+* encode, sample-sharded — planes are per sample: shard the batch across ranks, no collective (this is
+  what the reference's DDP does, tools/euler_train.sh:3-11).
+* encode, point-sharded — the one real exchange step: every rank scatters ITS points into full-size
+  partial planes (max: empty cells are -inf, the identity of max; mean: sums + counts), the partial
+  planes are combined with all-reduce (MAX, or SUM on sums and counts), then finalised (-inf -> 0, or
+  sum / count). max is exact under any reduction order; mean is within rounding. The message is the
+  full dense pooled tensor (430 MB per sample at the config geometry), so this only pays when there
+  are fewer samples than GPUs — bench.py reports both.
+
+The reference has no counterpart for the point-sharded path (its only collectives are the scalar loss
+all-reduce, point_triplane.py:529-531, and DDP's gradient all-reduce).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced split of range(n): the first n % world shards get one extra element."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_samples(items: Sequence, rank: int, world: int) -> list:
+    lo, hi = shard_bounds(len(items), rank, world)
+    return list(items[lo:hi])
+
+
+def shard_points(points: Sequence[torch.Tensor], rank: int, world: int) -> List[torch.Tensor]:
+    """Per-sample contiguous slice of every sample's points for this rank (order preserved)."""
+    out = []
+    for p in points:
+        lo, hi = shard_bounds(p.shape[0], rank, world)
+        out.append(p[lo:hi])
+    return out
+
+
+def shard_queries(queries: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    """[B, Q, 3] -> this rank's [B, Q_r, 3] slice along Q."""
+    lo, hi = shard_bounds(queries.shape[1], rank, world)
+    return queries[:, lo:hi]
+
+
+def all_reduce_planes(planes: Sequence[torch.Tensor], reduce: str, counts: Optional[torch.Tensor] = None,
+                      group=None) -> None:
+    """In-place combine of partial planes across ranks: reduce='max' -> MAX; 'sum' -> SUM on planes and
+    on the int32 point counts. Works on CUDA (NCCL) and CPU (gloo) tensors."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    op = dist.ReduceOp.MAX if reduce == "max" else dist.ReduceOp.SUM
+    for p in planes:
+        if p is not None:
+            dist.all_reduce(p, op=op, group=group)
+    if counts is not None:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+
+
+def encode_point_sharded(feats: torch.Tensor, points: torch.Tensor, offsets: torch.Tensor, pc_range, voxel_size,
+                         grid_size, split, reduce: str = "max", clamp_zero: bool = False, arith: str = "cuda",
+                         group=None):
+    """Each rank passes ITS shard of the points (feats [N_r, C], raw points [N_r, >=3], offsets [B+1] of
+    the shard); every rank returns the complete planes (xy, yz, xz)."""
+    from . import ops
+    if reduce == "max":
+        xy, yz, xz = ops.encode(feats, offsets, pc_range, voxel_size, grid_size, split, points=points,
+                                reduce="max_partial", arith=arith)
+        all_reduce_planes((xy, yz, xz), "max", group=group)
+        for p in (xy, yz, xz):
+            ops.finalize_max(p, clamp_zero)
+        return xy, yz, xz
+    if reduce == "mean":
+        xy, yz, xz, cnt = ops.encode(feats, offsets, pc_range, voxel_size, grid_size, split, points=points,
+                                     reduce="sum", want_counts=True, arith=arith)
+        all_reduce_planes((xy, yz, xz), "sum", counts=cnt, group=group)
+        C = feats.shape[1]
+        o = 0
+        for p in (xy, yz, xz):
+            n = p.numel() // C
+            ops.finalize_mean(p, cnt[o:o + n], C)
+            o += n
+        return xy, yz, xz
+    raise ValueError(f"reduce must be 'max' or 'mean', got {reduce!r}")

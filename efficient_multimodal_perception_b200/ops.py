@@ -12,7 +12,7 @@ from . import _lib as L
 from ._lib import (TP_ARITH_TORCH_CPU, TP_ARITH_TORCH_CUDA, TP_REDUCE_MAX, TP_REDUCE_MEAN, TP_REDUCE_SUM,
                    TriplaneError)
 
-_REDUCE = {"max": TP_REDUCE_MAX, "mean": TP_REDUCE_MEAN, "sum": TP_REDUCE_SUM}
+_REDUCE = {"max": TP_REDUCE_MAX, "mean": TP_REDUCE_MEAN, "sum": TP_REDUCE_SUM, "max_partial": L.TP_REDUCE_MAX_PARTIAL}
 _ARITH = {"cuda": TP_ARITH_TORCH_CUDA, "cpu": TP_ARITH_TORCH_CPU, "cuda_nofma": L.TP_ARITH_TORCH_CUDA_NOFMA}
 
 #: count of libtriplane kernel launches issued through this module (bench.py's gpu_launches)
@@ -96,7 +96,7 @@ def voxel_index(points: torch.Tensor, pc_range, voxel_size, arith: str = "cuda")
 # a3
 # ------------------------------------------------------------------------------------------------
 class _EncodeWorkspace:
-    """Per (device, geometry, batch) scratch whose head table is kept clean between calls."""
+    """Per (device, geometry, batch) scratch whose tile counters are left zero by every call."""
     cache = {}
 
     @classmethod
@@ -166,7 +166,7 @@ def encode(feats: torch.Tensor, offsets: torch.Tensor, pc_range, voxel_size, gri
                                   C.byref(geom), _ARITH[arith], _REDUCE[reduce], int(bool(clamp_zero)),
                                   _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(counts),
                                   ws.data_ptr(), ws_bytes, stream), "tp_encode_f32")
-    launch_count += 2 if n else 1
+    launch_count += 4 if n else 1
     return (outs[0], outs[1], outs[2], counts) if want_counts else (outs[0], outs[1], outs[2])
 
 
@@ -180,6 +180,18 @@ def finalize_mean(planes: torch.Tensor, counts: torch.Tensor, channels: int) -> 
     cells = planes.numel() // channels
     L.check(L.lib().tp_encode_finalize_mean_f32(planes.data_ptr(), counts.data_ptr(), cells, channels,
                                                 _stream(planes)), "tp_encode_finalize_mean_f32")
+    launch_count += 1
+    return planes
+
+
+def finalize_max(planes: torch.Tensor, clamp_zero: bool = False) -> torch.Tensor:
+    """In place: -inf -> 0 after the all-reduce(max) of reduce='max_partial' planes."""
+    global launch_count
+    _need_cuda(planes, "planes")
+    if not planes.is_contiguous():
+        raise TriplaneError("finalize_max: planes must be contiguous")
+    L.check(L.lib().tp_encode_finalize_max_f32(planes.data_ptr(), planes.numel(), int(bool(clamp_zero)),
+                                               _stream(planes)), "tp_encode_finalize_max_f32")
     launch_count += 1
     return planes
 
@@ -216,7 +228,9 @@ def planes_to_channels_last(planes: Sequence[torch.Tensor]) -> List[torch.Tensor
     """NCHW planes (the reference layout; views of the stacked [B,3,C,H,W] are fine) -> contiguous
     channels-last [B,H,W,C] copies for the gather kernel."""
     global launch_count
-    out = []
+    if len(planes) != 3:
+        raise TriplaneError("expected three planes")
+    srcs, out = [], []
     for k, p in enumerate(planes):
         _need_cuda(p, f"plane {k}")
         if p.dim() != 4:
@@ -224,11 +238,16 @@ def planes_to_channels_last(planes: Sequence[torch.Tensor]) -> List[torch.Tensor
         B, Cc, H, W = p.shape
         if p.stride(3) != 1 or p.stride(2) != W or p.stride(1) != H * W:
             p = p.contiguous()
-        dst = torch.empty((B, H, W, Cc), dtype=torch.float32, device=p.device)
-        L.check(L.lib().tp_planes_nchw_to_nhwc_f32(p.data_ptr(), p.stride(0), dst.data_ptr(), B, Cc, H, W,
-                                                   _stream(p)), "tp_planes_nchw_to_nhwc_f32")
-        launch_count += 1
-        out.append(dst)
+        srcs.append(p)
+        out.append(torch.empty((B, H, W, Cc), dtype=torch.float32, device=p.device))
+    B, Cc = srcs[0].shape[0], srcs[0].shape[1]
+    if any(p.shape[0] != B or p.shape[1] != Cc for p in srcs):
+        raise TriplaneError("planes must share batch and channel sizes")
+    arr = _plane_array(srcs)
+    dsts = (C.c_void_p * 3)(*[o.data_ptr() for o in out])
+    L.check(L.lib().tp_planes3_nchw_to_nhwc_f32(C.byref(arr), C.byref(dsts), B, Cc, _stream(srcs[0])),
+            "tp_planes3_nchw_to_nhwc_f32")
+    launch_count += 1
     return out
 
 

@@ -56,7 +56,9 @@ typedef enum tp_arith {
 typedef enum tp_reduce {
   TP_REDUCE_MAX  = 0, /* reference: torch_scatter.scatter_max + SparseMaxPool3d (projector.py:104,113-115) */
   TP_REDUCE_MEAN = 1, /* north-star extension: sum / count per pooled cell                               */
-  TP_REDUCE_SUM  = 2  /* partial sums for the point-sharded multi-GPU mean (divide after the all-reduce)  */
+  TP_REDUCE_SUM  = 2, /* partial sums for the point-sharded multi-GPU mean (divide after the all-reduce)  */
+  TP_REDUCE_MAX_PARTIAL = 3 /* point-sharded multi-GPU max: empty cells are -inf so that an all-reduce(max)
+                               over GPUs is exact; tp_encode_finalize_max_f32 then maps -inf -> 0          */
 } tp_reduce;
 
 /* Voxel geometry: pc_range / voxel_size / grid_size of configs/point_triplane.py:8-10. Host struct. */
@@ -127,8 +129,9 @@ TP_API int tp_voxel_index_f32(const float* points, int64_t n_total, int32_t poin
  * cell_count (optional, may be NULL): int32 [cells] number of points per pooled cell, same cell order
  * as the three outputs concatenated (xy, yz, xz).
  * Any of out_xy/out_yz/out_xz may be NULL to skip that plane.
- * workspace: tp_encode_workspace_bytes(); its `head` region must be all 0xFF bytes before the FIRST
- * call (tp_encode_workspace_init) and is left clean by every call.
+ * workspace: tp_encode_workspace_bytes() bytes; it must be zeroed once before the FIRST call
+ * (tp_encode_workspace_init) and every call leaves its tile counters zero again. One workspace per
+ * stream: calls sharing a workspace must be stream-ordered.
  * ------------------------------------------------------------------------------------------- */
 TP_API int64_t tp_encode_cells(const tp_geom* geom, int32_t batch, int64_t cells_per_plane[3]);
 TP_API int64_t tp_encode_workspace_bytes(const tp_geom* geom, int32_t batch, int64_t n_total);
@@ -143,6 +146,10 @@ TP_API int tp_encode_f32(const float* feats, int64_t feat_stride, int32_t C,
 /* Divide partial SUM planes by counts (after a point-sharded all-reduce): out[cell,:] /= max(cnt,1). */
 TP_API int tp_encode_finalize_mean_f32(float* planes, const int32_t* cell_count, int64_t cells, int32_t C,
                                 void* stream);
+
+/* After all-reduce(max) of TP_REDUCE_MAX_PARTIAL planes: -inf -> 0 (cell empty on every GPU), optional
+ * clamp at 0. In place over n_floats contiguous floats. */
+TP_API int tp_encode_finalize_max_f32(float* planes, int64_t n_floats, int32_t clamp_zero, void* stream);
 
 /* unq_cnt of projector.py:99 as a dense grid: counts [B, X, Y, Z] int32 += 1 per in-range point.
  * counts must be zeroed by the caller. */
@@ -162,6 +169,9 @@ TP_API int tp_voxel_counts_i32(const int32_t* idx, int64_t n_total, const int64_
  * ------------------------------------------------------------------------------------------- */
 TP_API int tp_planes_nchw_to_nhwc_f32(const float* src, int64_t src_batch_stride, float* dst,
                                int32_t batch, int32_t C, int32_t H, int32_t W, void* stream);
+/* the three planes in ONE launch: dst[k] receives [B, H_k, W_k, C] */
+TP_API int tp_planes3_nchw_to_nhwc_f32(const tp_plane planes_nchw[3], float* const dst[3], int32_t batch,
+                                int32_t C, void* stream);
 TP_API int tp_sample3_nhwc_f32(const tp_plane planes_nhwc[3], int32_t C,
                         const float* queries, int64_t Q, int32_t batch,
                         const tp_sample_geom* sg, int32_t arith,

@@ -11,105 +11,17 @@
 // is written as 128-B coalesced rows.
 #include <atomic>
 
-#include "tp_common.cuh"
+#include "tp_sample_dev.cuh"
 
 namespace tp {
 
-struct SampleParams {
-  const float* plane[3];
-  int64_t bstride[3];
-  int H[3], W[3];
-  float lo[3], vs[3], rcp_vs[3], half[3], rcp_half[3];
-  const float* queries;  // [B,Q,3]
-  float* out;            // [B,C,Q]
-  int64_t Q;
-  int64_t tiles_per_sample;
-  int64_t tiles;
-  int C;
-};
-
-// ATen grid_sampler_unnormalize, align_corners=False.
-//  CUDA (GridSampler.cuh): ((g + 1) * size - 1) / 2   -- nvcc contracts the mul+sub into one fma
-//  CPU  (GridSamplerKernel.cpp): (g + 1) * (size / 2) - 0.5
-template <int ARITH>
-__device__ __forceinline__ float unnormalize(float g, float size) {
-  float t = __fadd_rn(g, 1.0f);
-  if (ARITH == TP_ARITH_TORCH_CUDA) return __fmul_rn(__fmaf_rn(t, size, -1.0f), 0.5f);
-  if (ARITH == TP_ARITH_TORCH_CPU) return __fsub_rn(__fmul_rn(t, __fmul_rn(size, 0.5f)), 0.5f);
-  return __fmul_rn(__fsub_rn(__fmul_rn(t, size), 1.0f), 0.5f);  // 2: CUDA formula, no contraction
-}
-
 constexpr int kWarpsPerCta = 4;
-constexpr int kParamStride = 20;  // words per query: 16 used; 20 keeps 8-lane STS.128 phases conflict-free
-constexpr int kParamWords = 32 * kParamStride + 16;  // + 4-word skew per 8-query group (LDS.128 side)
-constexpr int kTileWords = 32 * 32;  // [32 channels][32 queries], column XOR-swizzled by (channel >> 2) & 7
-
-__device__ __forceinline__ int param_base(int qi) { return qi * kParamStride + (qi >> 3) * 4; }
 
 // Dynamic tile scheduler state: a ring of (next tile, finished warps) pairs; the host picks a slot
 // per launch, the last warp of a launch resets it. In-range and out-of-range tiles differ ~5x in
 // cost, so a static split leaves SMs idle.
 constexpr int kSchedSlots = 1024;
 __device__ unsigned int g_sched[kSchedSlots][2];  // [next tile, finished warps]
-
-// per-query setup for one plane: 4 weights, nw pixel index, 4-bit in-bounds mask
-template <int ARITH>
-__device__ __forceinline__ void plane_setup(float gx, float gy, int W, int H, float4& w, int& base,
-                                            int& mask) {
-  float ix = unnormalize<ARITH>(gx, (float)W);
-  float iy = unnormalize<ARITH>(gy, (float)H);
-  float fx0 = floorf(ix), fy0 = floorf(iy);
-  float fx1 = __fadd_rn(fx0, 1.0f), fy1 = __fadd_rn(fy0, 1.0f);
-  // nw=(x1-ix)(y1-iy) ne=(ix-x0)(y1-iy) sw=(x1-ix)(iy-y0) se=(ix-x0)(iy-y0)
-  float ax1 = __fsub_rn(fx1, ix), ax0 = __fsub_rn(ix, fx0);
-  float ay1 = __fsub_rn(fy1, iy), ay0 = __fsub_rn(iy, fy0);
-  w.x = __fmul_rn(ax1, ay1);
-  w.y = __fmul_rn(ax0, ay1);
-  w.z = __fmul_rn(ax1, ay0);
-  w.w = __fmul_rn(ax0, ay0);
-  // float->int like ATen's static_cast<int>(::floor(ix)) (cvt.rzi saturates, NaN -> 0)
-  int x0 = (int)fx0, y0 = (int)fy0;
-  int x1 = x0 + 1, y1 = y0 + 1;
-  bool bx0 = (x0 >= 0) & (x0 < W), bx1 = (x1 >= 0) & (x1 < W);
-  bool by0 = (y0 >= 0) & (y0 < H), by1 = (y1 >= 0) & (y1 < H);
-  mask = (int)(bx0 & by0) | ((int)(bx1 & by0) << 1) | ((int)(bx0 & by1) << 2) |
-         ((int)(bx1 & by1) << 3);
-  // keep the base small when nothing is in bounds so base*C cannot overflow
-  base = mask ? (y0 * W + x0) : 0;
-}
-
-// ATen accumulates out_acc += val * w for nw, ne, sw, se in that order (fma-contracted by nvcc),
-// starting from 0 and skipping out-of-bounds taps.
-__device__ __forceinline__ float4 fma4(float4 v, float w, float4 a) {
-  return make_float4(__fmaf_rn(v.x, w, a.x), __fmaf_rn(v.y, w, a.y), __fmaf_rn(v.z, w, a.z),
-                     __fmaf_rn(v.w, w, a.w));
-}
-__device__ __forceinline__ float4 mul4(float4 v, float w) {  // == fma(v, w, +0) bit for bit
-  return make_float4(__fmaf_rn(v.x, w, 0.f), __fmaf_rn(v.y, w, 0.f), __fmaf_rn(v.z, w, 0.f),
-                     __fmaf_rn(v.w, w, 0.f));
-}
-
-// One plane, one query, this lane's 4 channels. C4 = C/4 is a compile-time constant in the
-// specialised kernels so the x-neighbour is an immediate offset and only the row stride needs a
-// second 64-bit pointer.
-template <bool MASKED>
-__device__ __forceinline__ float4 plane_taps(const float4* __restrict__ pl, int off, int C4, int WC4,
-                                             float4 w, int mk, unsigned long long pol) {
-  const float4* t0 = pl + off;
-  const float4* t1 = t0 + WC4;
-  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (!MASKED) {
-    const float4 v00 = ld_keep_f4(t0, pol), v01 = ld_keep_f4(t0 + C4, pol), v10 = ld_keep_f4(t1, pol),
-                 v11 = ld_keep_f4(t1 + C4, pol);
-    return fma4(v11, w.w, fma4(v10, w.z, fma4(v01, w.y, mul4(v00, w.x))));
-  }
-  float4 a = z;
-  if (mk & 1) a = fma4(ld_keep_f4(t0, pol), w.x, a);
-  if (mk & 2) a = fma4(ld_keep_f4(t0 + C4, pol), w.y, a);
-  if (mk & 4) a = fma4(ld_keep_f4(t1, pol), w.z, a);
-  if (mk & 8) a = fma4(ld_keep_f4(t1 + C4, pol), w.w, a);
-  return a;
-}
 
 // C4T: C/4 known at compile time (8, 24, 32 for the reference's C = 32, 96, 128) or 0 = runtime.
 template <int ARITH, int C4T>
@@ -120,13 +32,6 @@ sample3_kernel(const SampleParams P, const int sched_slot) {
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int sub = lane >> 3, l8 = lane & 7;
-  float* sp = s_param[warp];
-  float* st = s_tile[warp];
-  const int C4 = C4T ? C4T : (P.C >> 2);
-  const int C = C4 * 4;
-  const int nchunk = (C4 + 7) >> 3;
-  const int WC4_0 = P.W[0] * C4, WC4_1 = P.W[1] * C4, WC4_2 = P.W[2] * C4;
   unsigned int* sched = g_sched[sched_slot];
   // planes (MBs) are re-read by every query while the output (10x larger) streams through L2 once
   const unsigned long long pol_planes = policy_evict_last(), pol_out = policy_evict_first();
@@ -140,117 +45,11 @@ sample3_kernel(const SampleParams P, const int sched_slot) {
     if (tile >= P.tiles) break;
     const int b = (int)(tile / P.tiles_per_sample);
     const int64_t q0 = (tile - (int64_t)b * P.tiles_per_sample) * 32;
-    const int64_t q = q0 + lane;
-    const bool qvalid = q < P.Q;
-
-    // ---- per-query coordinate chain (one lane per query) ---------------------------------
-    int anymask = 0;
-    {
-      float4 w[3];
-      int base[3], mask[3];
-      if (qvalid) {
-        const float* qp = P.queries + ((int64_t)b * P.Q + q) * 3;
-        float p[3] = {__ldg(qp), __ldg(qp + 1), __ldg(qp + 2)};
-        float g[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          float v = tp_voxel_coord<ARITH == TP_ARITH_TORCH_CPU ? TP_ARITH_TORCH_CPU
-                                                               : TP_ARITH_TORCH_CUDA>(
-              p[a], P.lo[a], P.vs[a], P.rcp_vs[a]);
-          float n = (ARITH == TP_ARITH_TORCH_CPU) ? __fdiv_rn(v, P.half[a])
-                                                  : __fmul_rn(v, P.rcp_half[a]);
-          g[a] = __fsub_rn(n, 1.0f);
-        }
-        plane_setup<ARITH>(g[0], g[1], P.W[0], P.H[0], w[0], base[0], mask[0]);  // (x,y)
-        plane_setup<ARITH>(g[1], g[2], P.W[1], P.H[1], w[1], base[1], mask[1]);  // (y,z)
-        plane_setup<ARITH>(g[0], g[2], P.W[2], P.H[2], w[2], base[2], mask[2]);  // (x,z)
-      } else {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          w[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-          base[k] = 0;
-          mask[k] = 0;
-        }
-      }
-      anymask = mask[0] | (mask[1] << 4) | (mask[2] << 8);
-      float4* dst = reinterpret_cast<float4*>(sp + param_base(lane));
-      dst[0] = w[0];
-      dst[1] = w[1];
-      dst[2] = w[2];
-      // tap offsets in float4 units (base * C/4 < 2^29, checked on the host)
-      dst[3] = make_float4(__int_as_float(base[0] * C4), __int_as_float(base[1] * C4),
-                           __int_as_float(base[2] * C4), __int_as_float(anymask));
-    }
-    const bool tile_empty = __all_sync(0xffffffffu, anymask == 0);
-    const bool tile_full = __all_sync(0xffffffffu, anymask == 0xfff);
-    __syncwarp();
-
-    const float4* pl0 = reinterpret_cast<const float4*>(P.plane[0] + (int64_t)b * P.bstride[0]) + l8;
-    const float4* pl1 = reinterpret_cast<const float4*>(P.plane[1] + (int64_t)b * P.bstride[1]) + l8;
-    const float4* pl2 = reinterpret_cast<const float4*>(P.plane[2] + (int64_t)b * P.bstride[2]) + l8;
-
-    for (int ch = 0; ch < nchunk; ++ch) {
-      const int cmax = min(32, C - ch * 32);
-      float* orow = P.out + ((int64_t)b * C + ch * 32) * P.Q + q0;
-      if (tile_empty) {
-        // every query of the tile misses all three planes: zeros, no gathers, no staging
-        if (q_vec4) {
-          const int r0 = lane >> 3, c4q = (lane & 7) * 4;
-          if (q0 + c4q < P.Q) {
-            for (int c = r0; c < cmax; c += 4)
-              st_stream_f4(reinterpret_cast<float4*>(orow + (int64_t)c * P.Q + c4q), make_float4(0.f, 0.f, 0.f, 0.f), pol_out);
-          }
-        } else if (qvalid) {
-          for (int c = 0; c < cmax; ++c) st_stream_f1(orow + (int64_t)c * P.Q + lane, 0.f, pol_out);
-        }
-        continue;
-      }
-      const int choff = ch * 8;
-      const bool chunk_full = cmax == 32;  // warp-uniform; partial chunks only when C % 32 != 0
-      float* tcol = st + (l8 * 4) * 32;
-      if (tile_full && chunk_full) {
-#pragma unroll
-        for (int pass = 0; pass < 8; ++pass) {
-          const int qi = sub * 8 + pass;  // 8 consecutive queries per 8-lane group
-          const float4* prm = reinterpret_cast<const float4*>(sp + param_base(qi));
-          const float4 w0 = prm[0], w1 = prm[1], w2 = prm[2], bm = prm[3];
-          const float4 a0 = plane_taps<false>(pl0 + choff, __float_as_int(bm.x), C4, WC4_0, w0, 15, pol_planes);
-          const float4 a1 = plane_taps<false>(pl1 + choff, __float_as_int(bm.y), C4, WC4_1, w1, 15, pol_planes);
-          const float4 a2 = plane_taps<false>(pl2 + choff, __float_as_int(bm.z), C4, WC4_2, w2, 15, pol_planes);
-          float* t = tcol + (qi ^ l8);
-          t[0] = __fadd_rn(__fadd_rn(a0.x, a1.x), a2.x);  // (xy + yz) + xz  (triplane_occ.py:345)
-          t[32] = __fadd_rn(__fadd_rn(a0.y, a1.y), a2.y);
-          t[64] = __fadd_rn(__fadd_rn(a0.z, a1.z), a2.z);
-          t[96] = __fadd_rn(__fadd_rn(a0.w, a1.w), a2.w);
-        }
-      } else {
-        const bool cvalid = ch * 32 + l8 * 4 < C;  // C % 4 == 0
-#pragma unroll 2
-        for (int pass = 0; pass < 8; ++pass) {
-          const int qi = sub * 8 + pass;
-          const float4* prm = reinterpret_cast<const float4*>(sp + param_base(qi));
-          const float4 w0 = prm[0], w1 = prm[1], w2 = prm[2], bm = prm[3];
-          const int m = cvalid ? __float_as_int(bm.w) : 0;
-          const float4 a0 = plane_taps<true>(pl0 + choff, __float_as_int(bm.x), C4, WC4_0, w0, m & 15, pol_planes);
-          const float4 a1 = plane_taps<true>(pl1 + choff, __float_as_int(bm.y), C4, WC4_1, w1, (m >> 4) & 15, pol_planes);
-          const float4 a2 = plane_taps<true>(pl2 + choff, __float_as_int(bm.z), C4, WC4_2, w2, (m >> 8) & 15, pol_planes);
-          float* t = tcol + (qi ^ l8);
-          t[0] = __fadd_rn(__fadd_rn(a0.x, a1.x), a2.x);
-          t[32] = __fadd_rn(__fadd_rn(a0.y, a1.y), a2.y);
-          t[64] = __fadd_rn(__fadd_rn(a0.z, a1.z), a2.z);
-          t[96] = __fadd_rn(__fadd_rn(a0.w, a1.w), a2.w);
-        }
-      }
-      __syncwarp();
-      // ---- coalesced write of the [32 channels][32 queries] tile -------------------------
-      if (qvalid) {
-        float* o = orow + lane;
-        const int64_t Qs = P.Q;
-#pragma unroll 8
-        for (int c = 0; c < cmax; ++c, o += Qs) st_stream_f1(o, st[c * 32 + (lane ^ ((c >> 2) & 7))], pol_out);
-      }
-      __syncwarp();
-    }
+    const int64_t left = P.Q - q0;
+    const int n0 = (int)(left < 16 ? left : 16);
+    const int n1 = (int)(left < 16 ? 0 : (left < 32 ? left - 16 : 16));
+    sample_tile<ARITH, C4T>(P, b, q0, q0 + 16, n0, n1, s_param[warp], s_tile[warp], pol_planes, pol_out,
+                            q_vec4);
   }
   // last warp out resets the scheduler slot for the next launch that draws it
   if (lane == 0) {

@@ -1,0 +1,430 @@
+// Triplane decode for [B,h,w,d,3] query tensors (triplane_occ.py:321-348, triplane_elev.py:286-313,
+// point_triplane_occ.py:407-440): the reference's 5-D callers always pass a voxel-centre lattice
+// (roi(), triplane_occ.py:291-318; get_reference_points(), triplane_elev.py:113-133) in which x
+// depends only on the h index, y only on w and z only on d. Then
+//     xy(i,j)  yz(j,k)  xz(i,k)
+// are functions of two lattice indices each, and out[c,i,j,k] = (xy[c,i,j] + yz[c,j,k]) + xz[c,i,k]
+// with exactly the per-plane values and the summation order of the per-query kernel: bit-identical
+// output, 0.2-0.6 bilinear footprints per query instead of 3, and the kernel becomes a streaming
+// write of the result.
+//
+// Nothing is assumed: every CTA takes a BI x BJ x 16 block of the lattice, loads its queries (they
+// are read once, as the algorithmic-bytes model says) and checks bit-for-bit that the block is
+// separable. A block that is not (jittered points, a permuted tensor, ...) falls back, inside the
+// same launch, to the per-query tile routine of tp_sample.cu.
+#include <cstdlib>
+
+#include "tp_sample_dev.cuh"
+
+namespace tp {
+
+struct GridParams {
+  SampleParams S;  // S.Q = h*w*d
+  int h, w, d;
+  int nib, njb, nkb;  // blocks along h, w, d
+  int nblocks;        // batch * nib * njb * nkb
+  int vec_ok;
+};
+
+constexpr int kGridThreads = 256;
+constexpr int kBK = 16;  // lattice block extent along d
+constexpr int kBJ = 8;   // ... along w: a warp-wide 16-byte store covers 8 (j) x 4 (k/4) = 512 contiguous bytes when d == 16
+constexpr int kFallbackWarps = 4;
+
+template <int BI>
+struct GridCfg {
+  static constexpr int E0 = BI * kBJ, E1 = kBJ * kBK, E2 = BI * kBK;  // table entries (xy, yz, xz)
+  static constexpr int E = E0 + E1 + E2;
+  // Table rows are channels. xy rows are read with 4-byte loads: stride == 1 (mod 32) makes the
+  // channel-major writes conflict-free. yz / xz rows are read as 16-byte k-runs: stride == 4 (mod 32)
+  // plus the column swizzle below does the same while keeping every run aligned.
+  static constexpr int S0 = E0 + 1, S1 = E1 + 4, S2 = E2 + 4;
+  static constexpr int kTableWords = 32 * (S0 + S1 + S2);
+  static constexpr int kFallbackWords = kFallbackWarps * (kParamWords + kTileWords);
+  static constexpr int kWords = kTableWords > kFallbackWords ? kTableWords : kFallbackWords;
+  static constexpr int kSmemBytes = kWords * 4 + E * (16 + 8);
+  static_assert(kWords % 4 == 0, "entry records are 16-byte aligned");
+  static_assert(E0 % 32 == 0 && E1 % 32 == 0 && E2 % 32 == 0, "one plane per warp-round of 32 entries");
+  static_assert(BI * kBJ * kBK % kGridThreads == 0, "whole queries per thread");
+};
+
+// column swizzle of the yz / xz tables: XOR bits 2-3 of the column with bits 3-4 of the channel.
+// Keeps every aligned 4-column group (one float4 of 4 consecutive k) intact.
+__device__ __forceinline__ int swz_bits(int c) { return ((c >> 3) & 3) << 2; }
+
+// loads without side effects: not volatile, so the scheduler may batch the taps of several table
+// entries ahead of the fmas that consume them (planes are read-only for the whole launch)
+__device__ __forceinline__ float4 ld_plane_f4(const float4* p, unsigned long long pol) {
+  float4 r;
+  asm("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+      : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+      : "l"(p), "l"(pol));
+  return r;
+}
+// predicated streaming store; no "memory" clobber: nothing in this kernel reads the output, and the
+// clobber would pin every later shared-memory load behind the store
+__device__ __forceinline__ void st_out_f4(float* p, float4 v, unsigned long long pol, bool pred) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+      "@p st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;\n\t}" ::"l"(p),
+      "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol), "r"((int)pred));
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+struct Taps {
+  float4 v00, v01, v10, v11;
+};
+// the four taps of one table entry, this lane's 4 channels; out-of-bounds taps are not touched
+__device__ __forceinline__ Taps load_taps(const float4* __restrict__ pl, int off, int C4, int WC4, int mk,
+                                          unsigned long long pol) {
+  const float4* t0 = pl + off;
+  const float4* t1 = t0 + WC4;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  Taps t;
+  t.v00 = (mk & 1) ? ld_plane_f4(t0, pol) : z;
+  t.v01 = (mk & 2) ? ld_plane_f4(t0 + C4, pol) : z;
+  t.v10 = (mk & 4) ? ld_plane_f4(t1, pol) : z;
+  t.v11 = (mk & 8) ? ld_plane_f4(t1 + C4, pol) : z;
+  return t;
+}
+// same accumulation as plane_taps<true>: nw, ne, sw, se in order, out-of-bounds taps skipped
+__device__ __forceinline__ float4 accum_taps(const Taps& t, float4 w, int mk) {
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (mk & 1) a = fma4(t.v00, w.x, a);
+  if (mk & 2) a = fma4(t.v01, w.y, a);
+  if (mk & 4) a = fma4(t.v10, w.z, a);
+  if (mk & 8) a = fma4(t.v11, w.w, a);
+  return a;
+}
+
+// lattice block -> coordinates. nblk = nib * njb * nkb blocks per sample, k fastest.
+struct BlockPos {
+  int b, i0, j0, k0;
+};
+template <int BI>
+__device__ __forceinline__ BlockPos block_pos(const GridParams& G, int blk) {
+  BlockPos p;
+  const int kb = blk % G.nkb; blk /= G.nkb;
+  const int jb = blk % G.njb; blk /= G.njb;
+  p.i0 = (blk % G.nib) * BI;
+  p.b = blk / G.nib;
+  p.j0 = jb * kBJ;
+  p.k0 = kb * kBK;
+  return p;
+}
+
+// Persistent CTAs: block n+1's queries are prefetched into L2 while block n is gathered and written,
+// so the only DRAM-latency-bound step of a block (reading its 12 B/query) is off the critical path.
+template <int ARITH, int C4T, int BI>
+__global__ void __launch_bounds__(kGridThreads, 4)
+sample3_grid_kernel(const GridParams G) {
+  using Cfg = GridCfg<BI>;
+  constexpr int BJ = kBJ;
+  constexpr int QPT = BI * BJ * kBK / kGridThreads;  // queries per thread
+  extern __shared__ __align__(16) float smem[];  // Cfg::kSmemBytes: tables (or fallback tiles) + entry records
+  float4* const s_w = reinterpret_cast<float4*>(smem + Cfg::kWords);  // bilinear weights (nw, ne, sw, se) per entry
+  int2* const s_om = reinterpret_cast<int2*>(s_w + Cfg::E);  // {nw tap offset in float4 units, in-bounds mask}
+
+  const SampleParams& P = G.S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C4 = C4T ? C4T : (P.C >> 2);
+  const int C = C4 * 4;
+  const unsigned long long pol_planes = policy_evict_last(), pol_out = policy_evict_first();
+  const int wd = G.w * G.d;  // h*w*d*3 < 2^31 (host-checked): in-sample query offsets fit 32 bits
+  const int nblocks = G.nblocks;
+
+  float* const T0 = smem;
+  float* const T1 = T0 + 32 * Cfg::S0;
+  float* const T2 = T1 + 32 * Cfg::S1;
+  const int l8 = tid & 7, ent = tid >> 3;
+  const int WC4_0 = P.W[0] * C4, WC4_1 = P.W[1] * C4, WC4_2 = P.W[2] * C4;
+  const int nchunk = (C4 + 7) >> 3;
+  // table write positions of this thread: rows 4*l8 .. 4*l8+3, column = entry (swizzled for yz / xz)
+  float* const w0 = T0 + (4 * l8) * Cfg::S0 + ent;
+  float* const w1 = T1 + (4 * l8) * Cfg::S1 + (ent ^ swz_bits(4 * l8));
+  float* const w2 = T2 + (4 * l8) * Cfg::S2 + (ent ^ swz_bits(4 * l8));
+  // query ownership in phase A: k and j fixed per thread, i = ia + t * (256 / 128)
+  const int ak = tid & (kBK - 1), aj = (tid / kBK) % BJ, ia = tid / (kBK * BJ);
+  // output phase: lane -> (j, 4 consecutive k)
+  const int kg = lane & 3, jj = lane >> 2;
+
+  int blk = blockIdx.x;
+  BlockPos bp = block_pos<BI>(G, blk);
+  for (;;) {
+    const int b = bp.b, i0 = bp.i0, j0 = bp.j0, k0 = bp.k0;
+    const int ni = min(BI, G.h - i0), nj = min(BJ, G.w - j0), nk = min(kBK, G.d - k0);
+    const float* q00 = P.queries + ((int64_t)b * P.Q + ((int64_t)i0 * G.w + j0) * G.d + k0) * 3;  // block origin
+
+    // ---- A: read the block's queries once; is x = x(i), y = y(j), z = z(k) bit for bit? --------
+    bool ok = true;
+    if (aj < nj && ak < nk) {
+      const unsigned yr = __float_as_uint(__ldg(q00 + aj * G.d * 3 + 1));
+      const unsigned zr = __float_as_uint(__ldg(q00 + ak * 3 + 2));
+#pragma unroll
+      for (int t = 0; t < QPT; ++t) {
+        const int ii = ia + t * (kGridThreads / (kBK * BJ));
+        if (ii < ni) {
+          const float* qi = q00 + ii * wd * 3;
+          const float* qp = qi + (aj * G.d + ak) * 3;
+          const unsigned x = __float_as_uint(__ldg(qp)), y = __float_as_uint(__ldg(qp + 1)),
+                         z = __float_as_uint(__ldg(qp + 2));
+          ok &= (x == __float_as_uint(__ldg(qi))) & (y == yr) & (z == zr);
+        }
+      }
+    }
+    // ---- B: one bilinear footprint per table entry (index pair), from the representative queries -
+    for (int e = tid; e < Cfg::E; e += kGridThreads) {
+      int pl, a0, a1, e0i, e1i, n0, n1, s0, s1;  // s: query stride of the two lattice indices
+      if (e < Cfg::E0) {                      // xy(i,j): x -> W, y -> H of plane 0
+        pl = 0; a0 = 0; a1 = 1; e0i = e / BJ; e1i = e % BJ; n0 = ni; n1 = nj; s0 = wd; s1 = G.d;
+      } else if (e < Cfg::E0 + Cfg::E1) {     // yz(j,k): y -> W, z -> H of plane 1
+        const int r = e - Cfg::E0;
+        pl = 1; a0 = 1; a1 = 2; e0i = r / kBK; e1i = r % kBK; n0 = nj; n1 = nk; s0 = G.d; s1 = 1;
+      } else {                                // xz(i,k): x -> W, z -> H of plane 2
+        const int r = e - Cfg::E0 - Cfg::E1;
+        pl = 2; a0 = 0; a1 = 2; e0i = r / kBK; e1i = r % kBK; n0 = ni; n1 = nk; s0 = wd; s1 = 1;
+      }
+      float4 wgt = make_float4(0.f, 0.f, 0.f, 0.f);
+      int base = 0, mask = 0;
+      if (e0i < n0 && e1i < n1) {
+        const float g0 = grid_coord<ARITH>(P, __ldg(q00 + e0i * s0 * 3 + a0), a0);
+        const float g1 = grid_coord<ARITH>(P, __ldg(q00 + e1i * s1 * 3 + a1), a1);
+        plane_setup<ARITH>(g0, g1, P.W[pl], P.H[pl], wgt, base, mask);
+      }
+      s_w[e] = wgt;
+      s_om[e] = make_int2(base * C4, mask);
+    }
+    // every warp is past the previous block's output phase once it arrives here
+    const bool separable = __syncthreads_and(ok);
+
+    // ---- prefetch the next block's queries (DRAM -> L2) behind this block's gathers and stores ---
+    const int next = blk + gridDim.x;
+    BlockPos np = bp;
+    if (next < nblocks) {
+      np = block_pos<BI>(G, next);
+      if (np.j0 + aj < G.w && np.k0 + ak < G.d) {
+        const float* n00 = P.queries + ((int64_t)np.b * P.Q + ((int64_t)np.i0 * G.w + np.j0) * G.d + np.k0) * 3;
+        // one lane per 32 bytes of the (j,k) run is plenty: 12 B per query
+        if ((ak & 1) == 0) {
+#pragma unroll
+          for (int t = 0; t < QPT; ++t) {
+            const int ii = ia + t * (kGridThreads / (kBK * BJ));
+            if (np.i0 + ii < G.h) prefetch_l2(n00 + (ii * wd + aj * G.d + ak) * 3);
+          }
+        }
+      }
+    }
+
+    if (!separable) {
+      // ---- per-query fallback: the flat kernel's tile routine on pairs of (i,j) columns ---------
+      if (warp < kFallbackWarps) {
+        float* sp = smem + warp * (kParamWords + kTileWords);
+        float* st = sp + kParamWords;
+        for (int t = warp; t < BI * BJ / 2; t += kFallbackWarps) {
+          const int r0 = 2 * t, r1 = 2 * t + 1;
+          const int ia0 = r0 / BJ, ja0 = r0 % BJ, ia1 = r1 / BJ, ja1 = r1 % BJ;
+          const int n0 = (ia0 < ni && ja0 < nj) ? nk : 0, n1 = (ia1 < ni && ja1 < nj) ? nk : 0;
+          if (n0 == 0 && n1 == 0) continue;
+          const int64_t run0 = ((int64_t)(i0 + ia0) * G.w + j0 + ja0) * G.d + k0;
+          const int64_t run1 = ((int64_t)(i0 + ia1) * G.w + j0 + ja1) * G.d + k0;
+          sample_tile<ARITH, C4T>(P, b, run0, run1, n0, n1, sp, st, pol_planes, pol_out, G.vec_ok != 0);
+        }
+      }
+      __syncthreads();  // the fallback tiles alias the next block's tables
+    } else {
+      const float4* const pl0 = reinterpret_cast<const float4*>(P.plane[0] + (int64_t)b * P.bstride[0]) + l8;
+      const float4* const pl1 = reinterpret_cast<const float4*>(P.plane[1] + (int64_t)b * P.bstride[1]) + l8;
+      const float4* const pl2 = reinterpret_cast<const float4*>(P.plane[2] + (int64_t)b * P.bstride[2]) + l8;
+      const bool jk_ok = (jj < nj) && (kg * 4 < nk);
+      float* const o_jk = P.out + (int64_t)b * C * P.Q + ((int64_t)i0 * G.w + j0 + jj) * G.d + k0 + kg * 4;
+
+      for (int ch = 0; ch < nchunk; ++ch) {
+        // ---- C: the three 2-D tables for 32 channels: 8 lanes x 16 B per bilinear tap -----------
+        // two entries per thread in flight: 8 independent 16-byte loads before the first fma
+        const bool cvalid = ch * 32 + l8 * 4 < C;
+        constexpr int R = Cfg::E / 32;
+#pragma unroll
+        for (int r = 0; r < R; r += 2) {
+          float4 wgt[2];
+          int mk[2];
+          Taps tp[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (r + u < R) {
+              const int e = (r + u) * 32 + ent;
+              wgt[u] = s_w[e];
+              const int2 om = s_om[e];
+              mk[u] = cvalid ? om.y : 0;
+              if ((r + u) * 32 < Cfg::E0) tp[u] = load_taps(pl0 + ch * 8, om.x, C4, WC4_0, mk[u], pol_planes);
+              else if ((r + u) * 32 < Cfg::E0 + Cfg::E1) tp[u] = load_taps(pl1 + ch * 8, om.x, C4, WC4_1, mk[u], pol_planes);
+              else tp[u] = load_taps(pl2 + ch * 8, om.x, C4, WC4_2, mk[u], pol_planes);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (r + u < R) {
+              const float4 a = accum_taps(tp[u], wgt[u], mk[u]);
+              float* t;
+              int stride;
+              if ((r + u) * 32 < Cfg::E0) { t = w0 + (r + u) * 32; stride = Cfg::S0; }
+              else if ((r + u) * 32 < Cfg::E0 + Cfg::E1) { t = w1 + ((r + u) * 32 - Cfg::E0); stride = Cfg::S1; }
+              else { t = w2 + ((r + u) * 32 - Cfg::E0 - Cfg::E1); stride = Cfg::S2; }
+              t[0] = a.x;
+              t[stride] = a.y;
+              t[2 * stride] = a.z;
+              t[3 * stride] = a.w;
+            }
+          }
+        }
+        __syncthreads();
+
+        // ---- D: out[c, i, j, k..k+3] = (xy[c,i,j] + yz[c,j,k..]) + xz[c,i,k..], 16-byte stores ---
+        const int cmax = min(32, C - ch * 32);
+        for (int c = warp; c < cmax; c += kGridThreads / 32) {
+          const int xk = (kg * 4) ^ swz_bits(c);
+          const float4 s1 = *reinterpret_cast<const float4*>(T1 + c * Cfg::S1 + jj * kBK + xk);
+          const float* t0 = T0 + c * Cfg::S0 + jj;
+          const float* t2 = T2 + c * Cfg::S2 + xk;
+          float* o = o_jk + (int64_t)(ch * 32 + c) * P.Q;
+#pragma unroll
+          for (int ii = 0; ii < BI; ++ii, o += wd) {
+            const float s0 = t0[ii * BJ];
+            const float4 s2 = *reinterpret_cast<const float4*>(t2 + ii * kBK);
+            float4 r;
+            r.x = __fadd_rn(__fadd_rn(s0, s1.x), s2.x);  // (xy + yz) + xz  (triplane_occ.py:345)
+            r.y = __fadd_rn(__fadd_rn(s0, s1.y), s2.y);
+            r.z = __fadd_rn(__fadd_rn(s0, s1.z), s2.z);
+            r.w = __fadd_rn(__fadd_rn(s0, s1.w), s2.w);
+            st_out_f4(o, r, pol_out, jk_ok && ii < ni);
+          }
+        }
+        if (ch + 1 < nchunk) __syncthreads();
+      }
+    }
+    if (next >= nblocks) break;
+    blk = next;
+    bp = np;
+  }
+}
+
+template <int ARITH, int C4T, int BI>
+static void launch_grid(const GridParams& G, int batch, cudaStream_t s) {
+  // persistent CTAs, 4 per SM; TP_GRID_CTAS (experiments) overrides the grid size
+  int64_t blocks = G.nblocks < 4 * kSMs ? G.nblocks : 4 * kSMs;
+  if (const char* e = getenv("TP_GRID_CTAS")) {
+    const int64_t v = atoll(e);
+    if (v > 0) blocks = v < G.nblocks ? v : G.nblocks;
+  }
+  auto kern = sample3_grid_kernel<ARITH, C4T, BI>;
+  static bool opted_in[64] = {};  // per device: > 48 KB of dynamic shared memory needs the opt-in once
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !opted_in[dev]) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GridCfg<BI>::kSmemBytes);
+    if (dev >= 0 && dev < 64) opted_in[dev] = true;
+  }
+  kern<<<(unsigned)blocks, kGridThreads, GridCfg<BI>::kSmemBytes, s>>>(G);
+}
+
+}  // namespace tp
+
+using namespace tp;
+
+extern "C" int tp_sample3_grid_nhwc_f32(const tp_plane planes[3], int32_t C, const float* queries,
+                                        const int32_t dims[3], int32_t batch, const tp_sample_geom* sg,
+                                        int32_t arith, float* out, void* stream) {
+  if (!dims) return fail(TP_E_NULL, "tp_sample3_grid_nhwc_f32: null dims");
+  const int h = dims[0], w = dims[1], d = dims[2];
+  if (h < 0 || w < 0 || d < 0) return fail(TP_E_SHAPE, "tp_sample3_grid_nhwc_f32: bad dims %d %d %d", h, w, d);
+  const int64_t Q = (int64_t)h * w * d;
+  // lattice path needs 16-byte aligned k-runs; anything else goes through the per-query kernel
+  if ((d & 3) || (reinterpret_cast<uintptr_t>(out) & 15) || arith == 2 || Q == 0 || Q * 3 >= ((int64_t)1 << 31))
+    return tp_sample3_nhwc_f32(planes, C, queries, Q, batch, sg, arith, out, stream);
+  if (C <= 0 || (C & 3)) return fail(TP_E_SHAPE, "tp_sample3_grid_nhwc_f32: C=%d must be a positive multiple of 4", C);
+  if (batch <= 0) return fail(TP_E_SHAPE, "tp_sample3_grid_nhwc_f32: bad B=%d", batch);
+  if (!planes || !queries || !out || !sg) return fail(TP_E_NULL, "tp_sample3_grid_nhwc_f32: null argument");
+  GridParams G;
+  SampleParams& P = G.S;
+  for (int k = 0; k < 3; ++k) {
+    if (!planes[k].data) return fail(TP_E_NULL, "tp_sample3_grid_nhwc_f32: plane %d is null", k);
+    if (planes[k].H <= 0 || planes[k].W <= 0 ||
+        (int64_t)planes[k].H * planes[k].W * C >= (int64_t)1 << 31 || planes[k].H >= (1 << 20) ||
+        planes[k].W >= (1 << 20))
+      return fail(TP_E_SHAPE, "tp_sample3_grid_nhwc_f32: plane %d H=%d W=%d unsupported", k, planes[k].H, planes[k].W);
+    if ((uintptr_t)planes[k].data & 15 || (planes[k].batch_stride & 3))
+      return fail(TP_E_SHAPE, "tp_sample3_grid_nhwc_f32: plane %d not 16-byte aligned", k);
+    P.plane[k] = planes[k].data;
+    P.bstride[k] = planes[k].batch_stride;
+    P.H[k] = planes[k].H;
+    P.W[k] = planes[k].W;
+    P.lo[k] = sg->lo[k];
+    P.vs[k] = sg->vs[k];
+    P.rcp_vs[k] = 1.0f / sg->vs[k];
+    P.half[k] = sg->half[k];
+    P.rcp_half[k] = 1.0f / sg->half[k];
+  }
+  P.queries = queries;
+  P.out = out;
+  P.Q = Q;
+  P.C = C;
+  P.tiles_per_sample = 0;
+  P.tiles = 0;
+  G.h = h; G.w = w; G.d = d;
+  G.vec_ok = 1;
+  G.nkb = (d + kBK - 1) / kBK;
+  // block shape BI x 8 x 16: the larger one shares each yz footprint between 8 lattice rows instead
+  // of 4; the smaller one is for grids that would otherwise leave SMs with < 8 blocks to balance
+  auto nblocks = [&](int bi) { return (int64_t)batch * ((h + bi - 1) / bi) * ((w + kBJ - 1) / kBJ) * G.nkb; };
+  int cfg = nblocks(8) >= 8 * kSMs ? 0 : 1;
+  if (const char* e = getenv("TP_GRID_TILE")) {  // experiments only: 0 = 8x8x16, 1 = 4x8x16
+    const int v = atoi(e);
+    if (v >= 0 && v <= 1) cfg = v;
+  }
+  const int bi = cfg == 0 ? 8 : 4;
+  G.nib = (h + bi - 1) / bi;
+  G.njb = (w + kBJ - 1) / kBJ;
+  if (nblocks(bi) >= ((int64_t)1 << 30)) return fail(TP_E_SHAPE, "tp_sample3_grid_nhwc_f32: too many queries");
+  G.nblocks = (int)nblocks(bi);
+  cudaStream_t s = (cudaStream_t)stream;
+#define TP_GRID_B(A, C4T)                                             \
+  switch (cfg) { case 0: launch_grid<A, C4T, 8>(G, batch, s); break; \
+                 default: launch_grid<A, C4T, 4>(G, batch, s); break; }
+#define TP_GRID_C(A)                                                      \
+  switch (C) { case 32: TP_GRID_B(A, 8) break; case 96: TP_GRID_B(A, 24) break; \
+               case 128: TP_GRID_B(A, 32) break; default: TP_GRID_B(A, 0) break; }
+  switch (arith) {
+    case TP_ARITH_TORCH_CUDA: TP_GRID_C(TP_ARITH_TORCH_CUDA) break;
+    case TP_ARITH_TORCH_CPU:  TP_GRID_C(TP_ARITH_TORCH_CPU) break;
+    default: return fail(TP_E_ENUM, "tp_sample3_grid_nhwc_f32: unknown arith %d", arith);
+  }
+#undef TP_GRID_C
+#undef TP_GRID_B
+  TP_LAUNCH_CHECK("sample3_grid_kernel");
+  return 0;
+}
+
+extern "C" int tp_sample3_grid_nchw_f32(const tp_plane planes_nchw[3], int32_t C, const float* queries,
+                                        const int32_t dims[3], int32_t batch, const tp_sample_geom* sg,
+                                        int32_t arith, float* out, float* ws, int64_t ws_floats,
+                                        void* stream) {
+  if (!planes_nchw || !ws) return fail(TP_E_NULL, "tp_sample3_grid_nchw_f32: null argument");
+  tp_plane nhwc[3];
+  int64_t need = 0;
+  for (int k = 0; k < 3; ++k) need += (int64_t)batch * C * planes_nchw[k].H * planes_nchw[k].W;
+  if (ws_floats < need)
+    return fail(TP_E_WORKSPACE, "tp_sample3_grid_nchw_f32: workspace %lld < %lld floats", (long long)ws_floats, (long long)need);
+  float* wp = ws;
+  float* dsts[3];
+  for (int k = 0; k < 3; ++k) {
+    dsts[k] = wp;
+    nhwc[k].data = wp;
+    nhwc[k].H = planes_nchw[k].H;
+    nhwc[k].W = planes_nchw[k].W;
+    nhwc[k].batch_stride = (int64_t)C * planes_nchw[k].H * planes_nchw[k].W;
+    wp += (int64_t)batch * nhwc[k].batch_stride;
+  }
+  if (int rc = tp_planes3_nchw_to_nhwc_f32(planes_nchw, dsts, batch, C, stream)) return rc;
+  return tp_sample3_grid_nhwc_f32(nhwc, C, queries, dims, batch, sg, arith, out, stream);
+}

@@ -137,7 +137,10 @@ def sample_points_triplane(triplane: Union[torch.Tensor, Sequence[torch.Tensor]]
         from .autograd import sample3_autograd
         out = sample3_autograd(triplane, q, lo, vs, half, arith)
     else:
-        out = ops.sample3(triplane, q, lo, vs, half, arith=arith)
+        # 5-D callers pass a voxel-centre lattice (roi() / get_reference_points()): the grid entry
+        # point exploits that per block and is bit-identical to the flat one on any other input
+        dims = tuple(points.shape[1:4]) if points.dim() == 5 else None
+        out = ops.sample3(triplane, q, lo, vs, half, arith=arith, grid_dims=dims)
     return out.view(B, -1, *points.shape[1:-1])
 
 

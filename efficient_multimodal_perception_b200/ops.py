@@ -252,12 +252,16 @@ def planes_to_channels_last(planes: Sequence[torch.Tensor]) -> List[torch.Tensor
 
 
 def sample3(planes: Union[torch.Tensor, Sequence[torch.Tensor]], queries: torch.Tensor, lo, vs, half, *,
-            arith: str = "cuda", channels_last: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+            arith: str = "cuda", channels_last: bool = False, out: Optional[torch.Tensor] = None,
+            grid_dims: Optional[Sequence[int]] = None) -> torch.Tensor:
     """Fused 3-plane bilinear sample + sum.
 
     planes: stacked [B,3,C,H,W] or a list of three NCHW planes [B,C,H_p,W_p] (channels_last=True:
     already-converted [B,H_p,W_p,C] copies from planes_to_channels_last()). queries [B,Q,3].
-    half[a] = S_a / 2 (triplane_occ.py:337 / point_triplane.py:455-458). Returns [B,C,Q]."""
+    half[a] = S_a / 2 (triplane_occ.py:337 / point_triplane.py:455-458). Returns [B,C,Q].
+    grid_dims=(h, w, d) with h*w*d == Q: the queries are a flattened [B,h,w,d,3] tensor (the 5-D
+    callers); same result bit for bit, through tp_sample3_grid_nhwc_f32 which evaluates lattice-
+    structured blocks once per index pair instead of once per query."""
     global launch_count
     if isinstance(planes, torch.Tensor):
         if planes.dim() != 5 or planes.shape[1] != 3:
@@ -286,7 +290,16 @@ def sample3(planes: Union[torch.Tensor, Sequence[torch.Tensor]], queries: torch.
         out = torch.empty((B, Cc, Q), dtype=torch.float32, device=queries.device)
     elif tuple(out.shape) != (B, Cc, Q) or not out.is_contiguous() or not out.is_cuda:
         raise TriplaneError("sample3: bad `out`")
-    L.check(L.lib().tp_sample3_nhwc_f32(C.byref(arr), Cc, queries.data_ptr(), Q, B, C.byref(sg), _ARITH[arith],
-                                        out.data_ptr(), _stream(queries)), "tp_sample3_nhwc_f32")
+    if grid_dims is not None:
+        h, w, d = (int(v) for v in grid_dims)
+        if h * w * d != Q:
+            raise TriplaneError(f"sample3: grid_dims {tuple(grid_dims)} do not multiply to Q={Q}")
+        dims = (C.c_int32 * 3)(h, w, d)
+        L.check(L.lib().tp_sample3_grid_nhwc_f32(C.byref(arr), Cc, queries.data_ptr(), C.byref(dims), B,
+                                                 C.byref(sg), _ARITH[arith], out.data_ptr(), _stream(queries)),
+                "tp_sample3_grid_nhwc_f32")
+    else:
+        L.check(L.lib().tp_sample3_nhwc_f32(C.byref(arr), Cc, queries.data_ptr(), Q, B, C.byref(sg),
+                                            _ARITH[arith], out.data_ptr(), _stream(queries)), "tp_sample3_nhwc_f32")
     launch_count += 1 if Q else 0
     return out

@@ -182,6 +182,23 @@ TP_API int tp_sample3_nchw_f32(const tp_plane planes_nchw[3], int32_t C,
                         float* out, float* nhwc_workspace, int64_t nhwc_workspace_floats,
                         void* stream);
 
+/* [B,h,w,d,3] query tensors (the 5-D callers: triplane_occ.py:338-346, triplane_elev.py:303-311,
+ * point_triplane_occ.py:427-438). Same result, bit for bit, as tp_sample3_nhwc_f32 on the flattened
+ * [B, h*w*d, 3] queries; out [B, C, h*w*d]. Every 3-D block of the tensor is tested on the device for
+ * the voxel-centre-lattice structure of roi() (triplane_occ.py:291-318) / get_reference_points()
+ * (triplane_elev.py:113-133) -- x a function of the h index only, y of w, z of d -- and, where it holds,
+ * the three per-plane sums are evaluated once per index pair instead of once per query. Blocks where
+ * it does not hold take the per-query path inside the same launch. dims = {h, w, d}. */
+TP_API int tp_sample3_grid_nhwc_f32(const tp_plane planes_nhwc[3], int32_t C,
+                             const float* queries, const int32_t dims[3], int32_t batch,
+                             const tp_sample_geom* sg, int32_t arith,
+                             float* out, void* stream);
+TP_API int tp_sample3_grid_nchw_f32(const tp_plane planes_nchw[3], int32_t C,
+                             const float* queries, const int32_t dims[3], int32_t batch,
+                             const tp_sample_geom* sg, int32_t arith,
+                             float* out, float* nhwc_workspace, int64_t nhwc_workspace_floats,
+                             void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Host-buffer entry points (what a non-PyTorch caller binds; bench.py's `e2e` leg).
  * All pointers are HOST memory (pinned recommended). They allocate a per-thread cached device

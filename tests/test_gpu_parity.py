@@ -348,6 +348,71 @@ def test_sample_baseline_size_640k():
     assert normwise(out, ref) <= TOL
 
 
+def _grid_case(dims, C, B, seed, lattice_vs=(0.5, 0.5, 0.5), origin=(-30.0, -28.0, -5.0), planes_grid=None):
+    lo, vs = [-25.0, -25.0, -5.0], (0.4, 0.4, 0.1)
+    pts = synth.lattice(dims, lattice_vs, origin)[None].repeat(B, 1, 1, 1, 1)
+    if planes_grid is None:
+        tri = cu(synth.triplane_stacked(B, C, 128, seed=seed))
+        return tri, cu(pts), lo, vs, [64.0] * 3
+    planes = [cu(p) for p in synth.triplane_list(B, C, planes_grid, seed=seed)]
+    vs = (50.0 / planes_grid[0], 50.0 / planes_grid[1], 8.0 / planes_grid[2])
+    return planes, cu(pts), lo, vs, [g / 2 for g in planes_grid]
+
+
+@pytest.mark.parametrize("dims,C,B,planes_grid", [
+    ((200, 200, 16), 32, 1, None),          # BASELINE.json config[1]: the 640k occupancy-GT lattice
+    ((99, 99, 16), 32, 2, None),            # configs/triplane_occ.py roi() lattice, ragged blocks in h and w
+    ((100, 100, 80), 32, 1, None),          # triplane_elev.py get_reference_points volume: five k blocks
+    ((37, 21, 20), 96, 2, [128, 128, 80]),  # list-of-planes variant, 3 channel chunks, ragged in h, w, d
+    ((9, 5, 4), 36, 1, [20, 24, 12]),       # runtime C, partial channel chunk, d < 16
+    ((16, 16, 6), 32, 1, None),             # d % 4 != 0: routed to the per-query kernel
+])
+@pytest.mark.parametrize("arith", ["cuda", "cpu"])
+def test_sample_grid_bit_identical_to_flat(dims, C, B, planes_grid, arith, monkeypatch):
+    """tp_sample3_grid_nhwc_f32 == tp_sample3_nhwc_f32 bit for bit: on the reference's lattices
+    (separable blocks), with every block-shape configuration, and on inputs where only some blocks
+    are lattices (in-launch fallback)."""
+    planes, pts, lo, vs, half = _grid_case(dims, C, B, seed=11 + C, planes_grid=planes_grid)
+    q = pts.reshape(B, -1, 3)
+    flat = ops.sample3(planes, q, lo, vs, half, arith=arith)
+    for tile in ("", "0", "1"):
+        if tile:
+            monkeypatch.setenv("TP_GRID_TILE", tile)
+        got = ops.sample3(planes, q, lo, vs, half, arith=arith, grid_dims=dims)
+        assert torch.equal(got, flat), f"lattice path differs (TP_GRID_TILE={tile!r})"
+    monkeypatch.delenv("TP_GRID_TILE", raising=False)
+    # break separability in a few places: those blocks must take the fallback, the rest the tables
+    g = torch.Generator().manual_seed(5)
+    jit = pts.clone()
+    n = max(1, q.shape[1] // 500)
+    idx = torch.randint(0, q.shape[1], (n,), generator=g).to(DEV)
+    jit.view(B, -1, 3)[:, idx] += 0.173
+    jit.view(B, -1, 3)[0, 0, 2] = float("nan")
+    qj = jit.reshape(B, -1, 3)
+    flat = ops.sample3(planes, qj, lo, vs, half, arith=arith)
+    got = ops.sample3(planes, qj, lo, vs, half, arith=arith, grid_dims=dims)
+    same = (got == flat) | (torch.isnan(got) & torch.isnan(flat))
+    assert bool(same.all())
+    # no lattice structure at all
+    rnd = cu(torch.stack([synth.uniform_queries(q.shape[1], seed=70 + b) for b in range(B)])) * 1.1
+    assert torch.equal(ops.sample3(planes, rnd, lo, vs, half, arith=arith, grid_dims=dims),
+                       ops.sample3(planes, rnd, lo, vs, half, arith=arith))
+
+
+def test_sample_grid_through_module_signature_matches_torch_cuda():
+    """sample_points_triplane with 5-D points (the TriplaneOcc call) goes through the lattice entry
+    point and is bitwise what torch-CUDA's grid_sample chain gives on >= 99.9 % of elements."""
+    tri = cu(synth.triplane_stacked(2, 32, 128, seed=1002))
+    pts = cu(synth.roi_lattice())[None].repeat(2, 1, 1, 1, 1)
+    lo, vs = synth.OCC["triplane_range"], synth.OCC["triplane_voxel_size"]
+    before = ops.launch_count
+    out = sample_points_triplane(tri, pts, lo, vs)
+    assert out.shape == (2, 32, 99, 99, 16) and ops.launch_count == before + 2
+    ref = _torch_cuda_sample([tri[:, 0], tri[:, 1], tri[:, 2]], pts.reshape(2, -1, 3), lo, vs, [64.0] * 3)
+    assert normwise(out.reshape(2, 32, -1), ref) <= TOL
+    assert float((out.reshape(2, 32, -1) == ref).float().mean()) > 0.999
+
+
 def test_host_buffer_entry_points():
     """tp_sample3_host_f32 / tp_encode_host_f32 (what a non-PyTorch caller binds)."""
     import ctypes as C

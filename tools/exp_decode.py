@@ -1,0 +1,96 @@
+"""Experiment: decode kernel timings, flat (per-query) vs lattice entry point, per block shape.
+usage: python tools/exp_decode.py"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from efficient_multimodal_perception_b200 import ops, synth  # noqa: E402
+
+dev = torch.device("cuda:0")
+LO, VS, HALF = [-25.0, -25.0, -5.0], (0.4, 0.4, 0.1), [64.0] * 3
+
+
+def timeit(fn, reps=200, group=20):
+    """Time `group` back-to-back launches replayed from one CUDA graph (launch overhead amortised the way
+    a real step sees it); returns avg / median / min per launch in us over reps // group replays."""
+    for i in range(group):
+        fn(i)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for i in range(group):
+            fn(i)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(group):
+            fn(i)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(max(3, reps // group)):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        g.replay()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) / group for a, b in evs)
+    return sum(ts) / len(ts) * 1e3, ts[len(ts) // 2] * 1e3, ts[0] * 1e3
+
+
+cases = {
+    "lattice640k": (synth.occ_gt_lattice(), 32),
+    "roi": (synth.roi_lattice(), 32),
+    "elev800k": (synth.lattice((100, 100, 80), (0.5, 0.5, 0.1), (-25.0, -25.0, -5.0)), 32),
+    "roi_x8": (synth.roi_lattice()[None].repeat(8, 1, 1, 1, 1), 32),
+}
+for name, (lat, C) in cases.items():
+    if lat.dim() == 4:
+        lat = lat[None]
+    B = lat.shape[0]
+    dims = tuple(lat.shape[1:4])
+    Q = dims[0] * dims[1] * dims[2]
+    per_set = B * Q * (12 + 4 * C)
+    nsets = max(4, -(-3 * 126 * 2**20 // per_set))
+    q = [lat.reshape(B, -1, 3).to(dev).clone() for _ in range(nsets)]
+    tris = [synth.triplane_stacked(B, C, 128, seed=1002 + s).to(dev) for s in range(min(nsets, 8))]
+    nhwc = [ops.planes_to_channels_last([t[:, 0], t[:, 1], t[:, 2]]) for t in tris]
+    outs = [torch.empty(B, C, Q, device=dev) for _ in range(nsets)]
+    byts = B * (Q * (12 + 4 * C) + 4 * C * 3 * 128 * 128)
+
+    def flat(i):
+        ops.sample3(nhwc[i % len(nhwc)], q[i % nsets], LO, VS, HALF, channels_last=True, out=outs[i % nsets])
+
+    def grid(i):
+        ops.sample3(nhwc[i % len(nhwc)], q[i % nsets], LO, VS, HALF, channels_last=True, out=outs[i % nsets], grid_dims=dims)
+
+    a, m, mn = timeit(flat)
+    print(f"{name:12s} B={B} Q={Q} flat      avg {a:7.1f} us med {m:7.1f} min {mn:7.1f}  {byts / a / 1e3:7.0f} GB/s", flush=True)
+    for tile in ("0", "1", ""):
+        if tile:
+            os.environ["TP_GRID_TILE"] = tile
+        else:
+            os.environ.pop("TP_GRID_TILE", None)
+        a, m, mn = timeit(grid)
+        print(f"{name:12s} B={B} Q={Q} grid[{tile or 'auto'}] avg {a:7.1f} us med {m:7.1f} min {mn:7.1f}  {byts / a / 1e3:7.0f} GB/s", flush=True)
+    os.environ.pop("TP_GRID_TILE", None)
+    for ctas in ("296", "444", "592"):
+        os.environ["TP_GRID_CTAS"] = ctas
+        for tile in ("0", "1"):
+            os.environ["TP_GRID_TILE"] = tile
+            a, m, mn = timeit(grid)
+            print(f"{name:12s} ctas={ctas} tile={tile} avg {a:7.1f} us med {m:7.1f} min {mn:7.1f}  {byts / a / 1e3:7.0f} GB/s", flush=True)
+    os.environ.pop("TP_GRID_CTAS", None)
+    os.environ.pop("TP_GRID_TILE", None)
+    ref = torch.empty_like(outs[0])
+    ops.sample3(nhwc[0], q[0], LO, VS, HALF, channels_last=True, out=ref)
+    ops.sample3(nhwc[0], q[0], LO, VS, HALF, channels_last=True, out=outs[0], grid_dims=dims)
+    print(f"{name:12s} bit-identical: {bool(torch.equal(ref, outs[0]))}")
+    z = outs[0]
+    a, m, mn = timeit(lambda i: outs[i % nsets].zero_())
+    print(f"{name:12s} torch zero_ of the output: avg {a:7.1f} us  ({B * Q * 4 * C / a / 1e3:7.0f} GB/s)")
+    del q, outs, tris, nhwc

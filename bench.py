@@ -61,6 +61,10 @@ def decode_queries(kind: str):
     raise SystemExit(f"unknown --queries {kind}")
 
 
+#: [h, w, d] of the query tensors the reference passes as [B,h,w,d,3] (5-D callers); None = a flat point list
+QUERY_DIMS = {"lattice640k": (200, 200, 16), "roi": (99, 99, 16), "uniform640k": None}
+
+
 def ncu_traffic(kernel: str, key: str):
     """dram bytes per launch from the committed ncu capture (profiles/), or None."""
     try:
@@ -123,21 +127,22 @@ class ClockSampler(threading.Thread):
 class DecodeSets:
     """nsets disjoint (planes, queries, out) buffer sets + CUDA graphs of the 2-launch step."""
 
-    def __init__(self, q_host: torch.Tensor, nsets: int, dev):
+    def __init__(self, q_host: torch.Tensor, nsets: int, dev, dims=None):
         from efficient_multimodal_perception_b200 import ops, synth
-        self.ops, self.dev, self.nsets = ops, dev, nsets
+        self.ops, self.dev, self.nsets, self.dims = ops, dev, nsets, dims
         self.Q = q_host.shape[1]
         self.sets = []
         for s in range(nsets):
             tri = synth.triplane_stacked(1, C_DEC, PLANE, seed=1002 + s).to(dev)
-            q = q_host.to(dev) if s == 0 else q_host.roll(s * 1013, 1).to(dev)
+            # every set has its own query buffer; point lists are also rotated, lattices keep their [h,w,d] order
+            q = q_host.to(dev).clone() if (s == 0 or dims is not None) else q_host.roll(s * 1013, 1).to(dev)
             out = torch.empty(1, C_DEC, self.Q, device=dev)
             self.sets.append((tri, q, out))
         self.graph_all = self.graph_one = None
 
     def step(self, s: int):
         tri, q, out = self.sets[s % self.nsets]
-        self.ops.sample3(tri, q, OCC_LO, OCC_VS, OCC_HALF, out=out)
+        self.ops.sample3(tri, q, OCC_LO, OCC_VS, OCC_HALF, out=out, grid_dims=self.dims)
 
     def capture(self):
         torch.cuda.synchronize()
@@ -179,19 +184,31 @@ def time_region(fn, barrier):
     return a.elapsed_time(b)
 
 
-def kernel_time_ms(launch, reps: int, pre=None):
-    """Average CUDA-event duration of a single kernel launch (events around the launch only)."""
+def kernel_time_ms(launch, reps: int, group: int):
+    """Average duration of ONE launch of a kernel: `group` back-to-back launches (one per rotating buffer set)
+    are captured in a CUDA graph, CUDA events bracket each replay, duration = elapsed / group. Events around a
+    single ~20 us launch would add the event/launch latency (~4 us) to every sample."""
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for i in range(group):
+            launch(i)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(group):
+            launch(i)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
     evs = []
-    for i in range(reps):
-        if pre:
-            pre(i)
+    for _ in range(max(3, reps // group)):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        launch(i)
+        g.replay()
         b.record()
         evs.append((a, b))
     torch.cuda.synchronize()
-    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    ts = sorted(a.elapsed_time(b) / group for a, b in evs)
     return sum(ts) / len(ts), ts[len(ts) // 2], ts[0]
 
 
@@ -200,7 +217,8 @@ def bench_decode_device(args, dev, barrier, sampler):
     Q = q_host.shape[1]
     per_set = decode_bytes(Q) + 4 * C_DEC * 3 * PLANE * PLANE  # + the channels-last copy
     nsets = max(4, -(-3 * L2_BYTES // per_set))
-    sets = DecodeSets(q_host, nsets, dev)
+    dims = QUERY_DIMS[args.queries]
+    sets = DecodeSets(q_host, nsets, dev, dims)
     sets.capture()
     sets.run_steps(args.warmup)
     sampler.active.set()
@@ -212,29 +230,31 @@ def bench_decode_device(args, dev, barrier, sampler):
 
     def launch(i):
         _, q, out = sets.sets[i % nsets]
-        ops.sample3(nhwc[i % nsets], q, OCC_LO, OCC_VS, OCC_HALF, channels_last=True, out=out)
+        ops.sample3(nhwc[i % nsets], q, OCC_LO, OCC_VS, OCC_HALF, channels_last=True, out=out, grid_dims=dims)
 
     for i in range(8):
         launch(i)
     torch.cuda.synchronize()
-    k_avg, k_med, k_min = kernel_time_ms(launch, reps)
+    k_avg, k_med, k_min = kernel_time_ms(launch, reps, nsets)
     # the other query sets of SURVEY 8(d) S2, gather kernel only, same rotation of plane / output sets
     variants = {}
     for kind in ("lattice640k", "uniform640k", "roi"):
         if kind == args.queries:
             continue
         qv = decode_queries(kind)
-        qs = [qv.roll(s * 1013, 1).to(dev) for s in range(nsets)]
-        outs = [sets.sets[s][2][:, :, :qv.shape[1]].contiguous() for s in range(nsets)]
+        vdims = QUERY_DIMS[kind]
+        vsets = max(nsets, -(-3 * L2_BYTES // decode_bytes(qv.shape[1])))
+        qs = [qv.to(dev).clone() if vdims is not None else qv.roll(s * 1013, 1).to(dev) for s in range(vsets)]
+        outs = [torch.empty(1, C_DEC, qv.shape[1], device=dev) for s in range(vsets)]
 
-        def launch_v(i):
-            ops.sample3(nhwc[i % nsets], qs[i % nsets], OCC_LO, OCC_VS, OCC_HALF, channels_last=True,
-                        out=outs[i % nsets])
+        def launch_v(i, qs=qs, outs=outs, vdims=vdims, vsets=vsets):
+            ops.sample3(nhwc[i % nsets], qs[i % vsets], OCC_LO, OCC_VS, OCC_HALF, channels_last=True,
+                        out=outs[i % vsets], grid_dims=vdims)
 
         for i in range(8):
             launch_v(i)
         torch.cuda.synchronize()
-        va, vm, vmin = kernel_time_ms(launch_v, min(reps, 200))
+        va, vm, vmin = kernel_time_ms(launch_v, min(reps, 200), vsets)
         vb = decode_bytes(qv.shape[1])
         variants[kind] = {"Q": qv.shape[1], "kernel_ms_avg": va, "kernel_ms_median": vm, "queries_per_s": qv.shape[1] / (va * 1e-3),
                           "algorithmic_bytes": vb, "achieved_gbs": vb / (va * 1e-3) / 1e9}
@@ -259,9 +279,17 @@ def bench_decode_e2e(args, Q_host, barrier):
     bs = (C.c_int64 * 3)(*[tri.stride(0)] * 3)
     sg = L.make_sample_geom(OCC_LO, OCC_VS, OCC_HALF)
 
+    dims = QUERY_DIMS[args.queries]
+    cdims = (C.c_int32 * 3)(*dims) if dims else None
+
     def call():
-        L.check(lib.tp_sample3_host_f32(C.byref(ptrs), C.byref(hw), C.byref(bs), C_DEC, q.data_ptr(), Q, 1,
-                                        C.byref(sg), L.TP_ARITH_TORCH_CUDA, out.data_ptr()), "tp_sample3_host_f32")
+        if dims:
+            L.check(lib.tp_sample3_grid_host_f32(C.byref(ptrs), C.byref(hw), C.byref(bs), C_DEC, q.data_ptr(),
+                                                 C.byref(cdims), 1, C.byref(sg), L.TP_ARITH_TORCH_CUDA,
+                                                 out.data_ptr()), "tp_sample3_grid_host_f32")
+        else:
+            L.check(lib.tp_sample3_host_f32(C.byref(ptrs), C.byref(hw), C.byref(bs), C_DEC, q.data_ptr(), Q, 1,
+                                            C.byref(sg), L.TP_ARITH_TORCH_CUDA, out.data_ptr()), "tp_sample3_host_f32")
 
     steps = max(5, min(args.steps, 100))
     for _ in range(3):
@@ -399,6 +427,7 @@ def run_b200(args):
         qps = world * Q * args.steps / (ms_total * 1e-3)
         kbytes = decode_bytes(Q)
         achieved = kbytes / (k_avg * 1e-3) / 1e9
+        kernel_name = ("tp::sample3_grid_kernel<0,8,8>" if QUERY_DIMS[args.queries] else "tp::sample3_kernel<0,8>")
         cpu, parity = None, None
         if world == 1:
             cpu, ref = cpu_baseline_decode(q_host)
@@ -407,7 +436,8 @@ def run_b200(args):
             dec["sets"].step(0)
             torch.cuda.synchronize()
             scale = float(ref.abs().max())
-            out_cpu_arith = dec["sets"].ops.sample3(tri0, q0, OCC_LO, OCC_VS, OCC_HALF, arith="cpu")
+            out_cpu_arith = dec["sets"].ops.sample3(tri0, q0, OCC_LO, OCC_VS, OCC_HALF, arith="cpu",
+                                                    grid_dims=QUERY_DIMS[args.queries])
             parity = {"note": "oracle = torch-CPU op chain; arith='cpu' replays it, the timed arith='cuda' replays "
                               "torch-CUDA's (x * fp32(1/vs)) and is checked bitwise-level against torch-CUDA in tests/",
                       "device_cpu_arith_vs_oracle_normwise": float((out_cpu_arith.cpu() - ref[:, :, 0]).abs().max()) / scale,
@@ -421,12 +451,15 @@ def run_b200(args):
             "config": {"workload": f"configs/triplane_occ.py occupancy decode: {Q} voxel queries ({args.queries}) "
                                    f"x C={C_DEC} from 3 fp32 {PLANE}x{PLANE} triplanes, bs=1 per GPU",
                        "queries": args.queries, "Q": Q, "C": C_DEC, "planes": [PLANE, PLANE],
+                       "query_tensor": (f"[1,{','.join(map(str, QUERY_DIMS[args.queries]))},3] through the 5-D entry point "
+                                        "tp_sample3_grid_nhwc_f32 (per-block lattice detection on the device)"
+                                        if QUERY_DIMS[args.queries] else "[1,Q,3] point list through tp_sample3_nhwc_f32"),
                        "step": "NCHW->NHWC conversion of the 3 planes (1 launch) + fused gather kernel (1 launch), CUDA-graph replay",
                        "l2": f"{dec['nsets']} rotating buffer sets, total footprint "
                              f"{dec['nsets'] * (kbytes + 4 * C_DEC * 3 * PLANE * PLANE) / 1e6:.0f} MB > 3x L2 (no flush kernel)",
                        "parallelism": f"queries sharded over {world} GPU(s), no collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic("sample3_kernel", args.queries), "kernel": "tp::sample3_kernel<0,8>",
+                         "traffic": ncu_traffic(kernel_name.split("<")[0].replace("tp::", ""), args.queries), "kernel": kernel_name,
                          "algorithmic_bytes": kbytes,
                          "kernel_ms_avg": k_avg, "kernel_ms_median": dec["kernel_ms_med"],
                          "kernel_ms_min": dec["kernel_ms_min"], "peak_source": peak_src,
@@ -434,7 +467,7 @@ def run_b200(args):
             "cpu_baseline": cpu,
             "e2e": {"value": world * Q / (e2e_ms * 1e-3), "unit": "queries/s",
                     "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e_ms,
-                    "steps": e2e["steps"], "api": "tp_sample3_host_f32 (C ABI, pinned host buffers; H2D planes+queries, "
+                    "steps": e2e["steps"], "api": "tp_sample3_grid_host_f32 / tp_sample3_host_f32 (C ABI, pinned host buffers; H2D planes+queries, "
                                                   "D2H full result, synchronised every step)"},
             "gpu_launches": dec["launches"],
             "variants_kernel_only": {k: dict(v, frac=v["achieved_gbs"] / peak) for k, v in dec["variants"].items()},

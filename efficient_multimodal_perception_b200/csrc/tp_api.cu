@@ -72,18 +72,18 @@ extern "C" void tp_host_arena_release(void) {
   A = Arena();
 }
 
-extern "C" int tp_sample3_host_f32(const float* planes_host[3], const int32_t HW[6],
-                                   const int64_t plane_batch_stride[3], int32_t C,
-                                   const float* queries_host, int64_t Q, int32_t batch,
-                                   const tp_sample_geom* sg, int32_t arith, float* out_host) {
+static int sample3_host_impl(const float* planes_host[3], const int32_t HW[6],
+                             const int64_t plane_batch_stride[3], int32_t C,
+                             const float* queries_host, int64_t Q, const int32_t* dims, int32_t batch,
+                             const tp_sample_geom* sg, int32_t arith, float* out_host) {
   if (!planes_host || !HW || !plane_batch_stride || !queries_host || !out_host || !sg)
-    return fail(TP_E_NULL, "tp_sample3_host_f32: null argument");
-  if (C <= 0 || (C & 3) || batch <= 0 || Q < 0) return fail(TP_E_SHAPE, "tp_sample3_host_f32: C=%d B=%d Q=%lld", C, batch, (long long)Q);
+    return fail(TP_E_NULL, "tp_sample3_host: null argument");
+  if (C <= 0 || (C & 3) || batch <= 0 || Q < 0) return fail(TP_E_SHAPE, "tp_sample3_host: C=%d B=%d Q=%lld", C, batch, (long long)Q);
   if (Q == 0) return 0;
   Arena& A = g_arena;
   size_t plane_elems[3], total = 0;
   for (int k = 0; k < 3; ++k) {
-    if (!planes_host[k]) return fail(TP_E_NULL, "tp_sample3_host_f32: plane %d null", k);
+    if (!planes_host[k]) return fail(TP_E_NULL, "tp_sample3_host: plane %d null", k);
     plane_elems[k] = (size_t)C * HW[2 * k] * HW[2 * k + 1];
     total += 2 * Arena::pad(plane_elems[k] * batch * 4);  // NCHW copy + NHWC copy
   }
@@ -113,10 +113,29 @@ extern "C" int tp_sample3_host_f32(const float* planes_host[3], const int32_t HW
   float* dq = A.take<float>((size_t)batch * Q * 3);
   float* dout = A.take<float>((size_t)batch * C * Q);
   TP_CUDA(cudaMemcpyAsync(dq, queries_host, qbytes, cudaMemcpyHostToDevice, s));
-  if (int rc = tp_sample3_nhwc_f32(nhwc, C, dq, Q, batch, sg, arith, dout, s)) return rc;
+  if (int rc = dims ? tp_sample3_grid_nhwc_f32(nhwc, C, dq, dims, batch, sg, arith, dout, s)
+                    : tp_sample3_nhwc_f32(nhwc, C, dq, Q, batch, sg, arith, dout, s))
+    return rc;
   TP_CUDA(cudaMemcpyAsync(out_host, dout, obytes, cudaMemcpyDeviceToHost, s));
   TP_CUDA(cudaStreamSynchronize(s));
   return 0;
+}
+
+extern "C" int tp_sample3_host_f32(const float* planes_host[3], const int32_t HW[6],
+                                   const int64_t plane_batch_stride[3], int32_t C,
+                                   const float* queries_host, int64_t Q, int32_t batch,
+                                   const tp_sample_geom* sg, int32_t arith, float* out_host) {
+  return sample3_host_impl(planes_host, HW, plane_batch_stride, C, queries_host, Q, nullptr, batch, sg, arith,
+                           out_host);
+}
+
+extern "C" int tp_sample3_grid_host_f32(const float* planes_host[3], const int32_t HW[6],
+                                        const int64_t plane_batch_stride[3], int32_t C,
+                                        const float* queries_host, const int32_t dims[3], int32_t batch,
+                                        const tp_sample_geom* sg, int32_t arith, float* out_host) {
+  if (!dims || dims[0] < 0 || dims[1] < 0 || dims[2] < 0) return fail(TP_E_SHAPE, "tp_sample3_grid_host_f32: bad dims");
+  return sample3_host_impl(planes_host, HW, plane_batch_stride, C, queries_host,
+                           (int64_t)dims[0] * dims[1] * dims[2], dims, batch, sg, arith, out_host);
 }
 
 extern "C" int tp_encode_host_f32(const float* feats_host, int32_t C, const float* points_host,

@@ -208,6 +208,11 @@ TP_API int tp_sample3_host_f32(const float* planes_nchw_host[3], const int32_t H
                         const int64_t plane_batch_stride[3], int32_t C,
                         const float* queries_host, int64_t Q, int32_t batch,
                         const tp_sample_geom* sg, int32_t arith, float* out_host);
+/* same, for a [B,h,w,d,3] query tensor (tp_sample3_grid_nhwc_f32 on the device); dims = {h, w, d} */
+TP_API int tp_sample3_grid_host_f32(const float* planes_nchw_host[3], const int32_t HW[6],
+                             const int64_t plane_batch_stride[3], int32_t C,
+                             const float* queries_host, const int32_t dims[3], int32_t batch,
+                             const tp_sample_geom* sg, int32_t arith, float* out_host);
 TP_API int tp_encode_host_f32(const float* feats_host, int32_t C, const float* points_host,
                        int32_t point_stride, int64_t n_total, const int64_t* offsets_host,
                        int32_t batch, const tp_geom* geom, int32_t arith, int32_t reduce,

@@ -78,13 +78,11 @@ for name, (lat, C) in cases.items():
         a, m, mn = timeit(grid)
         print(f"{name:12s} B={B} Q={Q} grid[{tile or 'auto'}] avg {a:7.1f} us med {m:7.1f} min {mn:7.1f}  {byts / a / 1e3:7.0f} GB/s", flush=True)
     os.environ.pop("TP_GRID_TILE", None)
-    for ctas in ("296", "444", "592"):
-        os.environ["TP_GRID_CTAS"] = ctas
-        for tile in ("0", "1"):
-            os.environ["TP_GRID_TILE"] = tile
-            a, m, mn = timeit(grid)
-            print(f"{name:12s} ctas={ctas} tile={tile} avg {a:7.1f} us med {m:7.1f} min {mn:7.1f}  {byts / a / 1e3:7.0f} GB/s", flush=True)
-    os.environ.pop("TP_GRID_CTAS", None)
+    for flags in ("0", "1", "2", "3"):
+        os.environ["TP_GRID_FLAGS"] = flags
+        a, m, mn = timeit(grid)
+        print(f"{name:12s} flags={flags} avg {a:7.1f} us med {m:7.1f} min {mn:7.1f}  {byts / a / 1e3:7.0f} GB/s", flush=True)
+    os.environ.pop("TP_GRID_FLAGS", None)
     os.environ.pop("TP_GRID_TILE", None)
     ref = torch.empty_like(outs[0])
     ops.sample3(nhwc[0], q[0], LO, VS, HALF, channels_last=True, out=ref)

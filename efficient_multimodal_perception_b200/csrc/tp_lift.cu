@@ -1,0 +1,178 @@
+// Camera -> point lift: PointTriplane.point_to_cam (point_triplane.py:164-241, twin
+// point_triplane_occ.py:163-239). For every LiDAR point: project with each camera's lidar2image
+// matrix, perspective divide, image augmentation (resize, crop, flip, the identity rotation),
+// in-image test, then a bilinear sample of that camera's feature map (zeros padding,
+// align_corners=False; the reference feeds the image ROW as grid-x, :230-235) summed over the
+// cameras that see the point. The reference runs B x 6 Python iterations of ~15 small kernels plus
+// a boolean-mask gather/scatter each; here it is one launch, one read of each point and one write
+// of its feature row.
+//
+// Feature maps are read channels-last [B, ncam, Hf, Wf, Cf] (tp_planes_nchw_to_nhwc_f32 with
+// batch = B * ncam converts the encoder's NCHW output): a tap is Cf contiguous floats, a warp reads
+// 512 contiguous bytes per instruction.
+#include "tp_sample_dev.cuh"
+
+namespace tp {
+
+constexpr int kLiftPts = 8;    // points per warp tile
+constexpr int kLiftCams = 8;   // camera slots per point (2 per lane in the projection phase)
+constexpr int kLiftWarps = 4;
+
+struct LiftParams {
+  const float* points;     // [N, point_stride], xyz first
+  const int64_t* offsets;  // [B+1]
+  const float* feats;      // [B, ncam, Hf, Wf, Cf]
+  const float* cams;       // [B, ncam, 20]: lidar2image row-major 4x4, resize, crop_x, crop_y, flip
+  float* out;              // [N, Cf]
+  int64_t n_total;
+  int point_stride, batch, ncam, Hf, Wf, Cf;
+  float R0, R1;            // resize_dims = img_shape[::-1]  (point_triplane.py:176)
+  float half0, half1;      // R0 / 2.0, R1 / 2.0
+  float rcp0, rcp1;        // fp32(1 / R0), fp32(1 / R1)
+};
+
+// one (point, camera): 4 bilinear weights + nw tap offset (in float4 units) + in-bounds mask (0 = the
+// camera does not see the point)
+template <int ARITH>
+__device__ __forceinline__ void lift_setup(const LiftParams& P, const float* __restrict__ cam, float px, float py,
+                                           float pz, float4& w, int& off, int& mask) {
+  // einsum("cij,hj->chi"): sum_j M[i][j] * hom[j], fp32 fma chain in j order from 0
+  float c[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float a = __fmaf_rn(__ldg(cam + 4 * i), px, 0.f);
+    a = __fmaf_rn(__ldg(cam + 4 * i + 1), py, a);
+    a = __fmaf_rn(__ldg(cam + 4 * i + 2), pz, a);
+    c[i] = __fmaf_rn(__ldg(cam + 4 * i + 3), 1.0f, a);
+  }
+  const float z = fmaxf(c[2], 1e-5f);  // torch.maximum(z, 1e-5) (NaN propagates below through the compares)
+  float x = __fdiv_rn(c[0], z), y = __fdiv_rn(c[1], z);
+  const float resize = __ldg(cam + 16), crop_x = __ldg(cam + 17), crop_y = __ldg(cam + 18);
+  const bool flip = __ldg(cam + 19) != 0.f;
+  x = __fsub_rn(__fmul_rn(x, resize), crop_x);
+  y = __fsub_rn(__fmul_rn(y, resize), crop_y);
+  if (flip) x = __fsub_rn(P.R1, x);
+  // "-= W/2, rotate by 0, += W/2" (:211-221): the rotation is the identity on finite values, the
+  // subtract/add pair is not (it rounds twice) and is replayed
+  x = __fadd_rn(__fsub_rn(x, P.half1), P.half1);
+  y = __fadd_rn(__fsub_rn(y, P.half0), P.half0);
+  const bool valid = (y < P.R0) & (x < P.R1) & (y >= 0.f) & (x >= 0.f) & !isnan(c[2]);
+  // swap to (row, col); normalise 2*row/H - 1, 2*col/W - 1 with H = R0, W = R1 (:229-233)
+  float g0 = __fmul_rn(2.0f, y), g1 = __fmul_rn(2.0f, x);
+  g0 = (ARITH == TP_ARITH_TORCH_CPU) ? __fdiv_rn(g0, P.R0) : __fmul_rn(g0, P.rcp0);
+  g1 = (ARITH == TP_ARITH_TORCH_CPU) ? __fdiv_rn(g1, P.R1) : __fmul_rn(g1, P.rcp1);
+  g0 = __fsub_rn(g0, 1.0f);
+  g1 = __fsub_rn(g1, 1.0f);
+  // grid[..., 0] = row -> feature-map x (width Wf); grid[..., 1] = col -> feature-map y (height Hf)
+  int base;
+  plane_setup<ARITH>(g0, g1, P.Wf, P.Hf, w, base, mask);
+  if (!valid) mask = 0;
+  off = mask ? base * (P.Cf >> 2) : 0;
+  // a camera that sees the point but whose 4 taps are all outside still contributes +0 (no effect)
+}
+
+template <int ARITH>
+__global__ void __launch_bounds__(kLiftWarps * 32)
+lift_kernel(const LiftParams P) {
+  __shared__ __align__(16) float4 s_w[kLiftWarps][kLiftPts * kLiftCams];
+  __shared__ __align__(8) int2 s_om[kLiftWarps][kLiftPts * kLiftCams];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t tile = (int64_t)blockIdx.x * kLiftWarps + warp;
+  const int64_t p0 = tile * kLiftPts;
+  if (p0 >= P.n_total) return;
+  const unsigned long long pol_feat = policy_evict_last(), pol_out = policy_evict_first();
+  const int C4 = P.Cf >> 2;
+
+  // ---- projection: lane -> (point lane & 7, cameras lane >> 3 and (lane >> 3) + 4) -------------
+  {
+    const int pi = lane & 7;
+    const int64_t p = p0 + pi;
+    const bool pv = p < P.n_total;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    int b = 0;
+    if (pv) {
+      const float* pp = P.points + p * P.point_stride;
+      px = __ldg(pp); py = __ldg(pp + 1); pz = __ldg(pp + 2);
+      b = tp_find_batch(P.offsets, P.batch, p);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int cam = (lane >> 3) + 4 * h;
+      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+      int off = 0, mask = 0, seen = 0;
+      if (pv && cam < P.ncam) {
+        lift_setup<ARITH>(P, P.cams + ((int64_t)b * P.ncam + cam) * 20, px, py, pz, w, off, mask);
+        seen = mask != 0;
+      }
+      s_w[warp][pi * kLiftCams + cam] = w;
+      // bits 0-3: tap mask; the map index rides in the offset: + (b * ncam + cam) * Hf * Wf * C4
+      s_om[warp][pi * kLiftCams + cam] =
+          make_int2(off, seen ? (mask | ((b * P.ncam + cam) << 4)) : 0);
+    }
+  }
+  __syncwarp();
+
+  // ---- gather: the whole warp per point, 512 contiguous bytes per load instruction ---------------
+  const int64_t map4 = (int64_t)P.Hf * P.Wf * C4;  // float4 per feature map
+  const int WC4 = P.Wf * C4;
+  const float4* feats = reinterpret_cast<const float4*>(P.feats);
+  for (int pi = 0; pi < kLiftPts; ++pi) {
+    const int64_t p = p0 + pi;
+    if (p >= P.n_total) break;
+    float4* orow = reinterpret_cast<float4*>(P.out + p * P.Cf);
+#pragma unroll 2
+    for (int c4 = lane; c4 < C4; c4 += 32) {
+      float4 total = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int cam = 0; cam < P.ncam; ++cam) {
+        const int2 om = s_om[warp][pi * kLiftCams + cam];
+        if (om.y == 0) continue;  // warp-uniform
+        const float4 w = s_w[warp][pi * kLiftCams + cam];
+        const float4* pl = feats + (int64_t)(om.y >> 4) * map4 + c4;
+        const float4 f = plane_taps<true>(pl, om.x, C4, WC4, w, om.y & 15, pol_feat);
+        // point_feature[valid] += features (:236), cameras in ascending order from zeros
+        total.x = __fadd_rn(total.x, f.x);
+        total.y = __fadd_rn(total.y, f.y);
+        total.z = __fadd_rn(total.z, f.z);
+        total.w = __fadd_rn(total.w, f.w);
+      }
+      st_stream_f4(orow + c4, total, pol_out);
+    }
+  }
+}
+
+}  // namespace tp
+
+using namespace tp;
+
+extern "C" int tp_lift_cam_f32(const float* points, int32_t point_stride, int64_t n_total,
+                               const int64_t* offsets, int32_t batch, const float* feats_nhwc,
+                               int32_t ncam, int32_t Hf, int32_t Wf, int32_t Cf, const float* cams,
+                               float resize_dim0, float resize_dim1, int32_t arith, float* out,
+                               void* stream) {
+  if (n_total < 0 || batch <= 0 || point_stride < 3) return fail(TP_E_SHAPE, "tp_lift_cam_f32: bad N=%lld B=%d stride=%d", (long long)n_total, batch, point_stride);
+  if (ncam <= 0 || ncam > kLiftCams) return fail(TP_E_SHAPE, "tp_lift_cam_f32: ncam=%d must be in 1..%d", ncam, kLiftCams);
+  if (Hf <= 0 || Wf <= 0 || Cf <= 0 || (Cf & 3)) return fail(TP_E_SHAPE, "tp_lift_cam_f32: bad feature map %dx%dx%d (Cf %% 4 == 0)", Hf, Wf, Cf);
+  if ((int64_t)batch * ncam >= (1 << 27) || (int64_t)Hf * Wf * Cf >= ((int64_t)1 << 31))
+    return fail(TP_E_SHAPE, "tp_lift_cam_f32: feature maps too large");
+  if (n_total == 0) return 0;
+  if (!points || !offsets || !feats_nhwc || !cams || !out) return fail(TP_E_NULL, "tp_lift_cam_f32: null argument");
+  if (((uintptr_t)feats_nhwc & 15) || ((uintptr_t)out & 15)) return fail(TP_E_SHAPE, "tp_lift_cam_f32: feats / out not 16-byte aligned");
+  LiftParams P;
+  P.points = points; P.offsets = offsets; P.feats = feats_nhwc; P.cams = cams; P.out = out;
+  P.n_total = n_total; P.point_stride = point_stride; P.batch = batch; P.ncam = ncam;
+  P.Hf = Hf; P.Wf = Wf; P.Cf = Cf;
+  P.R0 = resize_dim0; P.R1 = resize_dim1;
+  P.half0 = (float)((double)resize_dim0 / 2.0); P.half1 = (float)((double)resize_dim1 / 2.0);
+  P.rcp0 = 1.0f / resize_dim0; P.rcp1 = 1.0f / resize_dim1;
+  const int64_t tiles = (n_total + kLiftPts - 1) / kLiftPts;
+  const int64_t ctas = (tiles + kLiftWarps - 1) / kLiftWarps;
+  if (ctas >= ((int64_t)1 << 31)) return fail(TP_E_SHAPE, "tp_lift_cam_f32: too many points");
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (arith) {
+    case TP_ARITH_TORCH_CUDA: lift_kernel<TP_ARITH_TORCH_CUDA><<<(unsigned)ctas, kLiftWarps * 32, 0, s>>>(P); break;
+    case TP_ARITH_TORCH_CPU:  lift_kernel<TP_ARITH_TORCH_CPU><<<(unsigned)ctas, kLiftWarps * 32, 0, s>>>(P); break;
+    default: return fail(TP_E_ENUM, "tp_lift_cam_f32: unknown arith %d", arith);
+  }
+  TP_LAUNCH_CHECK("lift_kernel");
+  return 0;
+}

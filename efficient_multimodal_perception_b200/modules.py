@@ -117,6 +117,27 @@ def voxelize_points(points: Sequence[torch.Tensor], pc_range, voxel_size, arith:
     return cropped, grid_ind
 
 
+def point_to_cam(points: Sequence[torch.Tensor], img_features: torch.Tensor, img_metas, arith: str = "cuda"):
+    """point_triplane.py:164-241: list of [N_b, >=3] points, img_features [B,ncam,Cf,Hf,Wf], the
+    reference's img_metas -> list of [N_b, Cf] camera features per point. One launch for the whole
+    batch and all cameras (plus the channels-last copy of the feature maps)."""
+    dev = img_features.device
+    resize_dims = img_metas[0]["img_shape"][::-1]
+    cams = ops.pack_cameras(img_metas, dev)
+    sizes = [p.shape[0] for p in points]
+    cat = torch.cat([p[:, :3] for p in points], dim=0) if len(points) > 1 else points[0][:, :3]
+    offsets = _offsets(sizes, dev)
+    if torch.is_grad_enabled() and img_features.requires_grad:
+        from .autograd import lift_cam_autograd
+        out = lift_cam_autograd(cat, offsets, img_features, cams, resize_dims, arith)
+    else:
+        out = ops.lift_cam(cat, offsets, img_features, cams, resize_dims, arith=arith)
+    bounds = [0]
+    for n in sizes:
+        bounds.append(bounds[-1] + n)
+    return [out[bounds[i]:bounds[i + 1]] for i in range(len(points))]
+
+
 def sample_points_triplane(triplane: Union[torch.Tensor, Sequence[torch.Tensor]], points: torch.Tensor, lo, vs,
                            grid_size=None, arith: str = "cuda") -> torch.Tensor:
     """All five reference variants. Stacked [B,3,C,H,W]: every axis is normalised by
@@ -177,6 +198,9 @@ class TriplaneHotPathMixin:
 
     def voxelize_points(self, points):
         return voxelize_points(points, self.pc_range, self.voxel_size, self.tp_arith)
+
+    def point_to_cam(self, points, img_features, img_metas):
+        return point_to_cam(points, img_features, img_metas, self.tp_arith)
 
     def sample_points_triplane(self, triplane, points):
         lo, vs = self._tp_geometry()

@@ -303,3 +303,68 @@ def sample3(planes: Union[torch.Tensor, Sequence[torch.Tensor]], queries: torch.
                                             _ARITH[arith], out.data_ptr(), _stream(queries)), "tp_sample3_nhwc_f32")
     launch_count += 1 if Q else 0
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# a2
+# ------------------------------------------------------------------------------------------------
+def pack_cameras(img_metas, device) -> torch.Tensor:
+    """img_metas (the reference's per-sample dicts: 'lidar2image' [ncam,4,4], 'imgs_aug' list of
+    dict(resize, crop, flip)) -> [B, ncam, 20] fp32 on `device` for tp_lift_cam_f32. Host-side packing
+    of ~1 KB; the reference uploads the same matrices every call (point_triplane.py:183-184)."""
+    import numpy as np
+    rows = []
+    for meta in img_metas:
+        l2i = np.asarray(meta["lidar2image"], dtype=np.float64)
+        augs = meta["imgs_aug"]
+        per = np.zeros((l2i.shape[0], 20), dtype=np.float32)
+        per[:, :16] = l2i.reshape(l2i.shape[0], 16).astype(np.float32)  # new_tensor(float64) -> fp32
+        for c, aug in enumerate(augs):
+            per[c, 16] = np.float32(aug["resize"])
+            per[c, 17] = np.float32(aug["crop"][0])
+            per[c, 18] = np.float32(aug["crop"][1])
+            per[c, 19] = 1.0 if aug["flip"] else 0.0
+        rows.append(per)
+    return torch.from_numpy(np.stack(rows)).to(device, non_blocking=True)
+
+
+def features_to_channels_last(img_features: torch.Tensor) -> torch.Tensor:
+    """[B, ncam, Cf, Hf, Wf] (camera encoder output) -> contiguous [B, ncam, Hf, Wf, Cf]."""
+    global launch_count
+    _need_cuda(img_features, "img_features")
+    if img_features.dim() != 5:
+        raise TriplaneError(f"img_features must be [B,ncam,C,H,W], got {tuple(img_features.shape)}")
+    img_features = img_features.contiguous()
+    B, ncam, Cf, Hf, Wf = img_features.shape
+    out = torch.empty((B, ncam, Hf, Wf, Cf), dtype=torch.float32, device=img_features.device)
+    L.check(L.lib().tp_planes_nchw_to_nhwc_f32(img_features.data_ptr(), Cf * Hf * Wf, out.data_ptr(), B * ncam, Cf, Hf,
+                                               Wf, _stream(img_features)), "tp_planes_nchw_to_nhwc_f32")
+    launch_count += 1
+    return out
+
+
+def lift_cam(points: torch.Tensor, offsets: torch.Tensor, img_features: torch.Tensor, cams: torch.Tensor,
+             resize_dims, *, arith: str = "cuda", channels_last: bool = False) -> torch.Tensor:
+    """Fused point_to_cam (point_triplane.py:164-241): points [N, >=3] (samples concatenated, offsets
+    [B+1] int64), img_features [B,ncam,Cf,Hf,Wf] (or the [B,ncam,Hf,Wf,Cf] copy with
+    channels_last=True), cams = pack_cameras(img_metas). Returns [N, Cf]."""
+    global launch_count
+    _need_cuda(points, "points")
+    _need_cuda(offsets, "offsets", torch.int64)
+    _need_cuda(cams, "cams")
+    points = points.contiguous()
+    feats = img_features if channels_last else features_to_channels_last(img_features)
+    _need_cuda(feats, "img_features")
+    if feats.dim() != 5 or not feats.is_contiguous():
+        raise TriplaneError("lift_cam: channels-last features must be contiguous [B,ncam,Hf,Wf,Cf]")
+    B, ncam, Hf, Wf, Cf = feats.shape
+    if tuple(cams.shape) != (B, ncam, 20) or offsets.numel() != B + 1:
+        raise TriplaneError(f"lift_cam: cams must be [{B},{ncam},20] and offsets [{B + 1}]")
+    cams = cams.contiguous()
+    n = points.shape[0]
+    out = torch.empty((n, Cf), dtype=torch.float32, device=points.device)
+    L.check(L.lib().tp_lift_cam_f32(points.data_ptr(), points.shape[1], n, offsets.data_ptr(), B, feats.data_ptr(),
+                                    ncam, Hf, Wf, Cf, cams.data_ptr(), float(resize_dims[0]), float(resize_dims[1]),
+                                    _ARITH[arith], out.data_ptr(), _stream(points)), "tp_lift_cam_f32")
+    launch_count += 1 if n else 0
+    return out

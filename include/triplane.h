@@ -200,6 +200,25 @@ TP_API int tp_sample3_grid_nchw_f32(const tp_plane planes_nchw[3], int32_t C,
                              void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * a2  point_to_cam — point_triplane.py:164-241 (twin point_triplane_occ.py:163-239)
+ *     einsum(lidar2image, hom_points) -> / max(z, 1e-5) -> * resize - crop (-> flip) -> the -W/2, rotate
+ *     by 0, +W/2 round trip -> in-image mask -> (row, col) normalised by resize_dims -> F.grid_sample
+ *     of that camera's feature map (row fed as grid-x) -> sum over the cameras that see the point.
+ *
+ * points      [n_total, point_stride] fp32 (xyz first), samples concatenated; offsets [B+1] int64 (device)
+ * feats_nhwc  [B, ncam, Hf, Wf, Cf] fp32 channels-last copy of img_features [B, ncam, Cf, Hf, Wf]
+ *             (tp_planes_nchw_to_nhwc_f32 with batch = B * ncam), Cf % 4 == 0, ncam <= 8
+ * cams        [B, ncam, 20] fp32 (device): lidar2image 4x4 row-major, resize, crop[0], crop[1], flip (0/1)
+ *             (img_metas[b]['lidar2image'][cam], ['imgs_aug'][cam], point_triplane.py:177-199)
+ * resize_dim0/1 = img_metas[0]['img_shape'][::-1]  (point_triplane.py:176)
+ * out         [n_total, Cf]: row n = sum over cameras of the bilinear sample; 0 where no camera sees it.
+ * ------------------------------------------------------------------------------------------- */
+TP_API int tp_lift_cam_f32(const float* points, int32_t point_stride, int64_t n_total,
+                    const int64_t* offsets, int32_t batch, const float* feats_nhwc,
+                    int32_t ncam, int32_t Hf, int32_t Wf, int32_t Cf, const float* cams,
+                    float resize_dim0, float resize_dim1, int32_t arith, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Host-buffer entry points (what a non-PyTorch caller binds; bench.py's `e2e` leg).
  * All pointers are HOST memory (pinned recommended). They allocate a per-thread cached device
  * arena, copy in, run the kernels above, copy out and synchronise the internal stream.

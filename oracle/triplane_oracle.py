@@ -251,7 +251,8 @@ def point_to_cam(points: Sequence[torch.Tensor], img_features: torch.Tensor, img
     lidar2imgs = points[0].new_tensor(lidar2imgs)
     cam_point_features = []
     for i, pts in enumerate(points):
-        point_feature = torch.zeros((pts.shape[0], img_features.shape[2]), dtype=img_features.dtype)
+        point_feature = torch.zeros((pts.shape[0], img_features.shape[2]), dtype=img_features.dtype,
+                                    device=img_features.device)
         lidar2img = lidar2imgs[i]
         hom_points = torch.cat((pts[:, 0:3], torch.ones_like(pts[..., :1])), -1)
         cam_points = torch.einsum("cij, hj->chi", lidar2img, hom_points)

@@ -7,8 +7,8 @@ import torch
 import torch.nn.functional as F
 
 from conftest import load_golden, normwise
-from efficient_multimodal_perception_b200 import (PointTriplaneProjector, ops, sample_points_triplane, synth,
-                                                  voxelize_points)
+from efficient_multimodal_perception_b200 import (PointTriplaneProjector, ops, point_to_cam, sample_points_triplane,
+                                                  synth, voxelize_points)
 from oracle import triplane_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -216,6 +216,92 @@ def test_projector_forward_vs_reference_golden(name):
                      g["grid"].tolist(), g["split"].tolist(), grid_ind=cu(torch.cat(inds)))
     for a, b in zip(got, ref[:3]):
         assert torch.equal(a.cpu(), b)
+
+
+# ---------------------------------------------------------------------------------------------
+# a2 camera -> point lift
+# ---------------------------------------------------------------------------------------------
+def _lift_metas(g, flips):
+    return [dict(img_shape=tuple(int(v) for v in g["img_shape"]), lidar2image=g["lidar2image"],
+                 imgs_aug=[dict(resize=float(r), crop=tuple(int(c) for c in cr), flip=bool(f))
+                           for r, cr, f in zip(g["resize"], g["crop"], fl)]) for fl in flips]
+
+
+def _seen_mask(pts, metas, b):
+    """which points the oracle's projection puts inside at least one image, with a margin: points within
+    1e-3 px of an image border may legitimately flip between devices (einsum rounding)."""
+    H, W = metas[0]["img_shape"][::-1]
+    l2i = torch.as_tensor(metas[b]["lidar2image"], dtype=torch.float64)
+    hom = torch.cat([pts[:, :3].double(), torch.ones(pts.shape[0], 1, dtype=torch.float64)], 1)
+    cam = torch.einsum("cij,hj->chi", l2i, hom)
+    xy = cam[..., :2] / torch.clamp(cam[..., 2:3], min=1e-5)
+    border = torch.zeros(pts.shape[0], dtype=torch.bool)
+    for c, aug in enumerate(metas[b]["imgs_aug"]):
+        x = xy[c, :, 0] * aug["resize"] - aug["crop"][0]
+        y = xy[c, :, 1] * aug["resize"] - aug["crop"][1]
+        if aug["flip"]:
+            x = W - x
+        for v, lim in ((x, W), (y, H)):
+            border |= (v.abs() < 1e-3) | ((v - lim).abs() < 1e-3)
+    return ~border
+
+
+def test_lift_vs_reference_golden():
+    """point_to_cam executed from the reference's own source on torch-CPU (tests/golden/make_golden.py)
+    vs the fused kernel with arith='cpu'. The projection is a K=4 matmul whose accumulation order is
+    library-defined, so this is a tolerance test: normwise 1e-5 on points away from image borders."""
+    g = load_golden("lift")
+    metas = _lift_metas(g, [g["flip0"], g["flip1"]])
+    pts = [g.t("points0"), g.t("points1")]
+    out = point_to_cam([cu(p) for p in pts], cu(g.t("img_features")), metas, arith="cpu")
+    for b in range(2):
+        ref = g.t(f"out{b}")
+        assert out[b].shape == ref.shape
+        keep = _seen_mask(pts[b], metas, b)
+        assert int(keep.sum()) > 0.95 * keep.numel()
+        assert normwise(out[b].cpu()[keep], ref[keep]) <= TOL
+        seen_ref, seen_out = ref.abs().sum(1) > 0, out[b].cpu().abs().sum(1) > 0
+        assert torch.equal(seen_ref[keep], seen_out[keep]) and int(seen_ref.sum()) > 20
+
+
+@pytest.mark.parametrize("Cf,n", [(768, 30000), (32, 5000), (260, 3000)])
+def test_lift_vs_torch_cuda_chain(Cf, n):
+    """Config-size lift (6 cameras, 16x32 maps, 768 channels, one sweep) vs the reference's op sequence
+    run by torch on the same GPU (oracle.point_to_cam moved to CUDA tensors)."""
+    rig = synth.camera_rig(1004)
+    metas = [dict(img_shape=rig.img_shape, lidar2image=rig.lidar2image.numpy(), imgs_aug=rig.imgs_aug),
+             dict(img_shape=rig.img_shape, lidar2image=rig.lidar2image.numpy(),
+                  imgs_aug=[dict(a, flip=(i % 2 == 0)) for i, a in enumerate(rig.imgs_aug)])]
+    pts = [synth.lidar_sweep(n, seed=50)[:, :5], synth.lidar_sweep(n // 3, seed=51)[:, :5]]
+    feats = torch.randn(2, 6, Cf, 16, 32, generator=torch.Generator().manual_seed(52))
+    ref = O.point_to_cam([cu(p) for p in pts], cu(feats), metas)  # torch-CUDA executes the reference chain
+    out = point_to_cam([cu(p) for p in pts], cu(feats), metas, arith="cuda")
+    for b in range(2):
+        keep = cu(_seen_mask(pts[b], metas, b))
+        assert normwise(out[b][keep], ref[b][keep]) <= TOL
+        same = float((out[b][keep] == ref[b][keep]).float().mean())
+        print(f"\n[lift Cf={Cf} b={b}] bitwise-equal to the torch-CUDA chain: {same:.6f}; "
+              f"points seen by a camera: {int((ref[b].abs().sum(1) > 0).sum())}/{ref[b].shape[0]}")
+        assert same > 0.99
+        assert torch.equal((out[b].abs().sum(1) > 0)[keep], (ref[b].abs().sum(1) > 0)[keep])
+
+
+def test_lift_edge_cases():
+    rig = synth.camera_rig(7)
+    metas = [dict(img_shape=rig.img_shape, lidar2image=rig.lidar2image.numpy(), imgs_aug=rig.imgs_aug)]
+    feats = cu(torch.ones(1, 6, 8, 16, 32))
+    # no points
+    assert point_to_cam([torch.zeros(0, 5, device=DEV)], feats, metas)[0].shape == (0, 8)
+    # NaN / inf / behind-every-camera points -> zero rows, like the reference (masks are all False)
+    bad = torch.tensor([[float("nan"), 0, 0, 0, 0], [float("inf"), 1, 1, 0, 0], [0, 0, 1e6, 0, 0]], device=DEV)
+    out = point_to_cam([bad], feats, metas)[0]
+    ref = O.point_to_cam([bad], feats, metas)[0]
+    assert torch.equal(out, ref) and float(out.abs().max()) == 0
+    # constant feature maps: interior points get (#cameras seeing them) * 1 up to edge taps
+    pts = cu(synth.lidar_sweep(2000, seed=9)[:, :5])
+    out = point_to_cam([pts], feats, metas)[0]
+    ref = O.point_to_cam([pts], feats, metas)[0]
+    assert normwise(out, ref) <= TOL and float(out.max()) <= 2.0 + 1e-5
 
 
 # ---------------------------------------------------------------------------------------------

@@ -140,30 +140,116 @@ lift_kernel(const LiftParams P) {
   }
 }
 
+// backward w.r.t. the feature maps: grad_out[p, :] * weight into the four taps of every camera that
+// sees the point (channels-last gradient maps, pre-zeroed by the caller)
+template <int ARITH>
+__global__ void __launch_bounds__(kLiftWarps * 32)
+lift_backward_kernel(const LiftParams P, const float* __restrict__ gout, float* __restrict__ gfeats) {
+  __shared__ __align__(16) float4 s_w[kLiftWarps][kLiftPts * kLiftCams];
+  __shared__ __align__(8) int2 s_om[kLiftWarps][kLiftPts * kLiftCams];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t p0 = ((int64_t)blockIdx.x * kLiftWarps + warp) * kLiftPts;
+  if (p0 >= P.n_total) return;
+  const int C4 = P.Cf >> 2;
+  {
+    const int pi = lane & 7;
+    const int64_t p = p0 + pi;
+    const bool pv = p < P.n_total;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    int b = 0;
+    if (pv) {
+      const float* pp = P.points + p * P.point_stride;
+      px = __ldg(pp); py = __ldg(pp + 1); pz = __ldg(pp + 2);
+      b = tp_find_batch(P.offsets, P.batch, p);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int cam = (lane >> 3) + 4 * h;
+      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+      int off = 0, mask = 0;
+      if (pv && cam < P.ncam) lift_setup<ARITH>(P, P.cams + ((int64_t)b * P.ncam + cam) * 20, px, py, pz, w, off, mask);
+      s_w[warp][pi * kLiftCams + cam] = w;
+      s_om[warp][pi * kLiftCams + cam] = make_int2(off, mask ? (mask | ((b * P.ncam + cam) << 4)) : 0);
+    }
+  }
+  __syncwarp();
+  const int64_t map4 = (int64_t)P.Hf * P.Wf * C4;
+  const int WC4 = P.Wf * C4;
+  float4* gf = reinterpret_cast<float4*>(gfeats);
+  for (int pi = 0; pi < kLiftPts; ++pi) {
+    const int64_t p = p0 + pi;
+    if (p >= P.n_total) break;
+    const float4* grow = reinterpret_cast<const float4*>(gout + p * P.Cf);
+    for (int cam = 0; cam < P.ncam; ++cam) {
+      const int2 om = s_om[warp][pi * kLiftCams + cam];
+      if (om.y == 0) continue;  // warp-uniform
+      const float4 w = s_w[warp][pi * kLiftCams + cam];
+      for (int c4 = lane; c4 < C4; c4 += 32)
+        scatter_taps(gf + (int64_t)(om.y >> 4) * map4 + c4, om.x, C4, WC4, w, om.y & 15, __ldg(grow + c4));
+    }
+  }
+}
+
 }  // namespace tp
 
 using namespace tp;
+
+static int lift_params(LiftParams& P, const char* who, const float* points, int32_t point_stride, int64_t n_total,
+                       const int64_t* offsets, int32_t batch, int32_t ncam, int32_t Hf, int32_t Wf, int32_t Cf,
+                       const float* cams, float resize_dim0, float resize_dim1) {
+  if (n_total < 0 || batch <= 0 || point_stride < 3) return fail(TP_E_SHAPE, "%s: bad N=%lld B=%d stride=%d", who, (long long)n_total, batch, point_stride);
+  if (ncam <= 0 || ncam > kLiftCams) return fail(TP_E_SHAPE, "%s: ncam=%d must be in 1..%d", who, ncam, kLiftCams);
+  if (Hf <= 0 || Wf <= 0 || Cf <= 0 || (Cf & 3)) return fail(TP_E_SHAPE, "%s: bad feature map %dx%dx%d (Cf %% 4 == 0)", who, Hf, Wf, Cf);
+  if ((int64_t)batch * ncam >= (1 << 27) || (int64_t)Hf * Wf * Cf >= ((int64_t)1 << 31))
+    return fail(TP_E_SHAPE, "%s: feature maps too large", who);
+  P.points = points; P.offsets = offsets; P.cams = cams;
+  P.n_total = n_total; P.point_stride = point_stride; P.batch = batch; P.ncam = ncam;
+  P.Hf = Hf; P.Wf = Wf; P.Cf = Cf;
+  P.R0 = resize_dim0; P.R1 = resize_dim1;
+  P.half0 = (float)((double)resize_dim0 / 2.0); P.half1 = (float)((double)resize_dim1 / 2.0);
+  P.rcp0 = 1.0f / resize_dim0; P.rcp1 = 1.0f / resize_dim1;
+  return 0;
+}
+
+extern "C" int tp_lift_cam_backward_f32(const float* points, int32_t point_stride, int64_t n_total,
+                                        const int64_t* offsets, int32_t batch, int32_t ncam, int32_t Hf,
+                                        int32_t Wf, int32_t Cf, const float* cams, float resize_dim0,
+                                        float resize_dim1, int32_t arith, const float* grad_out,
+                                        float* grad_feats_nhwc, void* stream) {
+  LiftParams P;
+  if (int rc = lift_params(P, "tp_lift_cam_backward_f32", points, point_stride, n_total, offsets, batch, ncam, Hf, Wf,
+                           Cf, cams, resize_dim0, resize_dim1))
+    return rc;
+  if (n_total == 0) return 0;
+  if (!points || !offsets || !cams || !grad_out || !grad_feats_nhwc) return fail(TP_E_NULL, "tp_lift_cam_backward_f32: null argument");
+  if (((uintptr_t)grad_feats_nhwc & 15) || ((uintptr_t)grad_out & 15)) return fail(TP_E_SHAPE, "tp_lift_cam_backward_f32: buffers not 16-byte aligned");
+  P.feats = nullptr; P.out = nullptr;
+  const int64_t tiles = (n_total + kLiftPts - 1) / kLiftPts;
+  const int64_t ctas = (tiles + kLiftWarps - 1) / kLiftWarps;
+  if (ctas >= ((int64_t)1 << 31)) return fail(TP_E_SHAPE, "tp_lift_cam_backward_f32: too many points");
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (arith) {
+    case TP_ARITH_TORCH_CUDA: lift_backward_kernel<TP_ARITH_TORCH_CUDA><<<(unsigned)ctas, kLiftWarps * 32, 0, s>>>(P, grad_out, grad_feats_nhwc); break;
+    case TP_ARITH_TORCH_CPU:  lift_backward_kernel<TP_ARITH_TORCH_CPU><<<(unsigned)ctas, kLiftWarps * 32, 0, s>>>(P, grad_out, grad_feats_nhwc); break;
+    default: return fail(TP_E_ENUM, "tp_lift_cam_backward_f32: unknown arith %d", arith);
+  }
+  TP_LAUNCH_CHECK("lift_backward_kernel");
+  return 0;
+}
 
 extern "C" int tp_lift_cam_f32(const float* points, int32_t point_stride, int64_t n_total,
                                const int64_t* offsets, int32_t batch, const float* feats_nhwc,
                                int32_t ncam, int32_t Hf, int32_t Wf, int32_t Cf, const float* cams,
                                float resize_dim0, float resize_dim1, int32_t arith, float* out,
                                void* stream) {
-  if (n_total < 0 || batch <= 0 || point_stride < 3) return fail(TP_E_SHAPE, "tp_lift_cam_f32: bad N=%lld B=%d stride=%d", (long long)n_total, batch, point_stride);
-  if (ncam <= 0 || ncam > kLiftCams) return fail(TP_E_SHAPE, "tp_lift_cam_f32: ncam=%d must be in 1..%d", ncam, kLiftCams);
-  if (Hf <= 0 || Wf <= 0 || Cf <= 0 || (Cf & 3)) return fail(TP_E_SHAPE, "tp_lift_cam_f32: bad feature map %dx%dx%d (Cf %% 4 == 0)", Hf, Wf, Cf);
-  if ((int64_t)batch * ncam >= (1 << 27) || (int64_t)Hf * Wf * Cf >= ((int64_t)1 << 31))
-    return fail(TP_E_SHAPE, "tp_lift_cam_f32: feature maps too large");
+  LiftParams P;
+  if (int rc = lift_params(P, "tp_lift_cam_f32", points, point_stride, n_total, offsets, batch, ncam, Hf, Wf, Cf, cams,
+                           resize_dim0, resize_dim1))
+    return rc;
   if (n_total == 0) return 0;
   if (!points || !offsets || !feats_nhwc || !cams || !out) return fail(TP_E_NULL, "tp_lift_cam_f32: null argument");
   if (((uintptr_t)feats_nhwc & 15) || ((uintptr_t)out & 15)) return fail(TP_E_SHAPE, "tp_lift_cam_f32: feats / out not 16-byte aligned");
-  LiftParams P;
-  P.points = points; P.offsets = offsets; P.feats = feats_nhwc; P.cams = cams; P.out = out;
-  P.n_total = n_total; P.point_stride = point_stride; P.batch = batch; P.ncam = ncam;
-  P.Hf = Hf; P.Wf = Wf; P.Cf = Cf;
-  P.R0 = resize_dim0; P.R1 = resize_dim1;
-  P.half0 = (float)((double)resize_dim0 / 2.0); P.half1 = (float)((double)resize_dim1 / 2.0);
-  P.rcp0 = 1.0f / resize_dim0; P.rcp1 = 1.0f / resize_dim1;
+  P.feats = feats_nhwc; P.out = out;
   const int64_t tiles = (n_total + kLiftPts - 1) / kLiftPts;
   const int64_t ctas = (tiles + kLiftWarps - 1) / kLiftWarps;
   if (ctas >= ((int64_t)1 << 31)) return fail(TP_E_SHAPE, "tp_lift_cam_f32: too many points");

@@ -118,6 +118,25 @@ __device__ __forceinline__ float4 plane_taps(const float4* __restrict__ pl, int 
   return a;
 }
 
+// ---- backward: 16-byte vector reductions into channels-last gradient planes --------------------
+__device__ __forceinline__ void red_add_f4(float4* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float4 scale4(float4 g, float w) {
+  return make_float4(__fmul_rn(g.x, w), __fmul_rn(g.y, w), __fmul_rn(g.z, w), __fmul_rn(g.w, w));
+}
+// grad_out * weight into the in-bounds taps of one plane, this lane's 4 channels
+__device__ __forceinline__ void scatter_taps(float4* __restrict__ gp, int off, int C4, int WC4, float4 w, int mk,
+                                             float4 g) {
+  float4* t0 = gp + off;
+  float4* t1 = t0 + WC4;
+  if (mk & 1) red_add_f4(t0, scale4(g, w.x));
+  if (mk & 2) red_add_f4(t0 + C4, scale4(g, w.y));
+  if (mk & 4) red_add_f4(t1, scale4(g, w.z));
+  if (mk & 8) red_add_f4(t1 + C4, scale4(g, w.w));
+}
+
 // ---- one warp, one tile of 32 queries ----------------------------------------------------------
 constexpr int kParamStride = 20;  // words per query: 16 used; 20 keeps 8-lane STS.128 phases conflict-free
 constexpr int kParamWords = 32 * kParamStride + 16;  // + 4-word skew per 8-query group (LDS.128 side)

@@ -153,14 +153,14 @@ def sample_points_triplane(triplane: Union[torch.Tensor, Sequence[torch.Tensor]]
         raise TriplaneError(f"points must be [B,h,w,3] or [B,h,w,d,3], got {tuple(points.shape)}")
     B = points.shape[0]
     q = points.reshape(B, -1, 3)
+    # 5-D callers pass a voxel-centre lattice (roi() / get_reference_points()): the grid entry point
+    # exploits that per block and is bit-identical to the flat one on any other input
+    dims = tuple(points.shape[1:4]) if points.dim() == 5 else None
     if torch.is_grad_enabled() and (any(t.requires_grad for t in ([triplane] if isinstance(triplane, torch.Tensor)
                                                                   else triplane)) or points.requires_grad):
         from .autograd import sample3_autograd
-        out = sample3_autograd(triplane, q, lo, vs, half, arith)
+        out = sample3_autograd(triplane, q, lo, vs, half, arith, dims)
     else:
-        # 5-D callers pass a voxel-centre lattice (roi() / get_reference_points()): the grid entry
-        # point exploits that per block and is bit-identical to the flat one on any other input
-        dims = tuple(points.shape[1:4]) if points.dim() == 5 else None
         out = ops.sample3(triplane, q, lo, vs, half, arith=arith, grid_dims=dims)
     return out.view(B, -1, *points.shape[1:-1])
 

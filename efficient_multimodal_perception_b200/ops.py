@@ -368,3 +368,87 @@ def lift_cam(points: torch.Tensor, offsets: torch.Tensor, img_features: torch.Te
                                     _ARITH[arith], out.data_ptr(), _stream(points)), "tp_lift_cam_f32")
     launch_count += 1 if n else 0
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# backward (SURVEY 8f #1)
+# ------------------------------------------------------------------------------------------------
+def channels_last_to_nchw(x: torch.Tensor) -> torch.Tensor:
+    """[N, H, W, C] -> contiguous [N, C, H, W] (the transpose kernel with the roles of C and H*W swapped)."""
+    global launch_count
+    _need_cuda(x, "x")
+    N, H, W, Cc = x.shape
+    x = x.contiguous()
+    out = torch.empty((N, Cc, H, W), dtype=torch.float32, device=x.device)
+    # source viewed as [N, "C"=H*W, "HW"=C] NCHW-style -> destination [N, "HW"=C, "C"=H*W]
+    L.check(L.lib().tp_planes_nchw_to_nhwc_f32(x.data_ptr(), H * W * Cc, out.data_ptr(), N, H * W, 1, Cc, _stream(x)),
+            "tp_planes_nchw_to_nhwc_f32")
+    launch_count += 1
+    return out
+
+
+def sample3_backward(grad_out: torch.Tensor, queries: torch.Tensor, plane_shapes, lo, vs, half, *,
+                     arith: str = "cuda") -> List[torch.Tensor]:
+    """Gradient of sample3 w.r.t. the three planes. grad_out [B,C,Q], queries [B,Q,3], plane_shapes = three
+    (H, W). Returns three NCHW gradients [B,C,H,W]."""
+    global launch_count
+    _need_cuda(grad_out, "grad_out")
+    _need_cuda(queries, "queries")
+    grad_out, queries = grad_out.contiguous(), queries.contiguous()
+    B, Cc, Q = grad_out.shape
+    g_nhwc = [torch.zeros((B, H, W, Cc), dtype=torch.float32, device=grad_out.device) for H, W in plane_shapes]
+    arr = (L.tp_plane * 3)()
+    for k, p in enumerate(g_nhwc):
+        arr[k].data = p.data_ptr()
+        arr[k].batch_stride = p.stride(0)
+        arr[k].H, arr[k].W = p.shape[1], p.shape[2]
+    sg = L.make_sample_geom(lo, vs, half)
+    L.check(L.lib().tp_sample3_backward_nhwc_f32(C.byref(arr), Cc, queries.data_ptr(), Q, B, C.byref(sg), _ARITH[arith],
+                                                 grad_out.data_ptr(), _stream(grad_out)), "tp_sample3_backward_nhwc_f32")
+    launch_count += 1 if Q else 0
+    return [channels_last_to_nchw(g) for g in g_nhwc]
+
+
+def encode_backward(grads, feats: Optional[torch.Tensor], grid_ind: torch.Tensor, offsets: torch.Tensor, grid_size,
+                    split, *, outs=None, counts: Optional[torch.Tensor] = None, reduce: str = "max",
+                    clamp_zero: bool = False, channels: Optional[int] = None) -> torch.Tensor:
+    """Gradient of encode w.r.t. the point features: grads = (g_xy, g_yz, g_xz) (None to skip a plane),
+    outs = the forward outputs (reduce='max'), counts = the forward cell counts (reduce='mean')."""
+    global launch_count
+    _need_cuda(grid_ind, "grid_ind", torch.int32)
+    _need_cuda(offsets, "offsets", torch.int64)
+    n = grid_ind.shape[0]
+    Cc = feats.shape[1] if feats is not None else int(channels)
+    if feats is not None:
+        _need_cuda(feats, "feats")
+        if feats.stride(1) != 1 or feats.stride(0) % 4 or feats.data_ptr() % 16:
+            feats = feats.contiguous()
+    grads = [None if g is None else _need_cuda(g, "grad").contiguous() for g in grads]
+    outs = [None, None, None] if outs is None else [None if o is None else o.contiguous() for o in outs]
+    pool = pool_kernels(grid_size, split)
+    geom = L.make_geom([0] * 6, (1, 1, 1), grid_size, pool)
+    gf = torch.empty((n, Cc), dtype=torch.float32, device=grid_ind.device)
+    L.check(L.lib().tp_encode_backward_f32(_ptr(feats), 0 if feats is None else feats.stride(0), Cc,
+                                           grid_ind.contiguous().data_ptr(), n, offsets.data_ptr(), offsets.numel() - 1,
+                                           C.byref(geom), _REDUCE[reduce], int(bool(clamp_zero)), _ptr(outs[0]),
+                                           _ptr(outs[1]), _ptr(outs[2]), _ptr(counts), _ptr(grads[0]), _ptr(grads[1]),
+                                           _ptr(grads[2]), gf.data_ptr(), _stream(grid_ind)), "tp_encode_backward_f32")
+    launch_count += 1 if n else 0
+    return gf
+
+
+def lift_cam_backward(grad_out: torch.Tensor, points: torch.Tensor, offsets: torch.Tensor, feat_shape, cams,
+                      resize_dims, *, arith: str = "cuda") -> torch.Tensor:
+    """Gradient of lift_cam w.r.t. img_features: grad_out [N,Cf] -> [B,ncam,Cf,Hf,Wf]."""
+    global launch_count
+    _need_cuda(grad_out, "grad_out")
+    grad_out, points = grad_out.contiguous(), points.contiguous()
+    B, ncam, Cf, Hf, Wf = feat_shape
+    g = torch.zeros((B * ncam, Hf, Wf, Cf), dtype=torch.float32, device=grad_out.device)
+    n = points.shape[0]
+    L.check(L.lib().tp_lift_cam_backward_f32(points.data_ptr(), points.shape[1], n, offsets.data_ptr(), B, ncam, Hf, Wf,
+                                             Cf, cams.contiguous().data_ptr(), float(resize_dims[0]),
+                                             float(resize_dims[1]), _ARITH[arith], grad_out.data_ptr(), g.data_ptr(),
+                                             _stream(grad_out)), "tp_lift_cam_backward_f32")
+    launch_count += 1 if n else 0
+    return channels_last_to_nchw(g).view(B, ncam, Cf, Hf, Wf)

@@ -219,6 +219,33 @@ TP_API int tp_lift_cam_f32(const float* points, int32_t point_stride, int64_t n_
                     float resize_dim0, float resize_dim1, int32_t arith, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Backward: what autograd produces in the reference for the three ops above.
+ * No gradients w.r.t. point / query coordinates (they are data in every config).
+ *
+ * tp_sample3_backward_nhwc_f32: ATen grid_sampler_2d_backward w.r.t. the input of the three grid_sample
+ *   calls: gplanes_nhwc[k].data (channels-last [B,H,W,C], ZEROED by the caller, written here) +=
+ *   grad_out[b,c,q] * bilinear weight at every in-bounds tap. grad_out [B,C,Q]. Scatter-add order is not
+ *   deterministic (as in ATen): sums agree to fp32 rounding.
+ * tp_encode_backward_f32: reduce = TP_REDUCE_MAX: grad_feats[n,c] = sum over the three planes of
+ *   gout_p[cell_p(n), c] where feats[n,c] attains out_p[cell_p(n), c] (the scatter_max argmax routing followed by
+ *   spconv's max-pool backward; exact ties, measure-zero for real features, give every maximiser the gradient);
+ *   TP_REDUCE_MEAN: gout / count. idx [N,3] int32 as in tp_encode_f32; any gout_p may be NULL.
+ * tp_lift_cam_backward_f32: gradient w.r.t. the channels-last feature maps [B,ncam,Hf,Wf,Cf] (ZEROED by the caller).
+ * ------------------------------------------------------------------------------------------- */
+TP_API int tp_sample3_backward_nhwc_f32(const tp_plane gplanes_nhwc[3], int32_t C, const float* queries, int64_t Q,
+                                 int32_t batch, const tp_sample_geom* sg, int32_t arith, const float* grad_out,
+                                 void* stream);
+TP_API int tp_encode_backward_f32(const float* feats, int64_t feat_stride, int32_t C, const int32_t* idx,
+                           int64_t n_total, const int64_t* offsets, int32_t batch, const tp_geom* geom,
+                           int32_t reduce, int32_t clamp_zero, const float* out_xy, const float* out_yz,
+                           const float* out_xz, const int32_t* cell_count, const float* gout_xy,
+                           const float* gout_yz, const float* gout_xz, float* grad_feats, void* stream);
+TP_API int tp_lift_cam_backward_f32(const float* points, int32_t point_stride, int64_t n_total,
+                             const int64_t* offsets, int32_t batch, int32_t ncam, int32_t Hf, int32_t Wf,
+                             int32_t Cf, const float* cams, float resize_dim0, float resize_dim1, int32_t arith,
+                             const float* grad_out, float* grad_feats_nhwc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Host-buffer entry points (what a non-PyTorch caller binds; bench.py's `e2e` leg).
  * All pointers are HOST memory (pinned recommended). They allocate a per-thread cached device
  * arena, copy in, run the kernels above, copy out and synchronise the internal stream.

@@ -10,7 +10,8 @@
 // The three channels-last outputs are cut into TILES of consecutive cells (16 KB of output each).
 //   1. count:  every point computes its crop / voxel index / three pooled cells (fused a1) and
 //              bumps the point counter of the three tiles it lands in (int32 atomics, L2-resident).
-//   2. scan:   exclusive scan of the per-tile counters -> CSR offsets.
+//   2. alloc:  every occupied tile gets its CSR range by warp-aggregated bump allocation (the lists
+//              need not be in tile order, so there is no serial prefix scan); heavy tiles are listed.
 //   3. fill:   every point writes (point id, cell inside tile) into its slot of each tile's list.
 //   4. reduce: persistent 4-warp CTAs (about ten per SM) pull tiles from a global counter. An empty
 //              tile is 16 KB of streaming zero stores. An occupied tile is reduced in the CTA's
@@ -53,7 +54,8 @@ struct EncodeParams {
   int64_t feat_stride;
   int32_t* tile_cnt;    // [tiles_total]   zero on entry, zero on exit
   int32_t* tile_start;  // [tiles_total + 1]
-  int32_t* heavy;       // [1 + tiles_total]: count, then the tiles with >= kHeavy points (scan pass)
+  int32_t* heavy;       // [1 + tiles_total]: count, then the tiles with >= kHeavy points (alloc pass)
+  int32_t* cursor;      // [1] bump allocator of the CSR entries (zeroed by the count pass)
   int32_t* rank;        // [3][n]
   int2* entries;        // [3n] (point id, cell inside tile)
   float* out[3];
@@ -107,6 +109,7 @@ __device__ __forceinline__ int64_t point_cells(const EncodeParams& P, int64_t i,
 template <int ARITH>
 __global__ void __launch_bounds__(256)
 encode_count_kernel(const EncodeParams P) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) { P.heavy[0] = 0; P.cursor[0] = 0; }  // consumed by the alloc pass
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n;
        i += (int64_t)gridDim.x * blockDim.x) {
     int64_t cell[3];
@@ -120,69 +123,30 @@ encode_count_kernel(const EncodeParams P) {
   }
 }
 
-// ---- pass 2: exclusive scan of tile counters (one CTA, 8192 counters per iteration) -----------
-__global__ void __launch_bounds__(1024)
-encode_scan_kernel(const int32_t* __restrict__ cnt, int32_t* __restrict__ start, int32_t* __restrict__ heavy,
-                   int64_t T) {
-  __shared__ int s_warp[32];
-  __shared__ int s_carry;
-  __shared__ int s_hc;  // heavy tiles found so far
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) { s_carry = 0; s_hc = 0; }
-  __syncthreads();
-  for (int64_t base = 0; base < T; base += 8192) {
-    const int64_t i0 = base + (int64_t)tid * 8;
-    int v[8];
-    if (i0 + 8 <= T) {  // the counter array is 256-byte aligned: two 16-byte loads
-      const int4 a = *reinterpret_cast<const int4*>(cnt + i0);
-      const int4 b = *reinterpret_cast<const int4*>(cnt + i0 + 4);
-      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = (i0 + j < T) ? cnt[i0 + j] : 0;
-    }
-    int sum = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      sum += v[j];
-      if (v[j] >= kHeavy) heavy[1 + atomicAdd(&s_hc, 1)] = (int)(i0 + j);
-    }
-    int incl = sum;
+// ---- pass 2: CSR ranges + heavy-tile list (one lane per tile, one atomic per warp) ---------------
+__global__ void __launch_bounds__(256)
+encode_alloc_kernel(const EncodeParams P) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t base = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < P.tiles_total;
+       base += nwarp * 32) {
+    const int64_t t = base + lane;
+    const int c = t < P.tiles_total ? P.tile_cnt[t] : 0;
+    int incl = c;  // exclusive scan of the warp's counts -> one bump of the entries cursor per warp
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += t;
+      const int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
     }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      int w = s_warp[lane], wi = w;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, wi, d);
-        if (lane >= d) wi += t;
-      }
-      s_warp[lane] = wi - w;
-    }
-    __syncthreads();
-    int run = s_carry + s_warp[warp] + incl - sum;
-    int o[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { o[j] = run; run += v[j]; }
-    if (i0 + 8 <= T) {
-      *reinterpret_cast<int4*>(start + i0) = make_int4(o[0], o[1], o[2], o[3]);
-      *reinterpret_cast<int4*>(start + i0 + 4) = make_int4(o[4], o[5], o[6], o[7]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) if (i0 + j < T) start[i0 + j] = o[j];
-    }
-    __syncthreads();
-    if (tid == 1023) s_carry = run;
-    __syncthreads();
-  }
-  if (tid == 0) {
-    start[T] = s_carry;
-    heavy[0] = s_hc;
+    int wbase = 0;
+    if (lane == 31 && incl > 0) wbase = atomicAdd(P.cursor, incl);
+    wbase = __shfl_sync(0xffffffffu, wbase, 31);
+    if (c > 0) P.tile_start[t] = wbase + incl - c;
+    const unsigned mh = __ballot_sync(0xffffffffu, c >= kHeavy);
+    int bh = 0;
+    if (lane == 0 && mh) bh = atomicAdd(P.heavy, __popc(mh));
+    bh = __shfl_sync(0xffffffffu, bh, 0);
+    if (c >= kHeavy) P.heavy[1 + bh + __popc(mh & ((1u << lane) - 1u))] = (int)t;
   }
 }
 
@@ -535,7 +499,7 @@ static int cells_per_tile(int C) {
 
 struct EncodeLayout {
   int64_t tiles_per_sample[3], tiles_all, tiles_total;
-  int64_t off_cnt, off_start, off_heavy, off_rank, off_ent, bytes;
+  int64_t off_cnt, off_start, off_heavy, off_rank, off_ent, bytes, tmax;
 };
 
 static EncodeLayout encode_layout(const GeomDev& g, int batch, int64_t n, int C, const bool use[3]) {
@@ -556,10 +520,11 @@ static EncodeLayout encode_layout(const GeomDev& g, int batch, int64_t n, int C,
   for (int k = 0; k < 3; ++k) tmax += (cps[k] + cpt_min - 1) / cpt_min;
   tmax *= batch;
   auto pad = [](int64_t b) { return (b + 255) / 256 * 256; };
+  L.tmax = tmax;
   L.off_cnt = 0;
   L.off_start = L.off_cnt + pad(tmax * 4);
   L.off_heavy = L.off_start + pad((tmax + 1) * 4);
-  L.off_rank = L.off_heavy + pad((tmax + 1) * 4);
+  L.off_rank = L.off_heavy + pad((tmax + 2) * 4);  // + the CSR cursor
   L.off_ent = L.off_rank + pad(3 * n * 4);
   L.bytes = L.off_ent + pad(3 * n * 8);
   return L;
@@ -634,6 +599,7 @@ extern "C" int tp_encode_f32(const float* feats, int64_t feat_stride, int32_t C,
   P.tile_cnt = reinterpret_cast<int32_t*>(ws + L.off_cnt);
   P.tile_start = reinterpret_cast<int32_t*>(ws + L.off_start);
   P.heavy = reinterpret_cast<int32_t*>(ws + L.off_heavy);
+  P.cursor = P.heavy + 1 + L.tmax;
   P.rank = reinterpret_cast<int32_t*>(ws + L.off_rank);
   P.entries = reinterpret_cast<int2*>(ws + L.off_ent);
   P.out[0] = out_xy;
@@ -651,13 +617,14 @@ extern "C" int tp_encode_f32(const float* feats, int64_t feat_stride, int32_t C,
     if (arith == TP_ARITH_TORCH_CUDA) encode_count_kernel<TP_ARITH_TORCH_CUDA><<<grid, 256, 0, s>>>(P);
     else encode_count_kernel<TP_ARITH_TORCH_CPU><<<grid, 256, 0, s>>>(P);
     TP_LAUNCH_CHECK("encode_count_kernel");
-    encode_scan_kernel<<<1, 1024, 0, s>>>(P.tile_cnt, P.tile_start, P.heavy, L.tiles_total);
-    TP_LAUNCH_CHECK("encode_scan_kernel");
+    const int64_t ablocks = (L.tiles_total + 255) / 256;
+    encode_alloc_kernel<<<(int)(ablocks < (int64_t)kSMs * 4 ? ablocks : (int64_t)kSMs * 4), 256, 0, s>>>(P);
+    TP_LAUNCH_CHECK("encode_alloc_kernel");
     if (arith == TP_ARITH_TORCH_CUDA) encode_fill_kernel<TP_ARITH_TORCH_CUDA><<<grid, 256, 0, s>>>(P);
     else encode_fill_kernel<TP_ARITH_TORCH_CPU><<<grid, 256, 0, s>>>(P);
     TP_LAUNCH_CHECK("encode_fill_kernel");
   } else {
-    TP_CUDA(cudaMemsetAsync(P.heavy, 0, 4, s));  // no points: no heavy tiles (the scan pass did not run)
+    TP_CUDA(cudaMemsetAsync(P.heavy, 0, 4, s));  // no points: no heavy tiles (the alloc pass did not run)
   }
   constexpr int kSmem = kTileFloats * 4 + kMaxCpt * 4;  // 17 KB
   const size_t smem = kSmem;

@@ -62,6 +62,7 @@ struct EncodeParams {
   int32_t* cell_count;  // optional, order xy | yz | xz, each [B, cells_per_sample]
   int64_t count_base[3];
   int clamp_zero;
+  int keep_rows;  // 1: the point rows fit in L2 next to the output stream: prefetch + evict_last (else default policy)
   int partial;  // 1: TP_REDUCE_MAX_PARTIAL — empty cells are -inf (identity of max) for a cross-GPU max
 };
 
@@ -164,7 +165,7 @@ encode_fill_kernel(const EncodeParams P) {
     // Pull this point's feature row into L2 now, with evict_last priority: the reduce pass gathers it
     // up to three times while the dense output streams through L2, and a gather that misses waits in
     // the DRAM queues behind ~6 TB/s of writes.
-    if ((cell[0] & cell[1] & cell[2]) >= 0 || cell[0] >= 0 || cell[1] >= 0 || cell[2] >= 0) {
+    if (P.keep_rows && (cell[0] >= 0 || cell[1] >= 0 || cell[2] >= 0)) {
       const char* row = reinterpret_cast<const char*>(P.feats + i * P.feat_stride);
       for (int o = 0; o < P.C * 4; o += 128)
         asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(row + o));
@@ -239,7 +240,9 @@ encode_reduce_kernel(const EncodeParams P, int sched_slot) {
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const float fillv = P.partial ? __uint_as_float(0xff800000u) : 0.f;  // -inf or 0 for empty cells
   const float4 fill4 = make_float4(fillv, fillv, fillv, fillv);
-  const unsigned long long pol_out = policy_evict_first(), pol_in = policy_evict_last();
+  const unsigned long long pol_out = policy_evict_first();
+  unsigned long long pol_in = policy_evict_last();
+  if (!P.keep_rows) asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_in));
 
   // the tile buffer starts zeroed and is returned to all-zero before each reuse by clearing only the
   // cells the previous tile touched (their counters are still set): a sparse tile costs O(points).
@@ -279,6 +282,11 @@ encode_reduce_kernel(const EncodeParams P, int sched_slot) {
     }
     __syncthreads();
     const int2* ent = P.entries + start;
+    // points per cell first (one integer atomic per point): a cell with a single point — the common case
+    // in one sweep — is then written with plain stores, and only shared cells pay for feature atomics
+    // (the ATOMS pipe, 4 x 32 lanes per row, was the busiest unit of the previous version)
+    for (int e = tid; e < npts; e += kRedThreads) atomicAdd(s_cnt + __ldg(ent + e).y, 1);
+    __syncthreads();
     for (int e0 = warp * 4; e0 < npts; e0 += kWarps * 4) {
       int2 en[4];
 #pragma unroll
@@ -293,7 +301,12 @@ encode_reduce_kernel(const EncodeParams P, int sched_slot) {
         for (int j = 0; j < 4; ++j) {
           if (en[j].x < 0) continue;
           float* w = s_work + en[j].y * C + v * 4;
-          if (REDUCE == TP_REDUCE_MAX) {
+          if (s_cnt[en[j].y] == 1) {  // warp-uniform: sole owner of the row
+            if (REDUCE == TP_REDUCE_MAX)
+              *reinterpret_cast<uint4*>(w) = make_uint4(f2key(x[j].x), f2key(x[j].y), f2key(x[j].z), f2key(x[j].w));
+            else
+              *reinterpret_cast<float4*>(w) = x[j];
+          } else if (REDUCE == TP_REDUCE_MAX) {
             unsigned* wk = reinterpret_cast<unsigned*>(w);
             atomicMax(wk + 0, f2key(x[j].x));
             atomicMax(wk + 1, f2key(x[j].y));
@@ -307,7 +320,6 @@ encode_reduce_kernel(const EncodeParams P, int sched_slot) {
           }
         }
       }
-      if (lane < 4 && en[lane].x >= 0) atomicAdd(s_cnt + en[lane].y, 1);
     }
     __syncthreads();
     // finalise touched cells in place: keys -> floats, or sum -> mean
@@ -608,6 +620,8 @@ extern "C" int tp_encode_f32(const float* feats, int64_t feat_stride, int32_t C,
   P.cell_count = cell_count;
   P.clamp_zero = (reduce == TP_REDUCE_MAX_PARTIAL) ? 0 : clamp_zero;  // clamp after the cross-GPU max
   P.partial = (reduce == TP_REDUCE_MAX_PARTIAL) ? 1 : 0;
+  // 179 MB of rows (350k points) do not fit in the 126 MB L2: pinning them only thrashes it (550 -> 500 us)
+  P.keep_rows = (n * (int64_t)C * 4 <= ((int64_t)48 << 20)) ? 1 : 0;
   cudaStream_t s = (cudaStream_t)stream;
   if (L.tiles_total == 0) return 0;
 

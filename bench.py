@@ -336,6 +336,78 @@ def bench_encode_device(args, dev, barrier, sampler):
                 launches=4 * steps)
 
 
+def bench_encode_dense(args, dev, barrier, sampler):
+    """BASELINE.json configs[4] shape per GPU: samples of 10 accumulated sweeps (~350k points each), sample-sharded
+    (bs=64 over 8 GPUs = 8 per GPU; 4 per GPU here to bound the footprint), one batched encode call."""
+    from efficient_multimodal_perception_b200 import ops, synth
+    G = synth.GEOM_A
+    B, Cc = 4, G["channels"]
+    pts = [synth.multi_sweep(10, 35000, seed=1005 + b) for b in range(B)]
+    sizes = [p.shape[0] for p in pts]
+    xyz = torch.cat([p[:, :3] for p in pts]).contiguous().to(dev)
+    feats = synth.point_features(sum(sizes), Cc, seed=1005).to(dev)
+    off = synth.batch_offsets(sizes).to(dev)
+    inside = int(sum(int(((p[:, 0].abs() < 25) & (p[:, 1].abs() < 25) & (p[:, 2] > -5) & (p[:, 2] < 3)).sum()) for p in pts))
+    cells = B * (128 * 128 * 20 + 2 * 128 * 80 * 25)
+
+    def step():
+        return ops.encode(feats, off, G["pc_range"], G["voxel_size"], G["grid_size"], G["split"], points=xyz)
+
+    for _ in range(3):
+        step()
+    steps = max(5, min(args.steps, 20))
+    sampler.active.set()
+
+    def run():
+        for _ in range(steps):
+            step()
+
+    ms = time_region(run, barrier)
+    sampler.active.clear()
+    n = sum(sizes)
+    return dict(n=n, B=B, inside=inside, steps=steps, ms_per_step=ms / steps,
+                bytes=n * 12 + inside * 4 * Cc + 4 * Cc * cells, launches=4 * steps)
+
+
+def bench_lift(args, dev, barrier, sampler):
+    """Camera -> point lift (point_to_cam) at the PointTriplane config: 6 cameras x [768,16,32] feature maps per
+    sample, bs=2 sweeps of 34 720 points. A step = channels-last copy of the maps + the fused lift kernel."""
+    from efficient_multimodal_perception_b200 import ops, synth
+    B, ncam, Cf, Hf, Wf, n = 2, 6, 768, 16, 32, 34720
+    rig = synth.camera_rig(1004)
+    metas = [dict(img_shape=rig.img_shape, lidar2image=rig.lidar2image.numpy(), imgs_aug=rig.imgs_aug) for _ in range(B)]
+    pts = torch.cat([synth.lidar_sweep(n, seed=1004 + b)[:, :3] for b in range(B)]).contiguous().to(dev)
+    off = synth.batch_offsets([n] * B).to(dev)
+    feats = torch.randn(B, ncam, Cf, Hf, Wf, generator=torch.Generator().manual_seed(1004)).to(dev)
+    cams = ops.pack_cameras(metas, dev)
+    dims = rig.img_shape[::-1]
+
+    def step():
+        return ops.lift_cam(pts, off, feats, cams, dims)
+
+    for _ in range(3):
+        step()
+    nhwc = ops.features_to_channels_last(feats)
+    steps = max(10, min(args.steps, 100))
+    sampler.active.set()
+
+    def run():
+        for _ in range(steps):
+            step()
+
+    ms = time_region(run, barrier) / steps
+
+    def run_k():
+        for _ in range(steps):
+            ops.lift_cam(pts, off, nhwc, cams, dims, channels_last=True)
+
+    ms_k = time_region(run_k, barrier) / steps
+    sampler.active.clear()
+    # SURVEY 8(d): N'*(12 + 4*768) + the feature maps once
+    return dict(n=B * n, steps=steps, ms_per_step=ms, kernel_ms=ms_k, launches=2 * steps,
+                bytes=B * n * (12 + 4 * Cf) + B * ncam * Cf * Hf * Wf * 4)
+
+
 def bench_encode_point_sharded(args, dev, barrier, rank, world):
     """N > 1 only: ONE 10-sweep sample (350 000 raw points) point-sharded over the ranks:
     partial planes (-inf empties) -> NCCL all-reduce(max) of the 430 MB dense planes -> finalise."""
@@ -405,13 +477,15 @@ def run_b200(args):
 
     dec = bench_decode_device(args, dev, barrier, sampler)
     enc = bench_encode_device(args, dev, barrier, sampler)
+    encd = bench_encode_dense(args, dev, barrier, sampler)
+    lift = bench_lift(args, dev, barrier, sampler)
     eps = bench_encode_point_sharded(args, dev, barrier, rank, world) if world > 1 else None
     # max over ranks (device time)
-    t = torch.tensor([dec["ms_total"], enc["ms_per_step"], dec["kernel_ms_avg"], eps["ms_per_step"] if eps else 0.0],
-                     device=dev, dtype=torch.float64)
+    t = torch.tensor([dec["ms_total"], enc["ms_per_step"], dec["kernel_ms_avg"], eps["ms_per_step"] if eps else 0.0,
+                      encd["ms_per_step"], lift["ms_per_step"], lift["kernel_ms"]], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, enc_ms, k_avg, eps_ms = (float(x) for x in t.tolist())
+    ms_total, enc_ms, k_avg, eps_ms, encd_ms, lift_ms, lift_k_ms = (float(x) for x in t.tolist())
     clocks = sampler.stop()
 
     q_host = decode_queries(args.queries)
@@ -485,6 +559,22 @@ def run_b200(args):
                                     "note": "whole step: count + scan + fill + reduce (4 launches)"},
                        "steps": enc["steps"], "gpu_launches": enc["launches"]},
         }
+        line["encode_dense"] = {
+            "metric": "triplane encode points/s, 10-sweep samples (BASELINE.json configs[4] shape, sample-sharded)",
+            "value": world * encd["n"] / (encd_ms * 1e-3), "unit": "points/s", "ms_per_step": encd_ms,
+            "workload": f"{encd['B']} samples x ~350k raw pts per GPU ({encd['n']} pts, {encd['inside']} in range), geometry "
+                        f"128x128x80 C=128, one batched call, dense pooled output",
+            "roofline": {"bound": "hbm", "achieved": encd["bytes"] / (encd_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": encd["bytes"] / (encd_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": encd["bytes"]},
+            "steps": encd["steps"], "gpu_launches": encd["launches"]}
+        line["lift"] = {
+            "metric": "camera->point lift points/s (point_to_cam: 6 cameras x [768,16,32] maps, bilinear gather + camera sum)",
+            "value": world * lift["n"] / (lift_ms * 1e-3), "unit": "points/s", "ms_per_step": lift_ms,
+            "kernel_ms": lift_k_ms, "workload": f"bs=2 x 34720 pts per GPU, Cf=768; step = channels-last copy + lift kernel",
+            "roofline": {"bound": "hbm", "achieved": lift["bytes"] / (lift_k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": lift["bytes"] / (lift_k_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": lift["bytes"],
+                         "note": "lift kernel alone (events around the loop of launches)"},
+            "steps": lift["steps"], "gpu_launches": lift["launches"]}
         if eps:
             line["encode_point_sharded"] = {
                 "workload": f"ONE 10-sweep sample ({eps['n']} raw pts) point-sharded over {world} GPUs, geometry "

@@ -28,12 +28,18 @@ struct Arena {
   char* base = nullptr;
   size_t cap = 0, used = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream_d2h = nullptr;  // result copies of chunk i overlap the kernel and the H2D of chunk i+1
+  cudaEvent_t ev[8] = {};
   void* enc_ws = nullptr;  // encode workspace keeps its "clean head table" invariant across calls
   size_t enc_ws_bytes = 0;
   int reserve(size_t bytes) {
-    if (!stream) TP_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (!stream) {
+      TP_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+      TP_CUDA(cudaStreamCreateWithFlags(&stream_d2h, cudaStreamNonBlocking));
+      for (auto& e : ev) TP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     if (bytes > cap) {
-      if (base) { TP_CUDA(cudaStreamSynchronize(stream)); TP_CUDA(cudaFree(base)); base = nullptr; cap = 0; }
+      if (base) { TP_CUDA(cudaStreamSynchronize(stream)); TP_CUDA(cudaStreamSynchronize(stream_d2h)); TP_CUDA(cudaFree(base)); base = nullptr; cap = 0; }
       TP_CUDA(cudaMalloc((void**)&base, bytes));
       cap = bytes;
     }
@@ -69,6 +75,8 @@ extern "C" void tp_host_arena_release(void) {
   if (A.base) cudaFree(A.base);
   if (A.enc_ws) cudaFree(A.enc_ws);
   if (A.stream) cudaStreamDestroy(A.stream);
+  if (A.stream_d2h) { cudaStreamSynchronize(A.stream_d2h); cudaStreamDestroy(A.stream_d2h); }
+  for (auto& e : A.ev) if (e) cudaEventDestroy(e);
   A = Arena();
 }
 
@@ -112,11 +120,46 @@ static int sample3_host_impl(const float* planes_host[3], const int32_t HW[6],
   }
   float* dq = A.take<float>((size_t)batch * Q * 3);
   float* dout = A.take<float>((size_t)batch * C * Q);
-  TP_CUDA(cudaMemcpyAsync(dq, queries_host, qbytes, cudaMemcpyHostToDevice, s));
-  if (int rc = dims ? tp_sample3_grid_nhwc_f32(nhwc, C, dq, dims, batch, sg, arith, dout, s)
-                    : tp_sample3_nhwc_f32(nhwc, C, dq, Q, batch, sg, arith, dout, s))
-    return rc;
-  TP_CUDA(cudaMemcpyAsync(out_host, dout, obytes, cudaMemcpyDeviceToHost, s));
+  // Pipeline over chunks of the query range (rows of the lattice for the 5-D entry): the device->host copy of
+  // chunk i (the 4C bytes per query that dominate the PCIe time) runs on its own stream while chunk i+1's
+  // queries go up and its kernel runs. Each chunk's result is a compact [C, q_chunk] block on the device and
+  // lands in the caller's [B, C, Q] tensor with a strided copy.
+  const int64_t unit = dims ? (int64_t)dims[1] * dims[2] : 32;  // queries per indivisible slice
+  const int64_t units = dims ? dims[0] : (Q + 31) / 32;
+  int nchunk = (obytes / batch >= ((size_t)8 << 20) && units >= 4) ? 4 : 1;
+  const int64_t upc = (units + nchunk - 1) / nchunk;
+  size_t off_out = 0;
+  int evi = 0;
+  for (int b = 0; b < batch; ++b) {
+    tp_plane pb[3];
+    for (int k = 0; k < 3; ++k) {
+      pb[k] = nhwc[k];
+      pb[k].data = nhwc[k].data + (size_t)b * nhwc[k].batch_stride;
+    }
+    for (int64_t u0 = 0; u0 < units; u0 += upc) {
+      const int64_t q0 = u0 * unit;
+      const int64_t qc = (u0 + upc < units ? upc * unit : Q - q0);
+      const float* hq = queries_host + ((size_t)b * Q + q0) * 3;
+      float* dqc = dq + ((size_t)b * Q + q0) * 3;
+      float* doc = dout + off_out;
+      off_out += (size_t)C * qc;
+      TP_CUDA(cudaMemcpyAsync(dqc, hq, (size_t)qc * 12, cudaMemcpyHostToDevice, s));
+      int rc;
+      if (dims) {
+        const int32_t cd[3] = {(int32_t)(qc / unit), dims[1], dims[2]};
+        rc = tp_sample3_grid_nhwc_f32(pb, C, dqc, cd, 1, sg, arith, doc, s);
+      } else {
+        rc = tp_sample3_nhwc_f32(pb, C, dqc, qc, 1, sg, arith, doc, s);
+      }
+      if (rc) return rc;
+      cudaEvent_t e = A.ev[evi++ & 7];
+      TP_CUDA(cudaEventRecord(e, s));
+      TP_CUDA(cudaStreamWaitEvent(A.stream_d2h, e, 0));
+      TP_CUDA(cudaMemcpy2DAsync(out_host + (size_t)b * C * Q + q0, (size_t)Q * 4, doc, (size_t)qc * 4, (size_t)qc * 4,
+                                (size_t)C, cudaMemcpyDeviceToHost, A.stream_d2h));
+    }
+  }
+  TP_CUDA(cudaStreamSynchronize(A.stream_d2h));
   TP_CUDA(cudaStreamSynchronize(s));
   return 0;
 }

@@ -532,3 +532,38 @@ def test_host_buffer_entry_points():
     for a, b in zip(outs, ref[:3]):
         assert torch.equal(a, b)
     lib.tp_host_arena_release()
+
+
+@pytest.mark.parametrize("dims", [(100, 100, 16), None])
+def test_host_entry_points_chunked_pipeline(dims):
+    """Large enough for the host entry points to pipeline the query range in 4 chunks (H2D / kernel / D2H
+    overlapped on two streams): the result must be bitwise what the device entry points give, including a
+    ragged last chunk (Q = 100003 point list) and batch > 1."""
+    import ctypes as C
+    from efficient_multimodal_perception_b200 import _lib as L
+    lib = L.lib()
+    lo, vs = [-25.0, -25.0, -5.0], (0.4, 0.4, 0.1)
+    B, Cc = 2, 32
+    tri = synth.triplane_stacked(B, Cc, 128, seed=21).contiguous().pin_memory()
+    if dims:
+        q = synth.lattice(dims, (0.5, 0.5, 0.5), (-26.0, -24.0, -5.0)).reshape(1, -1, 3).repeat(B, 1, 1).contiguous()
+    else:
+        q = torch.stack([synth.uniform_queries(100003, seed=s) for s in (1, 2)]).contiguous() * 1.05
+    Q = q.shape[1]
+    q = q.pin_memory()
+    out = torch.empty(B, Cc, Q).pin_memory()
+    ptrs = (C.c_void_p * 3)(*[tri[:, k].data_ptr() for k in range(3)])
+    hw = (C.c_int32 * 6)(*[128] * 6)
+    bs = (C.c_int64 * 3)(*[tri.stride(0)] * 3)
+    sg = L.make_sample_geom(lo, vs, [64.0] * 3)
+    for _ in range(2):  # second call reuses the arena
+        if dims:
+            cd = (C.c_int32 * 3)(*dims)
+            L.check(lib.tp_sample3_grid_host_f32(C.byref(ptrs), C.byref(hw), C.byref(bs), Cc, q.data_ptr(), C.byref(cd), B,
+                                                 C.byref(sg), 0, out.data_ptr()), "tp_sample3_grid_host_f32")
+        else:
+            L.check(lib.tp_sample3_host_f32(C.byref(ptrs), C.byref(hw), C.byref(bs), Cc, q.data_ptr(), Q, B, C.byref(sg), 0,
+                                            out.data_ptr()), "tp_sample3_host_f32")
+    ref = ops.sample3(cu(tri), cu(q), lo, vs, [64.0] * 3)
+    assert torch.equal(out, ref.cpu())
+    lib.tp_host_arena_release()

@@ -35,6 +35,8 @@ constexpr int kRedThreads = 128;   // small CTAs, ~10 resident per SM: that many
 constexpr int kRedCtasPerSm = 10;
 constexpr int kGrab = 4;           // tiles taken per scheduler atomic
 constexpr int kHeavy = 48;         // tiles with at least this many points are reduced first
+constexpr int kSplit = 256;        // tiles with at least this many points are cut into items of kSub list entries,
+constexpr int kSub = 128;          // reduced by different CTAs and combined in the output tile itself
 
 struct EncodeParams {
   GeomDev g;
@@ -56,6 +58,12 @@ struct EncodeParams {
   int32_t* tile_start;  // [tiles_total + 1]
   int32_t* heavy;       // [1 + tiles_total]: count, then the tiles with >= kHeavy points (alloc pass)
   int32_t* cursor;      // [1] bump allocator of the CSR entries (zeroed by the count pass)
+  // split tiles (>= kSplit points; ground-plane tiles collect thousands): split_ctr = {#split tiles, #items}
+  int32_t* split_ctr;   // [2] zeroed by the count pass
+  int32_t* split_tile;  // [#split] tile index
+  int2* split_item;     // [#items] (split tile slot, sub-range index)
+  int32_t* split_done;  // [#split] items finished (zeroed by the fill pass)
+  int32_t* split_cnt;   // [#split][kMaxCpt] points per cell, accumulated over the items (zeroed by the fill pass)
   int32_t* rank;        // [3][n]
   int2* entries;        // [3n] (point id, cell inside tile)
   float* out[3];
@@ -73,6 +81,21 @@ __device__ __forceinline__ int64_t tile_index(const EncodeParams& P, int64_t b, 
   if (k >= 1) t += P.tiles_per_sample[0];
   if (k >= 2) t += P.tiles_per_sample[1];
   return t;
+}
+
+// tile -> its slice of the output: first float, optional cell counters, number of cells (the last tile
+// of a plane may be short)
+__device__ __forceinline__ int tile_dest(const EncodeParams& P, int64_t t, float*& gdst, int32_t*& gcount) {
+  const int64_t b = t / P.tiles_all;
+  int64_t r = t - b * P.tiles_all;
+  int k = 0;
+  if (r >= P.tiles_per_sample[0]) { r -= P.tiles_per_sample[0]; k = 1;
+    if (r >= P.tiles_per_sample[1]) { r -= P.tiles_per_sample[1]; k = 2; } }
+  const int64_t cps = P.cells_per_sample[k];
+  const int64_t c0 = r * P.cpt;
+  gdst = P.out[k] + (b * cps + c0) * P.C;
+  gcount = P.cell_count ? P.cell_count + P.count_base[k] + b * cps + c0 : nullptr;
+  return (int)min((int64_t)P.cpt, cps - c0);
 }
 
 // crop + voxel index + the three pooled cells of point i; cell[k] = -1 where the point does not
@@ -110,7 +133,9 @@ __device__ __forceinline__ int64_t point_cells(const EncodeParams& P, int64_t i,
 template <int ARITH>
 __global__ void __launch_bounds__(256)
 encode_count_kernel(const EncodeParams P) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) { P.heavy[0] = 0; P.cursor[0] = 0; }  // consumed by the alloc pass
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // consumed by the alloc pass
+    P.heavy[0] = 0; P.cursor[0] = 0; P.split_ctr[0] = 0; P.split_ctr[1] = 0;
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n;
        i += (int64_t)gridDim.x * blockDim.x) {
     int64_t cell[3];
@@ -143,11 +168,18 @@ encode_alloc_kernel(const EncodeParams P) {
     if (lane == 31 && incl > 0) wbase = atomicAdd(P.cursor, incl);
     wbase = __shfl_sync(0xffffffffu, wbase, 31);
     if (c > 0) P.tile_start[t] = wbase + incl - c;
-    const unsigned mh = __ballot_sync(0xffffffffu, c >= kHeavy);
+    if (c >= kSplit) {  // rare: this lane lists the tile and its items by itself
+      const int m = atomicAdd(P.split_ctr, 1);
+      const int ns = (c + kSub - 1) / kSub;
+      const int i0 = atomicAdd(P.split_ctr + 1, ns);
+      P.split_tile[m] = (int)t;
+      for (int j = 0; j < ns; ++j) P.split_item[i0 + j] = make_int2(m, j);
+    }
+    const unsigned mh = __ballot_sync(0xffffffffu, c >= kHeavy && c < kSplit);
     int bh = 0;
     if (lane == 0 && mh) bh = atomicAdd(P.heavy, __popc(mh));
     bh = __shfl_sync(0xffffffffu, bh, 0);
-    if (c >= kHeavy) P.heavy[1 + bh + __popc(mh & ((1u << lane) - 1u))] = (int)t;
+    if (c >= kHeavy && c < kSplit) P.heavy[1 + bh + __popc(mh & ((1u << lane) - 1u))] = (int)t;
   }
 }
 
@@ -157,6 +189,18 @@ __global__ void __launch_bounds__(256)
 encode_fill_kernel(const EncodeParams P) {
   unsigned long long pol_keep;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+  // split tiles are accumulated in place by several CTAs of the reduce pass: start them (and their
+  // per-cell counters) from zero bits = key 0 / 0.0f
+  const int nsplit = P.split_ctr[0];
+  for (int m = blockIdx.x; m < nsplit; m += gridDim.x) {
+    float* gdst;
+    int32_t* gcount;
+    const int ncell = tile_dest(P, P.split_tile[m], gdst, gcount);
+    float4* g4 = reinterpret_cast<float4*>(gdst);
+    for (int v = threadIdx.x; v < ncell * P.C4; v += blockDim.x) g4[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = threadIdx.x; c < kMaxCpt; c += blockDim.x) P.split_cnt[(int64_t)m * kMaxCpt + c] = 0;
+    if (threadIdx.x == 0) P.split_done[m] = 0;
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n;
        i += (int64_t)gridDim.x * blockDim.x) {
     int64_t cell[3];
@@ -216,6 +260,10 @@ __device__ __forceinline__ float4 add4(float4 a, float4 b) {
   return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
 }
 
+__device__ __forceinline__ void red_add_v4(float4* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 constexpr int kEncSchedSlots = 256;
 __device__ unsigned long long g_enc_sched[kEncSchedSlots][4];  // [next tile, finished CTAs, next phase-1 window, -]
 
@@ -232,6 +280,7 @@ encode_reduce_kernel(const EncodeParams P, int sched_slot) {
   __shared__ long long s_t0;
   __shared__ int s_npts[kGrab], s_start[kGrab];
   __shared__ int s_heavy[1][3];  // phase 1: (tile, points, CSR start)
+  __shared__ int s_last, s_split;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int kWarps = kRedThreads / 32;
@@ -251,17 +300,12 @@ encode_reduce_kernel(const EncodeParams P, int sched_slot) {
   bool in_flight = false;  // thread 0: a bulk store may still be reading s_work
 
   // One tile: empty -> 16 KB of streaming zero stores; occupied -> reduce in shared memory, one TMA store.
-  auto process_tile = [&](const int64_t t, const int npts, const int start) {
-    const int64_t b = t / P.tiles_all;
-    int64_t r = t - b * P.tiles_all;
-    int k = 0;
-    if (r >= P.tiles_per_sample[0]) { r -= P.tiles_per_sample[0]; k = 1;
-      if (r >= P.tiles_per_sample[1]) { r -= P.tiles_per_sample[1]; k = 2; } }
-    const int64_t cps = P.cells_per_sample[k];
-    const int64_t c0 = r * cpt;
-    const int ncell = (int)min((int64_t)cpt, cps - c0);
-    float* gdst = P.out[k] + (b * cps + c0) * C;
-    int32_t* gcount = P.cell_count ? P.cell_count + P.count_base[k] + b * cps + c0 : nullptr;
+  // split_m < 0: the whole tile. split_m >= 0: one item of split tile slot split_m — npts list entries from
+  // `start`; the partial result is folded into the output tile with reductions, the last item finalises it.
+  auto process_tile = [&](const int64_t t, const int npts, const int start, const int split_m) {
+    float* gdst;
+    int32_t* gcount;
+    const int ncell = tile_dest(P, t, gdst, gcount);
 
     if (npts == 0) {
       float4* g4 = reinterpret_cast<float4*>(gdst);
@@ -322,6 +366,60 @@ encode_reduce_kernel(const EncodeParams P, int sched_slot) {
       }
     }
     __syncthreads();
+    if (split_m >= 0) {
+      // ---- fold this item's partial rows into the output tile (keys / sums) and its cell counters ------
+      int32_t* gcnt = P.split_cnt + (int64_t)split_m * kMaxCpt;
+      for (int c = warp; c < ncell; c += kWarps) {
+        const int cnt = s_cnt[c];
+        if (cnt <= 0) continue;
+        const float* row = s_work + c * C;
+        float* grow = gdst + (int64_t)c * C;
+        for (int v = lane; v < C4; v += 32) {
+          if (REDUCE == TP_REDUCE_MAX) {
+            const uint4 kk = *reinterpret_cast<const uint4*>(row + v * 4);
+            unsigned* gk = reinterpret_cast<unsigned*>(grow + v * 4);
+            atomicMax(gk + 0, kk.x); atomicMax(gk + 1, kk.y); atomicMax(gk + 2, kk.z); atomicMax(gk + 3, kk.w);
+          } else {
+            const float4 x = *reinterpret_cast<const float4*>(row + v * 4);
+            red_add_v4(reinterpret_cast<float4*>(grow + v * 4), x);
+          }
+        }
+        if (lane == 0) atomicAdd(gcnt + c, cnt);
+      }
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        const int items = (P.tile_cnt[t] + kSub - 1) / kSub;
+        s_last = atomicAdd(P.split_done + split_m, 1) == items - 1;
+      }
+      __syncthreads();
+      if (!s_last) return;
+      // ---- last item of the tile: keys -> floats / sums -> means, in place (the tile is in L2) ---------
+      __threadfence();
+      for (int c = warp; c < ncell; c += kWarps) {
+        const int cnt = __ldcg(gcnt + c);
+        float4* grow = reinterpret_cast<float4*>(gdst + (int64_t)c * C);
+        for (int v = lane; v < C4; v += 32) {
+          float4 o = fill4;
+          if (cnt > 0) {
+            const float4 x = __ldcg(grow + v);
+            if (REDUCE == TP_REDUCE_MAX) {
+              o = make_float4(key2f(__float_as_uint(x.x)), key2f(__float_as_uint(x.y)), key2f(__float_as_uint(x.z)),
+                              key2f(__float_as_uint(x.w)));
+              if (P.clamp_zero) o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
+            } else if (REDUCE == TP_REDUCE_MEAN) {
+              const float d = (float)cnt;
+              o = make_float4(__fdiv_rn(x.x, d), __fdiv_rn(x.y, d), __fdiv_rn(x.z, d), __fdiv_rn(x.w, d));
+            } else {
+              o = x;
+            }
+          }
+          grow[v] = o;
+        }
+        if (gcount && lane == 0) gcount[c] = cnt;
+      }
+      return;  // tile_cnt[t] stays >= kSplit until the last CTA cleans up: phase 2 must keep skipping this tile
+    }
     // finalise touched cells in place: keys -> floats, or sum -> mean
     for (int c = warp; c < ncell; c += kWarps) {
       const int cnt = s_cnt[c];
@@ -357,6 +455,28 @@ encode_reduce_kernel(const EncodeParams P, int sched_slot) {
   // folds onto one z row of the yz / xz planes) is a ~50 us chain of gathers for one CTA; started
   // last it is the tail of the kernel, started first it hides under the streaming of the rest. The
   // scan pass listed them; CTAs pop them one at a time.
+  // ---- phase 0: items of the split tiles (the longest chains of all, cut into kSub-entry pieces) ------
+  const int nitems = P.split_ctr[1];
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) {
+      const long long i = (long long)atomicAdd(&sched[3], 1ull);
+      s_t0 = i;
+      if (i < nitems) {
+        const int2 it = P.split_item[i];
+        const int t = P.split_tile[it.x];
+        const int np = P.tile_cnt[t];  // stays >= kSplit until the last CTA of the launch cleans up
+        s_heavy[0][0] = t;
+        s_heavy[0][1] = min(kSub, np - it.y * kSub);
+        s_heavy[0][2] = P.tile_start[t] + it.y * kSub;
+        s_split = it.x;
+      }
+    }
+    __syncthreads();
+    if (s_t0 >= nitems) break;
+    process_tile(s_heavy[0][0], s_heavy[0][1], s_heavy[0][2], s_split);
+  }
+
   const int nheavy = P.heavy[0];
   for (;;) {
     __syncthreads();
@@ -372,7 +492,7 @@ encode_reduce_kernel(const EncodeParams P, int sched_slot) {
     }
     __syncthreads();
     if (s_t0 >= nheavy) break;
-    process_tile(s_heavy[0][0], s_heavy[0][1], s_heavy[0][2]);
+    process_tile(s_heavy[0][0], s_heavy[0][1], s_heavy[0][2], -1);
   }
 
   // ---- phase 2: everything else, in order -----------------------------------------------------
@@ -403,7 +523,7 @@ encode_reduce_kernel(const EncodeParams P, int sched_slot) {
       const int64_t t = t0 + gi;
       if (t >= P.tiles_total) break;
       if (s_npts[gi] >= kHeavy) continue;  // phase 1's
-      process_tile(t, s_npts[gi], s_start[gi]);
+      process_tile(t, s_npts[gi], s_start[gi], -1);
     }
   }
   __syncthreads();
@@ -415,11 +535,13 @@ encode_reduce_kernel(const EncodeParams P, int sched_slot) {
   __syncthreads();
   if (s_t0) {  // last CTA out: leave the heavy tiles' counters and the scheduler slot clean
     for (int i = tid; i < nheavy; i += kRedThreads) P.tile_cnt[P.heavy[1 + i]] = 0;
+    for (int i = tid; i < P.split_ctr[0]; i += kRedThreads) P.tile_cnt[P.split_tile[i]] = 0;
     __syncthreads();
     if (tid == 0) {
       sched[0] = 0;
       sched[1] = 0;
       sched[2] = 0;
+      sched[3] = 0;
       __threadfence();
     }
   }
@@ -511,7 +633,7 @@ static int cells_per_tile(int C) {
 
 struct EncodeLayout {
   int64_t tiles_per_sample[3], tiles_all, tiles_total;
-  int64_t off_cnt, off_start, off_heavy, off_rank, off_ent, bytes, tmax;
+  int64_t off_cnt, off_start, off_heavy, off_split, off_rank, off_ent, bytes, tmax, max_split, max_items;
 };
 
 static EncodeLayout encode_layout(const GeomDev& g, int batch, int64_t n, int C, const bool use[3]) {
@@ -536,7 +658,12 @@ static EncodeLayout encode_layout(const GeomDev& g, int batch, int64_t n, int C,
   L.off_cnt = 0;
   L.off_start = L.off_cnt + pad(tmax * 4);
   L.off_heavy = L.off_start + pad((tmax + 1) * 4);
-  L.off_rank = L.off_heavy + pad((tmax + 2) * 4);  // + the CSR cursor
+  L.off_split = L.off_heavy + pad((tmax + 2) * 4);  // + the CSR cursor
+  // split tiles: each holds >= kSplit of the 3n list entries; items: ceil(c / kSub) <= c / kSub + 1 each
+  L.max_split = 3 * n / kSplit + 1;
+  L.max_items = 3 * n / kSub + L.max_split + 1;
+  L.off_rank = L.off_split + pad(8) + pad(L.max_split * 4) + pad(L.max_items * 8) + pad(L.max_split * 4) +
+               pad(L.max_split * (int64_t)kMaxCpt * 4);
   L.off_ent = L.off_rank + pad(3 * n * 4);
   L.bytes = L.off_ent + pad(3 * n * 8);
   return L;
@@ -612,6 +739,15 @@ extern "C" int tp_encode_f32(const float* feats, int64_t feat_stride, int32_t C,
   P.tile_start = reinterpret_cast<int32_t*>(ws + L.off_start);
   P.heavy = reinterpret_cast<int32_t*>(ws + L.off_heavy);
   P.cursor = P.heavy + 1 + L.tmax;
+  {
+    auto pad = [](int64_t b) { return (b + 255) / 256 * 256; };
+    char* q = ws + L.off_split;
+    P.split_ctr = reinterpret_cast<int32_t*>(q); q += pad(8);
+    P.split_tile = reinterpret_cast<int32_t*>(q); q += pad(L.max_split * 4);
+    P.split_item = reinterpret_cast<int2*>(q); q += pad(L.max_items * 8);
+    P.split_done = reinterpret_cast<int32_t*>(q); q += pad(L.max_split * 4);
+    P.split_cnt = reinterpret_cast<int32_t*>(q);
+  }
   P.rank = reinterpret_cast<int32_t*>(ws + L.off_rank);
   P.entries = reinterpret_cast<int2*>(ws + L.off_ent);
   P.out[0] = out_xy;
@@ -638,7 +774,8 @@ extern "C" int tp_encode_f32(const float* feats, int64_t feat_stride, int32_t C,
     else encode_fill_kernel<TP_ARITH_TORCH_CPU><<<grid, 256, 0, s>>>(P);
     TP_LAUNCH_CHECK("encode_fill_kernel");
   } else {
-    TP_CUDA(cudaMemsetAsync(P.heavy, 0, 4, s));  // no points: no heavy tiles (the alloc pass did not run)
+    TP_CUDA(cudaMemsetAsync(P.heavy, 0, 4, s));  // no points: no heavy / split tiles (the alloc pass did not run)
+    TP_CUDA(cudaMemsetAsync(P.split_ctr, 0, 8, s));
   }
   constexpr int kSmem = kTileFloats * 4 + kMaxCpt * 4;  // 17 KB
   const size_t smem = kSmem;

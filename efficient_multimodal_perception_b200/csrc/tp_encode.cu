@@ -35,8 +35,8 @@ constexpr int kRedThreads = 128;   // small CTAs, ~10 resident per SM: that many
 constexpr int kRedCtasPerSm = 10;
 constexpr int kGrab = 4;           // tiles taken per scheduler atomic
 constexpr int kHeavy = 48;         // tiles with at least this many points are reduced first
-constexpr int kSplit = 256;        // tiles with at least this many points are cut into items of kSub list entries,
-constexpr int kSub = 128;          // reduced by different CTAs and combined in the output tile itself
+constexpr int kSplit = 384;        // tiles with at least this many points are cut into items of kSub list entries,
+constexpr int kSub = 192;          // reduced by different CTAs and combined in the output tile itself
 
 struct EncodeParams {
   GeomDev g;

@@ -251,6 +251,14 @@ def planes_to_channels_last(planes: Sequence[torch.Tensor]) -> List[torch.Tensor
     return out
 
 
+def _check_out(out, B, Cc, Q, device):
+    if out is None:
+        return torch.empty((B, Cc, Q), dtype=torch.float32, device=device)
+    if tuple(out.shape) != (B, Cc, Q) or not out.is_contiguous() or not out.is_cuda:
+        raise TriplaneError("sample3: bad `out`")
+    return out
+
+
 def sample3(planes: Union[torch.Tensor, Sequence[torch.Tensor]], queries: torch.Tensor, lo, vs, half, *,
             arith: str = "cuda", channels_last: bool = False, out: Optional[torch.Tensor] = None,
             grid_dims: Optional[Sequence[int]] = None) -> torch.Tensor:
@@ -274,7 +282,42 @@ def sample3(planes: Union[torch.Tensor, Sequence[torch.Tensor]], queries: torch.
         raise TriplaneError(f"queries must be [B,Q,3], got {tuple(queries.shape)}")
     queries = queries.contiguous()
     B, Q, _ = queries.shape
-    nhwc = list(planes) if channels_last else planes_to_channels_last(planes)
+    sg = L.make_sample_geom(lo, vs, half)
+    dims = None
+    if grid_dims is not None:
+        h, w, d = (int(v) for v in grid_dims)
+        if h * w * d != Q:
+            raise TriplaneError(f"sample3: grid_dims {tuple(grid_dims)} do not multiply to Q={Q}")
+        dims = (C.c_int32 * 3)(h, w, d)
+    if not channels_last:
+        # reference layout in: ONE C-ABI call = conversion kernel + gather kernel
+        srcs = []
+        for k, p in enumerate(planes):
+            _need_cuda(p, f"plane {k}")
+            if p.dim() != 4:
+                raise TriplaneError(f"plane {k} must be [B,C,H,W], got {tuple(p.shape)}")
+            if p.stride(3) != 1 or p.stride(2) != p.shape[3] or p.stride(1) != p.shape[2] * p.shape[3]:
+                p = p.contiguous()
+            srcs.append(p)
+        Cc = srcs[0].shape[1]
+        if any(p.shape[0] != B or p.shape[1] != Cc for p in srcs):
+            raise TriplaneError("planes must share the queries' batch size and one channel count")
+        arr = _plane_array(srcs)
+        ws_floats = sum(B * Cc * p.shape[2] * p.shape[3] for p in srcs)
+        ws = torch.empty(ws_floats, dtype=torch.float32, device=queries.device)
+        out = _check_out(out, B, Cc, Q, queries.device)
+        if Q:
+            if dims is not None:
+                L.check(L.lib().tp_sample3_grid_nchw_f32(C.byref(arr), Cc, queries.data_ptr(), C.byref(dims), B, C.byref(sg),
+                                                         _ARITH[arith], out.data_ptr(), ws.data_ptr(), ws_floats,
+                                                         _stream(queries)), "tp_sample3_grid_nchw_f32")
+            else:
+                L.check(L.lib().tp_sample3_nchw_f32(C.byref(arr), Cc, queries.data_ptr(), Q, B, C.byref(sg), _ARITH[arith],
+                                                    out.data_ptr(), ws.data_ptr(), ws_floats, _stream(queries)),
+                        "tp_sample3_nchw_f32")
+            launch_count += 2
+        return out
+    nhwc = list(planes)
     Cc = nhwc[0].shape[-1]
     for k, p in enumerate(nhwc):
         _need_cuda(p, f"plane {k}")
@@ -285,16 +328,8 @@ def sample3(planes: Union[torch.Tensor, Sequence[torch.Tensor]], queries: torch.
         arr[k].data = p.data_ptr()
         arr[k].batch_stride = p.stride(0)
         arr[k].H, arr[k].W = p.shape[1], p.shape[2]
-    sg = L.make_sample_geom(lo, vs, half)
-    if out is None:
-        out = torch.empty((B, Cc, Q), dtype=torch.float32, device=queries.device)
-    elif tuple(out.shape) != (B, Cc, Q) or not out.is_contiguous() or not out.is_cuda:
-        raise TriplaneError("sample3: bad `out`")
-    if grid_dims is not None:
-        h, w, d = (int(v) for v in grid_dims)
-        if h * w * d != Q:
-            raise TriplaneError(f"sample3: grid_dims {tuple(grid_dims)} do not multiply to Q={Q}")
-        dims = (C.c_int32 * 3)(h, w, d)
+    out = _check_out(out, B, Cc, Q, queries.device)
+    if dims is not None:
         L.check(L.lib().tp_sample3_grid_nhwc_f32(C.byref(arr), Cc, queries.data_ptr(), C.byref(dims), B,
                                                  C.byref(sg), _ARITH[arith], out.data_ptr(), _stream(queries)),
                 "tp_sample3_grid_nhwc_f32")

@@ -259,6 +259,29 @@ def bench_decode_device(args, dev, barrier, sampler):
         variants[kind] = {"Q": qv.shape[1], "kernel_ms_avg": va, "kernel_ms_median": vm, "queries_per_s": qv.shape[1] / (va * 1e-3),
                           "algorithmic_bytes": vb, "achieved_gbs": vb / (va * 1e-3) / 1e9}
         del qs, outs
+    # range-image points of configs/triplane_surf_sam.py, bs=8: [8,32,1024,3] (30 % empty pixels at
+    # the origin), per-query kernel, one stacked triplane per sample
+    from efficient_multimodal_perception_b200 import synth
+    Br = 8
+    rq = synth.range_image_points(Br, seed=1003).reshape(Br, -1, 3).contiguous()
+    rbytes = Br * decode_bytes(rq.shape[1])
+    rsets = max(4, -(-3 * L2_BYTES // rbytes))
+    r_tri = [ops.planes_to_channels_last([t[:, 0], t[:, 1], t[:, 2]])
+             for t in (synth.triplane_stacked(Br, C_DEC, PLANE, seed=1003 + s).to(dev) for s in range(rsets))]
+    r_q = [rq.to(dev).clone() for _ in range(rsets)]
+    r_out = [torch.empty(Br, C_DEC, rq.shape[1], device=dev) for _ in range(rsets)]
+
+    def launch_r(i):
+        ops.sample3(r_tri[i % rsets], r_q[i % rsets], OCC_LO, OCC_VS, OCC_HALF, channels_last=True, out=r_out[i % rsets])
+
+    for i in range(rsets):
+        launch_r(i)
+    torch.cuda.synchronize()
+    ra, rm, _ = kernel_time_ms(launch_r, min(reps, 200), rsets)
+    variants["range_points_bs8"] = {"Q": Br * rq.shape[1], "kernel_ms_avg": ra, "kernel_ms_median": rm,
+                                    "queries_per_s": Br * rq.shape[1] / (ra * 1e-3), "algorithmic_bytes": rbytes,
+                                    "achieved_gbs": rbytes / (ra * 1e-3) / 1e9}
+    del r_tri, r_q, r_out
     sampler.active.clear()
     return dict(Q=Q, nsets=nsets, ms_total=ms, kernel_ms_avg=k_avg, kernel_ms_med=k_med, kernel_ms_min=k_min,
                 launches=args.steps * 2, sets=sets, variants=variants)

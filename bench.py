@@ -478,6 +478,31 @@ def cpu_baseline_decode(q_host, budget_s=15.0):
                        f"(oracle.sample_points_triplane_stacked = the reference's 3 x F.grid_sample path on torch-CPU)"), ref
 
 
+def bind_to_gpu_numa_node(local: int):
+    """Pin this rank's threads (and therefore its pinned host buffers, first-touch) to the NUMA node of its GPU:
+    the e2e leg moves ~96 MB per step over PCIe per rank and 8 ranks on the wrong socket share one inter-socket
+    link. Best effort: returns the node or None."""
+    try:
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        dev_id = torch.cuda.get_device_properties(local).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def run_b200(args):
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -485,6 +510,7 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU path (use --impl reference)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     dev = torch.device("cuda", local)
     import torch.distributed as dist
     if world > 1:
@@ -564,7 +590,7 @@ def run_b200(args):
             "cpu_baseline": cpu,
             "e2e": {"value": world * Q / (e2e_ms * 1e-3), "unit": "queries/s",
                     "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e_ms,
-                    "steps": e2e["steps"], "api": "tp_sample3_grid_host_f32 / tp_sample3_host_f32 (C ABI, pinned host buffers; H2D planes+queries, "
+                    "steps": e2e["steps"], "numa_node_rank0": numa, "api": "tp_sample3_grid_host_f32 / tp_sample3_host_f32 (C ABI, pinned host buffers; H2D planes+queries, "
                                                   "D2H full result, synchronised every step)"},
             "gpu_launches": dec["launches"],
             "variants_kernel_only": {k: dict(v, frac=v["achieved_gbs"] / peak) for k, v in dec["variants"].items()},

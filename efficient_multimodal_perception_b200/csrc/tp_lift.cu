@@ -120,12 +120,33 @@ lift_kernel(const LiftParams P) {
     const int64_t p = p0 + pi;
     if (p >= P.n_total) break;
     float4* orow = reinterpret_cast<float4*>(P.out + p * P.Cf);
-#pragma unroll 2
+    // which cameras see this point (warp-uniform bit mask): most points are seen by none or by one
+    const unsigned seen = __ballot_sync(0xffffffffu, lane < P.ncam && s_om[warp][pi * kLiftCams + (lane & 7)].y != 0);
+    if (seen == 0) {
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 6
+      for (int c4 = lane; c4 < C4; c4 += 32) st_stream_f4(orow + c4, z, pol_out);
+      continue;
+    }
+    if ((seen & (seen - 1)) == 0) {
+      // exactly one camera: 0 + f == f bit for bit except f == -0 (-> +0), which the add below reproduces
+      const int cam = __ffs(seen) - 1;
+      const int2 om = s_om[warp][pi * kLiftCams + cam];
+      const float4 w = s_w[warp][pi * kLiftCams + cam];
+      const float4* pl = feats + (int64_t)(om.y >> 4) * map4;
+#pragma unroll 3
+      for (int c4 = lane; c4 < C4; c4 += 32) {
+        const float4 f = plane_taps<true>(pl + c4, om.x, C4, WC4, w, om.y & 15, pol_feat);
+        st_stream_f4(orow + c4, make_float4(__fadd_rn(0.f, f.x), __fadd_rn(0.f, f.y), __fadd_rn(0.f, f.z),
+                                            __fadd_rn(0.f, f.w)), pol_out);
+      }
+      continue;
+    }
     for (int c4 = lane; c4 < C4; c4 += 32) {
       float4 total = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int cam = 0; cam < P.ncam; ++cam) {
+      for (unsigned m = seen; m; m &= m - 1) {  // cameras in ascending order
+        const int cam = __ffs(m) - 1;
         const int2 om = s_om[warp][pi * kLiftCams + cam];
-        if (om.y == 0) continue;  // warp-uniform
         const float4 w = s_w[warp][pi * kLiftCams + cam];
         const float4* pl = feats + (int64_t)(om.y >> 4) * map4 + c4;
         const float4 f = plane_taps<true>(pl, om.x, C4, WC4, w, om.y & 15, pol_feat);

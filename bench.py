@@ -443,20 +443,23 @@ def bench_encode_point_sharded(args, dev, barrier, rank, world):
     my_pts, my_feats = pts[lo:hi].to(dev), feats[lo:hi].contiguous().to(dev)
     off = synth.batch_offsets([hi - lo]).to(dev)
 
-    def step():
-        return tpd.encode_point_sharded(my_feats, my_pts, off, G["pc_range"], G["voxel_size"], G["grid_size"],
-                                        G["split"], reduce="max")
+    out = {}
+    for strategy in ("planes", "points"):
+        def step(strategy=strategy):
+            return tpd.encode_point_sharded(my_feats, my_pts, off, G["pc_range"], G["voxel_size"], G["grid_size"],
+                                            G["split"], reduce="max", strategy=strategy)
 
-    for _ in range(3):
-        step()
-    steps = max(5, min(args.steps, 30))
-
-    def run():
-        for _ in range(steps):
+        for _ in range(3):
             step()
+        steps = max(5, min(args.steps, 30))
 
-    ms = time_region(run, barrier) / steps
-    return dict(n=pts.shape[0], ms_per_step=ms, steps=steps, allreduce_bytes=4 * G["channels"] * 839680)
+        def run(step=step, steps=steps):
+            for _ in range(steps):
+                step()
+
+        out[strategy] = time_region(run, barrier) / steps
+    return dict(n=pts.shape[0], ms_per_step=out["planes"], ms_points=out["points"], steps=steps,
+                allreduce_bytes=4 * G["channels"] * 839680, gather_bytes=pts.shape[0] * (12 + 4 * G["channels"]))
 
 
 def cpu_baseline_decode(q_host, budget_s=15.0):
@@ -531,10 +534,11 @@ def run_b200(args):
     eps = bench_encode_point_sharded(args, dev, barrier, rank, world) if world > 1 else None
     # max over ranks (device time)
     t = torch.tensor([dec["ms_total"], enc["ms_per_step"], dec["kernel_ms_avg"], eps["ms_per_step"] if eps else 0.0,
-                      encd["ms_per_step"], lift["ms_per_step"], lift["kernel_ms"]], device=dev, dtype=torch.float64)
+                      encd["ms_per_step"], lift["ms_per_step"], lift["kernel_ms"], eps["ms_points"] if eps else 0.0],
+                     device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, enc_ms, k_avg, eps_ms, encd_ms, lift_ms, lift_k_ms = (float(x) for x in t.tolist())
+    ms_total, enc_ms, k_avg, eps_ms, encd_ms, lift_ms, lift_k_ms, eps_pts_ms = (float(x) for x in t.tolist())
     clocks = sampler.stop()
 
     q_host = decode_queries(args.queries)
@@ -627,10 +631,15 @@ def run_b200(args):
         if eps:
             line["encode_point_sharded"] = {
                 "workload": f"ONE 10-sweep sample ({eps['n']} raw pts) point-sharded over {world} GPUs, geometry "
-                            f"128x128x80 C=128: partial planes -> NCCL all-reduce(max) of {eps['allreduce_bytes'] / 1e6:.0f} MB "
-                            f"-> finalise (strong scaling of one sample; the sample-sharded path above needs no collective)",
-                "value": eps["n"] / (eps_ms * 1e-3), "unit": "points/s", "ms_per_step": eps_ms, "steps": eps["steps"],
-                "allreduce_bytes_per_step": eps["allreduce_bytes"]}
+                            f"128x128x80 C=128; strategy 'planes': partial planes -> NCCL all-reduce(max) of {eps['allreduce_bytes'] / 1e6:.0f} MB "
+                            f"-> finalise; strategy 'points': NCCL all-gather of the point shards -> full encode on every rank "
+                            f"(strong scaling of one sample; value = the faster; the sample-sharded path above needs no collective)",
+                "value": eps["n"] / (min(eps_ms, eps_pts_ms) * 1e-3), "unit": "points/s",
+                "ms_per_step": min(eps_ms, eps_pts_ms), "steps": eps["steps"],
+                "strategy_planes": {"ms_per_step": eps_ms, "allreduce_bytes_per_step": eps["allreduce_bytes"]},
+                "strategy_points": {"ms_per_step": eps_pts_ms, "allgather_bytes_per_step": eps["gather_bytes"],
+                                    "what": "all-gather of the point shards (12 + 4C bytes per point), full fused encode on "
+                                            "every rank: same planes, no partial planes / finalise pass"}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

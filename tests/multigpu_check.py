@@ -29,16 +29,17 @@ def main():
     for reduce in ("max", "mean"):
         ref = ops.encode(torch.cat(feats).to(dev), full_off, G["pc_range"], G["voxel_size"], G["grid_size"], G["split"],
                          points=torch.cat(raw).to(dev), reduce=reduce)
-        got = tpd.encode_point_sharded(torch.cat(my_feats).to(dev), torch.cat(my_raw).to(dev), my_off, G["pc_range"],
-                                       G["voxel_size"], G["grid_size"], G["split"], reduce=reduce)
-        for a, b in zip(got, ref):
-            if reduce == "max":
-                good = torch.equal(a, b)
-            else:
-                good = float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
-            ok &= bool(good)
-            if not good:
-                print(f"[rank {rank}] {reduce}: mismatch, max diff {float((a - b).abs().max())}", flush=True)
+        for strategy in ("planes", "points"):
+            got = tpd.encode_point_sharded(torch.cat(my_feats).to(dev), torch.cat(my_raw).to(dev), my_off, G["pc_range"],
+                                           G["voxel_size"], G["grid_size"], G["split"], reduce=reduce, strategy=strategy)
+            for a, b in zip(got, ref):
+                if reduce == "max":
+                    good = torch.equal(a, b)
+                else:
+                    good = float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
+                ok &= bool(good)
+                if not good:
+                    print(f"[rank {rank}] {reduce}/{strategy}: mismatch, max diff {float((a - b).abs().max())}", flush=True)
     # decode: each rank samples its slice of the queries; gathered result == full result
     tri = synth.triplane_stacked(1, 32, 128, seed=9).to(dev)
     q = synth.uniform_queries(100003, seed=10)[None].to(dev)

@@ -82,6 +82,14 @@ def _worker(rank, world, port, ret):
             o += n
             ok &= float((m.double() - ref.reshape(-1, C)).abs().max()) <= 1e-5 * float(ref.abs().max())
         ok &= int(cnt.sum()) == 3 * 1600  # every point counted once per plane (grid divisible: nothing dropped)
+        # "points" strategy: all-gather of the shards -> every rank holds the whole batch, sample-major
+        my_off = synth.batch_offsets([f.shape[0] for f in my_f])
+        f_all, i_all, off_all = tpd.gather_point_shards(torch.cat(my_f), torch.cat(my_i).float(), my_off)
+        ok &= off_all.tolist() == synth.batch_offsets([f.shape[0] for f in feats]).tolist()
+        ok &= torch.equal(f_all, torch.cat(feats)) and torch.equal(i_all.int(), torch.cat(inds))
+        g_inds = [i_all[off_all[b]:off_all[b + 1]].int() for b in range(len(inds))]
+        g = O.encode_pooled(f_all, O.cat_indices(g_inds), GRID, SPLIT, len(inds))
+        ok &= all(torch.equal(a, b) for a, b in zip(g[:3], full[:3]))
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()

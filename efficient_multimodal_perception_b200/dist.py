@@ -82,15 +82,28 @@ def gather_point_shards(feats: torch.Tensor, points: torch.Tensor, offsets: torc
     sizes = offs[:, -1].tolist()
     nmax = max(max(sizes), 1)
 
-    def gather(x):
-        pad = torch.zeros((nmax,) + tuple(x.shape[1:]), dtype=x.dtype, device=dev)
-        pad[:x.shape[0]] = x
-        parts = [torch.empty_like(pad) for _ in range(world)]
-        dist.all_gather(parts, pad, group=group)
-        return parts
+    even = all(sz == nmax for sz in sizes)
 
-    f_parts, p_parts = gather(feats), gather(points)
+    def gather(x):
+        if even:  # the usual case (shard_bounds splits differ by at most one row): no padding copy
+            pad = x.contiguous()
+        else:
+            pad = torch.zeros((nmax,) + tuple(x.shape[1:]), dtype=x.dtype, device=dev)
+            pad[:x.shape[0]] = x
+        flat = torch.empty((world * nmax,) + tuple(x.shape[1:]), dtype=x.dtype, device=dev)
+        dist.all_gather_into_tensor(flat, pad, group=group)
+        return flat
+
+    f_flat, p_flat = gather(feats), gather(points)
     B = offsets.numel() - 1
+    ends = [0]
+    for b in range(B):
+        ends.append(ends[-1] + int((offs[:, b + 1] - offs[:, b]).sum()))
+    off_all = torch.tensor(ends, dtype=torch.int64, device=dev)
+    if even and B == 1:
+        return f_flat, p_flat, off_all  # rank order IS sample-major order: nothing to move
+    f_parts = [f_flat[r * nmax:(r + 1) * nmax] for r in range(world)]
+    p_parts = [p_flat[r * nmax:(r + 1) * nmax] for r in range(world)]
     f_out, p_out = [], []
     for b in range(B):
         for r in range(world):
@@ -98,12 +111,8 @@ def gather_point_shards(feats: torch.Tensor, points: torch.Tensor, offsets: torc
             if hi > lo:
                 f_out.append(f_parts[r][lo:hi])
                 p_out.append(p_parts[r][lo:hi])
-    ends = [0]
-    for b in range(B):
-        ends.append(ends[-1] + int((offs[:, b + 1] - offs[:, b]).sum()))
     cat = lambda xs, like: torch.cat(xs) if xs else like[:0]  # noqa: E731
-    return (cat(f_out, feats).contiguous(), cat(p_out, points).contiguous(),
-            torch.tensor(ends, dtype=torch.int64, device=dev))
+    return cat(f_out, feats).contiguous(), cat(p_out, points).contiguous(), off_all
 
 
 def encode_point_sharded(feats: torch.Tensor, points: torch.Tensor, offsets: torch.Tensor, pc_range, voxel_size,

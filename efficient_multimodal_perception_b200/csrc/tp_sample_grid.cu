@@ -27,6 +27,12 @@ struct GridParams {
 };
 
 constexpr int kGridThreads = 256;
+// resident CTAs per SM: 3 (85 registers) measured equal or better than 4 (64 registers, spills in the block loop whose
+// local loads queue behind the store stream): 640k lattice 23.6 / 23.6 us, roi 9.9 / 10.5, elev 28.7 / 30.3, 8 x roi 46.6 / 47.0
+#ifndef TP_GRID_CTAS_PER_SM
+#define TP_GRID_CTAS_PER_SM 3
+#endif
+constexpr int kGridCtasPerSm = TP_GRID_CTAS_PER_SM;
 constexpr int kBK = 16;  // lattice block extent along d
 constexpr int kBJ = 8;   // ... along w: a warp-wide 16-byte store covers 8 (j) x 4 (k/4) = 512 contiguous bytes when d == 16
 constexpr int kFallbackWarps = 4;
@@ -115,11 +121,34 @@ __device__ __forceinline__ BlockPos block_pos(const GridParams& G, int blk) {
   return p;
 }
 
+// The per-query path for a block that is not a lattice. Kept out of line: its register needs (the flat kernel's
+// tile routine) must not shape the register allocation of the table path.
+template <int ARITH, int C4T, int BI>
+__device__ __noinline__ void grid_fallback(const GridParams& G, int b, int i0, int j0, int k0, float* smem) {
+  constexpr int BJ = kBJ;
+  const SampleParams& P = G.S;
+  const int warp = threadIdx.x >> 5;
+  if (warp >= kFallbackWarps) return;
+  const unsigned long long pol_planes = policy_evict_last(), pol_out = policy_evict_first();
+  const int ni = min(BI, G.h - i0), nj = min(BJ, G.w - j0), nk = min(kBK, G.d - k0);
+  float* sp = smem + warp * (kParamWords + kTileWords);
+  float* st = sp + kParamWords;
+  for (int t = warp; t < BI * BJ / 2; t += kFallbackWarps) {
+    const int r0 = 2 * t, r1 = 2 * t + 1;
+    const int ia0 = r0 / BJ, ja0 = r0 % BJ, ia1 = r1 / BJ, ja1 = r1 % BJ;
+    const int n0 = (ia0 < ni && ja0 < nj) ? nk : 0, n1 = (ia1 < ni && ja1 < nj) ? nk : 0;
+    if (n0 == 0 && n1 == 0) continue;
+    const int64_t run0 = ((int64_t)(i0 + ia0) * G.w + j0 + ja0) * G.d + k0;
+    const int64_t run1 = ((int64_t)(i0 + ia1) * G.w + j0 + ja1) * G.d + k0;
+    sample_tile<ARITH, C4T>(P, b, run0, run1, n0, n1, sp, st, pol_planes, pol_out, G.vec_ok != 0);
+  }
+}
+
 // Persistent CTAs: block n+1's queries are prefetched into L2 while block n is gathered and written,
 // so the only DRAM-latency-bound step of a block (reading its 12 B/query) is off the critical path.
 template <int ARITH, int C4T, int BI>
-__global__ void __launch_bounds__(kGridThreads, 4)
-sample3_grid_kernel(const GridParams G) {
+__global__ void __launch_bounds__(kGridThreads, kGridCtasPerSm)
+sample3_grid_kernel(const __grid_constant__ GridParams G) {
   using Cfg = GridCfg<BI>;
   constexpr int BJ = kBJ;
   constexpr int QPT = BI * BJ * kBK / kGridThreads;  // queries per thread
@@ -150,9 +179,8 @@ sample3_grid_kernel(const GridParams G) {
   // output phase: lane -> (j, 4 consecutive k)
   const int kg = lane & 3, jj = lane >> 2;
 
-  int blk = blockIdx.x;
-  BlockPos bp = block_pos<BI>(G, blk);
-  for (;;) {
+  for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const BlockPos bp = block_pos<BI>(G, blk);  // recomputed per block: carrying it across the loop spills
     const int b = bp.b, i0 = bp.i0, j0 = bp.j0, k0 = bp.k0;
     const int ni = min(BI, G.h - i0), nj = min(BJ, G.w - j0), nk = min(kBK, G.d - k0);
     const float* q00 = P.queries + ((int64_t)b * P.Q + ((int64_t)i0 * G.w + j0) * G.d + k0) * 3;  // block origin
@@ -201,9 +229,8 @@ sample3_grid_kernel(const GridParams G) {
 
     // ---- prefetch the next block's queries (DRAM -> L2) behind this block's gathers and stores ---
     const int next = blk + gridDim.x;
-    BlockPos np = bp;
     if (next < nblocks) {
-      np = block_pos<BI>(G, next);
+      const BlockPos np = block_pos<BI>(G, next);
       if (np.j0 + aj < G.w && np.k0 + ak < G.d) {
         const float* n00 = P.queries + ((int64_t)np.b * P.Q + ((int64_t)np.i0 * G.w + np.j0) * G.d + np.k0) * 3;
         // one lane per 32 bytes of the (j,k) run is plenty: 12 B per query
@@ -219,19 +246,7 @@ sample3_grid_kernel(const GridParams G) {
 
     if (!separable) {
       // ---- per-query fallback: the flat kernel's tile routine on pairs of (i,j) columns ---------
-      if (warp < kFallbackWarps) {
-        float* sp = smem + warp * (kParamWords + kTileWords);
-        float* st = sp + kParamWords;
-        for (int t = warp; t < BI * BJ / 2; t += kFallbackWarps) {
-          const int r0 = 2 * t, r1 = 2 * t + 1;
-          const int ia0 = r0 / BJ, ja0 = r0 % BJ, ia1 = r1 / BJ, ja1 = r1 % BJ;
-          const int n0 = (ia0 < ni && ja0 < nj) ? nk : 0, n1 = (ia1 < ni && ja1 < nj) ? nk : 0;
-          if (n0 == 0 && n1 == 0) continue;
-          const int64_t run0 = ((int64_t)(i0 + ia0) * G.w + j0 + ja0) * G.d + k0;
-          const int64_t run1 = ((int64_t)(i0 + ia1) * G.w + j0 + ja1) * G.d + k0;
-          sample_tile<ARITH, C4T>(P, b, run0, run1, n0, n1, sp, st, pol_planes, pol_out, G.vec_ok != 0);
-        }
-      }
+      grid_fallback<ARITH, C4T, BI>(G, b, i0, j0, k0, smem);
       __syncthreads();  // the fallback tiles alias the next block's tables
     } else {
       const float4* const pl0 = reinterpret_cast<const float4*>(P.plane[0] + (int64_t)b * P.bstride[0]) + l8;
@@ -303,16 +318,13 @@ sample3_grid_kernel(const GridParams G) {
         if (ch + 1 < nchunk) __syncthreads();
       }
     }
-    if (next >= nblocks) break;
-    blk = next;
-    bp = np;
   }
 }
 
 template <int ARITH, int C4T, int BI>
 static void launch_grid(const GridParams& G, int batch, cudaStream_t s) {
   // persistent CTAs, 4 per SM; TP_GRID_CTAS (experiments) overrides the grid size
-  int64_t blocks = G.nblocks < 4 * kSMs ? G.nblocks : 4 * kSMs;
+  int64_t blocks = G.nblocks < kGridCtasPerSm * kSMs ? G.nblocks : kGridCtasPerSm * kSMs;
   if (const char* e = getenv("TP_GRID_CTAS")) {
     const int64_t v = atoll(e);
     if (v > 0) blocks = v < G.nblocks ? v : G.nblocks;

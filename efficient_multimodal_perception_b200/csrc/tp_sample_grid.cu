@@ -27,10 +27,11 @@ struct GridParams {
 };
 
 constexpr int kGridThreads = 256;
-// resident CTAs per SM: 3 (85 registers) measured equal or better than 4 (64 registers, spills in the block loop whose
-// local loads queue behind the store stream): 640k lattice 23.6 / 23.6 us, roi 9.9 / 10.5, elev 28.7 / 30.3, 8 x roi 46.6 / 47.0
+// resident CTAs per SM: 4 (64 registers). 3 (85 registers, no spills in the block loop) is a little faster when the
+// planes are warm in L2 (roi 9.9 vs 10.5 us, elev 28.7 vs 30.3) but slower in bench.py's rotation over cold plane
+// sets (640k lattice 24.8 vs 23.8 us): the fourth CTA hides the DRAM latency of first touches.
 #ifndef TP_GRID_CTAS_PER_SM
-#define TP_GRID_CTAS_PER_SM 3
+#define TP_GRID_CTAS_PER_SM 4
 #endif
 constexpr int kGridCtasPerSm = TP_GRID_CTAS_PER_SM;
 constexpr int kBK = 16;  // lattice block extent along d

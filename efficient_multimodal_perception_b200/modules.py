@@ -197,7 +197,10 @@ class TriplaneHotPathMixin:
         return lo, vs
 
     def voxelize_points(self, points):
-        return voxelize_points(points, self.pc_range, self.voxel_size, self.tp_arith)
+        # PointTriplane crops / indexes with pc_range + voxel_size (point_triplane.py:148-156), its fine-tune twin
+        # PointTriplaneOcc with triplane_range + triplane_voxel_size (point_triplane_occ.py:147-155)
+        rng, vs = self._tp_geometry()
+        return voxelize_points(points, rng, vs, self.tp_arith)
 
     def point_to_cam(self, points, img_features, img_metas):
         return point_to_cam(points, img_features, img_metas, self.tp_arith)

@@ -53,6 +53,42 @@ def test_argument_errors_are_reported_without_a_device():
     assert rc == -4 and b"workspace" in lib.tp_last_error()
 
 
+def test_new_entry_points_validate_arguments_without_a_device():
+    lib = L.lib()
+    sg = L.make_sample_geom([0, 0, 0], [1, 1, 1], [1, 1, 1])
+    planes = (L.tp_plane * 3)()
+    dims = (C.c_int32 * 3)(4, 4, 16)
+    rc = lib.tp_sample3_grid_nhwc_f32(C.byref(planes), 32, 16, C.byref(dims), 1, C.byref(sg), 0, 16, None)
+    assert rc == -1 and b"plane 0 is null" in lib.tp_last_error()
+    rc = lib.tp_sample3_grid_nhwc_f32(C.byref(planes), 30, 16, C.byref(dims), 1, C.byref(sg), 0, 16, None)
+    assert rc == -2
+    bad = (C.c_int32 * 3)(4, -1, 16)
+    rc = lib.tp_sample3_grid_nhwc_f32(C.byref(planes), 32, 16, C.byref(bad), 1, C.byref(sg), 0, 16, None)
+    assert rc == -2 and b"dims" in lib.tp_last_error()
+    # lift: camera slots, channel multiple, null pointers
+    rc = lib.tp_lift_cam_f32(16, 3, 10, 16, 1, 16, 9, 16, 32, 768, 16, 512.0, 256.0, 0, 16, None)
+    assert rc == -2 and b"ncam" in lib.tp_last_error()
+    rc = lib.tp_lift_cam_f32(16, 3, 10, 16, 1, 16, 6, 16, 32, 770, 16, 512.0, 256.0, 0, 16, None)
+    assert rc == -2 and b"Cf" in lib.tp_last_error()
+    rc = lib.tp_lift_cam_f32(None, 3, 10, 16, 1, 16, 6, 16, 32, 768, 16, 512.0, 256.0, 0, 16, None)
+    assert rc == -1
+    assert lib.tp_lift_cam_f32(None, 3, 0, None, 1, None, 6, 16, 32, 768, None, 512.0, 256.0, 0, None, None) == 0  # no points
+    rc = lib.tp_lift_cam_f32(16, 3, 10, 16, 1, 16, 6, 16, 32, 768, 16, 512.0, 256.0, 5, 16, None)
+    assert rc == -3
+    # backward entry points
+    geom = L.make_geom([-1, -1, -1, 1, 1, 1], (1, 1, 1), (4, 4, 4), (1, 1, 1))
+    rc = lib.tp_encode_backward_f32(16, 8, 8, 16, 5, 16, 1, C.byref(geom), 2, 0, None, None, None, None, None, None,
+                                    None, 16, None)
+    assert rc == -3 and b"MAX or MEAN" in lib.tp_last_error()
+    rc = lib.tp_encode_backward_f32(16, 8, 8, 16, 5, 16, 1, C.byref(geom), 1, 0, None, None, None, None, None, None,
+                                    None, 16, None)
+    assert rc == -1 and b"cell_count" in lib.tp_last_error()
+    rc = lib.tp_sample3_backward_nhwc_f32(C.byref(planes), 32, 16, 10, 1, C.byref(sg), 0, 16, None)
+    assert rc == -1
+    rc = lib.tp_sample3_backward_nhwc_f32(C.byref(planes), 32, 16, 10, 1, C.byref(sg), 9, 16, None)
+    assert rc == -3
+
+
 def test_cell_and_workspace_sizes():
     lib = L.lib()
     geom = L.make_geom([-25, -25, -5, 25, 25, 3], (0.4, 0.4, 0.1), (128, 128, 80), (5, 5, 4))

@@ -49,6 +49,24 @@ def test_mixin_geometry_resolution():
     assert Mae()._tp_geometry() == ([9] * 6, (3, 3, 3))
 
 
+def test_mixin_voxelize_uses_the_class_own_geometry(monkeypatch):
+    """PointTriplane crops with pc_range / voxel_size, its twin PointTriplaneOcc with triplane_range /
+    triplane_voxel_size (point_triplane.py:148-156 vs point_triplane_occ.py:147-155)."""
+    from efficient_multimodal_perception_b200 import modules
+    seen = []
+    monkeypatch.setattr(modules, "voxelize_points", lambda pts, rng, vs, arith: seen.append((rng, vs)) or ([], []))
+
+    class Pre(TriplaneHotPathMixin):
+        pc_range, voxel_size = [9] * 6, (3, 3, 3)
+
+    class Occ(TriplaneHotPathMixin):
+        pc_range, voxel_size, triplane_range, triplane_voxel_size = [9] * 6, (3, 3, 3), [1] * 6, (2, 2, 2)
+
+    Pre().voxelize_points([])
+    Occ().voxelize_points([])
+    assert seen == [([9] * 6, (3, 3, 3)), ([1] * 6, (2, 2, 2))]
+
+
 def test_synth_shapes():
     assert synth.lidar_sweep(1000, 1).shape == (1000, 11)
     assert synth.occ_gt_lattice().reshape(-1, 3).shape[0] == 640000

@@ -287,6 +287,34 @@ def bench_decode_device(args, dev, barrier, sampler):
                 launches=args.steps * 2, sets=sets, variants=variants)
 
 
+def torch_cuda_decode(q_dev, tri_dev, reps=5):
+    """The reference's own op sequence (normalise + 3 x F.grid_sample + 2 adds, triplane_occ.py:332-346) run by
+    torch on the same GPU: the GPU baseline the kernels replace. Returns ms per pass."""
+    import torch.nn.functional as F
+
+    def chain():
+        v = torch.zeros_like(q_dev)
+        for a in range(3):
+            v[..., a] = (q_dev[..., a] - OCC_LO[a]) / OCC_VS[a]
+        v = v / OCC_HALF[0] - 1
+        v = v[:, None]
+        xy = F.grid_sample(tri_dev[:, 0], v[..., [0, 1]], mode="bilinear", padding_mode="zeros", align_corners=False)
+        yz = F.grid_sample(tri_dev[:, 1], v[..., [1, 2]], mode="bilinear", padding_mode="zeros", align_corners=False)
+        xz = F.grid_sample(tri_dev[:, 2], v[..., [0, 2]], mode="bilinear", padding_mode="zeros", align_corners=False)
+        return xy + yz + xz
+
+    for _ in range(2):
+        chain()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        chain()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
 def bench_decode_e2e(args, Q_host, barrier):
     """Host buffers through the C ABI (tp_sample3_host_f32): H2D of planes + queries, conversion,
     gather, D2H of the full [C,Q] result, synchronised, every step."""
@@ -555,7 +583,7 @@ def run_b200(args):
         kbytes = decode_bytes(Q)
         achieved = kbytes / (k_avg * 1e-3) / 1e9
         kernel_name = ("tp::sample3_grid_kernel<0,8,8>" if QUERY_DIMS[args.queries] else "tp::sample3_kernel<0,8>")
-        cpu, parity = None, None
+        cpu, parity, torch_ms = None, None, None
         if world == 1:
             cpu, ref = cpu_baseline_decode(q_host)
             # live parity check of what was just timed (device result of set 0 and the e2e result)
@@ -563,6 +591,7 @@ def run_b200(args):
             dec["sets"].step(0)
             torch.cuda.synchronize()
             scale = float(ref.abs().max())
+            torch_ms = torch_cuda_decode(q0, tri0)
             out_cpu_arith = dec["sets"].ops.sample3(tri0, q0, OCC_LO, OCC_VS, OCC_HALF, arith="cpu",
                                                     grid_dims=QUERY_DIMS[args.queries])
             parity = {"note": "oracle = torch-CPU op chain; arith='cpu' replays it, the timed arith='cuda' replays "
@@ -592,6 +621,10 @@ def run_b200(args):
                          "kernel_ms_min": dec["kernel_ms_min"], "peak_source": peak_src,
                          "step_frac": kbytes / (ms_per_step * 1e-3) / 1e9 / peak},
             "cpu_baseline": cpu,
+            "torch_cuda_reference": (None if torch_ms is None else {
+                "value": Q / (torch_ms * 1e-3), "unit": "queries/s", "ms_per_step": torch_ms,
+                "what": "the reference's op sequence (normalise + 3 x F.grid_sample + sum) run by torch-CUDA on this GPU, "
+                        "same queries and planes; reported, not a target"}),
             "e2e": {"value": world * Q / (e2e_ms * 1e-3), "unit": "queries/s",
                     "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e_ms,
                     "steps": e2e["steps"], "numa_node_rank0": numa, "api": "tp_sample3_grid_host_f32 / tp_sample3_host_f32 (C ABI, pinned host buffers; H2D planes+queries, "

@@ -1,0 +1,284 @@
+// Occupancy head on the decode output: the reference's `Mlp` (mmdet3d/models/dense_heads/mlp.py:25-70) is three
+// bias-free 1x1x1 Conv3d with ReLU between them, C -> 2C -> C -> num_classes, applied to the sampled triplane
+// features [B,C,X,Y,Z] (triplane_occ.py:182-186). Per query that is a 32 -> 64 -> 32 -> 5 dense contraction: the one
+// GEMM-shaped piece next to the hot path. Here the three layers run back to back on the 5th-gen
+// tensor cores for a tile of 128 queries: A (activations) and B (weights) in shared memory in the canonical
+// K-major SWIZZLE_128B layout, tcgen05.mma kind::tf32 issued by one thread, accumulators in TMEM, read back with
+// tcgen05.ld for the ReLU, written straight into the next layer's A tile. The 2C and C wide intermediates never
+// leave the SM: 4C bytes in and 4*num_classes bytes out per query instead of three passes over [B,2C,Q] tensors.
+// Precision: TF32 inputs with fp32 accumulation — what cuDNN gives the reference's Conv3d by default
+// (torch.backends.cudnn.allow_tf32 = True); inputs are rounded to nearest TF32 (cvt.rna), not truncated.
+#include "tp_common.cuh"
+
+namespace tp {
+
+constexpr int kMlpThreads = 128;   // 4 warps = the 4 TMEM lane quadrants = 128 rows of a tile
+constexpr int kMlpC = 32;          // input channels (configs/triplane_occ.py: Mlp(input_dim=32))
+constexpr int kMlpH = 64;          // hidden = 2C
+constexpr int kMlpNOut = 16;       // num_classes padded to the next multiple of 16 (UMMA N for M = 128)
+constexpr int kTmemCols = 128;     // D1 [0,64) | D2 [64,96) | D3 [96,112)
+
+// shared-memory map (bytes, every operand tile 1024-byte aligned for the 128-byte swizzle)
+constexpr int kOffA1 = 0;                       // [128 x 32]  16 KB   (layer-1 A, reused as layer-3 A)
+constexpr int kOffA2 = 16384;                   // [128 x 64]  2 K-blocks of 16 KB
+constexpr int kOffW1 = kOffA2 + 32768;          // [64 x 32]   8 KB
+constexpr int kOffW2 = kOffW1 + 8192;           // [32 x 64]   2 K-blocks of 4 KB
+constexpr int kOffW3 = kOffW2 + 8192;           // [16 x 32]   2 KB
+constexpr int kMlpSmem = kOffW3 + 2048 + 1024;  // + slack to align the base to 1024 B
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// byte offset of (row r, 16-byte chunk c16 of the 128-byte row) inside a K-major SWIZZLE_128B tile:
+// 8-row groups of 1024 B, the chunk index XORed with the row inside the group (Swizzle<3,4,3>)
+__device__ __forceinline__ uint32_t swz128(int r, int c16) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c16 ^ (r & 7)) << 4));
+}
+
+// UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): K-major, SWIZZLE_128B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);  // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                  // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset: next 8-row group
+  d |= (uint64_t)1 << 46;                  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                  // layout type SWIZZLE_128B
+  return d;
+}
+// UMMA instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, dense
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem_mlp() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 32 lanes x 16 consecutive columns of TMEM -> 16 registers per thread (thread = lane = row)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+struct MlpParams {
+  const float* feats;  // [B, C, Q]
+  const float* w1;     // [2C, C]
+  const float* w2;     // [C, 2C]
+  const float* w3;     // [ncls, C]
+  float* logits;       // [B, ncls, Q]
+  int64_t Q;
+  int64_t tiles_per_sample, tiles;
+  int ncls;
+};
+
+__global__ void __launch_bounds__(kMlpThreads)
+mlp_head_kernel(const MlpParams P) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t s_mbar;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t mbar = smem_u32(&s_mbar);
+
+  // ---- one-time setup: weights into their swizzled tiles, TMEM, mbarrier ---------------------------------
+  for (int i = tid; i < kMlpH * kMlpC / 4; i += kMlpThreads) {  // W1 [64][32]: row n, chunk k/4
+    const int n = i / (kMlpC / 4), c16 = i % (kMlpC / 4);
+    const float4 w = __ldg(reinterpret_cast<const float4*>(P.w1) + i);
+    *reinterpret_cast<float4*>(smem + kOffW1 + swz128(n, c16)) = make_float4(to_tf32(w.x), to_tf32(w.y), to_tf32(w.z), to_tf32(w.w));
+  }
+  for (int i = tid; i < kMlpC * kMlpH / 4; i += kMlpThreads) {  // W2 [32][64]: two K blocks of [32][32]
+    const int n = i / (kMlpH / 4), c = i % (kMlpH / 4);         // c: 16-byte chunk of the 64-wide row
+    const float4 w = __ldg(reinterpret_cast<const float4*>(P.w2) + i);
+    *reinterpret_cast<float4*>(smem + kOffW2 + (c >> 3) * 4096 + swz128(n, c & 7)) =
+        make_float4(to_tf32(w.x), to_tf32(w.y), to_tf32(w.z), to_tf32(w.w));
+  }
+  for (int i = tid; i < kMlpNOut * kMlpC / 4; i += kMlpThreads) {  // W3 [16][32], rows >= ncls are zero
+    const int n = i / (kMlpC / 4), c16 = i % (kMlpC / 4);
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < P.ncls) w = __ldg(reinterpret_cast<const float4*>(P.w3) + i);
+    *reinterpret_cast<float4*>(smem + kOffW3 + swz128(n, c16)) = make_float4(to_tf32(w.x), to_tf32(w.y), to_tf32(w.z), to_tf32(w.w));
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fence_async_smem_mlp();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's lane quadrant
+  constexpr uint32_t kI1 = umma_idesc_tf32(128, kMlpH), kI2 = umma_idesc_tf32(128, kMlpC), kI3 = umma_idesc_tf32(128, kMlpNOut);
+  uint32_t phase = 0;
+  const int row = tid;  // tile row = TMEM lane = query inside the tile
+
+  for (int64_t tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
+    const int b = (int)(tile / P.tiles_per_sample);
+    const int64_t q0 = (tile - (int64_t)b * P.tiles_per_sample) * 128;
+    const int64_t q = q0 + row;
+    const bool qv = q < P.Q;
+    // ---- A1: 128 queries x 32 channels, coalesced over q for every channel ------------------------------
+    {
+      const float* f = P.feats + (int64_t)b * kMlpC * P.Q + q;
+#pragma unroll
+      for (int c16 = 0; c16 < kMlpC / 4; ++c16) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (qv) {
+          x.x = __ldg(f + (int64_t)(c16 * 4 + 0) * P.Q);
+          x.y = __ldg(f + (int64_t)(c16 * 4 + 1) * P.Q);
+          x.z = __ldg(f + (int64_t)(c16 * 4 + 2) * P.Q);
+          x.w = __ldg(f + (int64_t)(c16 * 4 + 3) * P.Q);
+        }
+        *reinterpret_cast<float4*>(smem + kOffA1 + swz128(row, c16)) = make_float4(to_tf32(x.x), to_tf32(x.y), to_tf32(x.z), to_tf32(x.w));
+      }
+    }
+    fence_async_smem_mlp();
+    tc_fence_before();
+    __syncthreads();
+    // ---- layer 1: D1[128 x 64] = A1[128 x 32] . W1^T -------------------------------------------------------
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < kMlpC / 8; ++k)
+        umma_tf32(tmem + 0, umma_desc(sbase + kOffA1 + k * 32), umma_desc(sbase + kOffW1 + k * 32), kI1, k > 0);
+      umma_commit(mbar);
+    }
+    mbar_wait(mbar, phase);
+    phase ^= 1;
+    tc_fence_after();
+#pragma unroll
+    for (int n0 = 0; n0 < kMlpH; n0 += 16) {  // ReLU, straight into the layer-2 A tile (two K blocks)
+      float v[16];
+      tmem_ld16(t_lane + n0, v);
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const int n = n0 + j;
+        *reinterpret_cast<float4*>(smem + kOffA2 + (n >> 5) * 16384 + swz128(row, (n & 31) >> 2)) =
+            make_float4(to_tf32(fmaxf(v[j], 0.f)), to_tf32(fmaxf(v[j + 1], 0.f)), to_tf32(fmaxf(v[j + 2], 0.f)),
+                        to_tf32(fmaxf(v[j + 3], 0.f)));
+      }
+    }
+    fence_async_smem_mlp();
+    tc_fence_before();
+    __syncthreads();
+    // ---- layer 2: D2[128 x 32] = A2[128 x 64] . W2^T -------------------------------------------------------
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < kMlpH / 8; ++k)
+        umma_tf32(tmem + 64, umma_desc(sbase + kOffA2 + (k >> 2) * 16384 + (k & 3) * 32),
+                  umma_desc(sbase + kOffW2 + (k >> 2) * 4096 + (k & 3) * 32), kI2, k > 0);
+      umma_commit(mbar);
+    }
+    mbar_wait(mbar, phase);
+    phase ^= 1;
+    tc_fence_after();
+#pragma unroll
+    for (int n0 = 0; n0 < kMlpC; n0 += 16) {  // ReLU -> layer-3 A tile (the A1 buffer: layer 1 has consumed it)
+      float v[16];
+      tmem_ld16(t_lane + 64 + n0, v);
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(smem + kOffA1 + swz128(row, (n0 + j) >> 2)) =
+            make_float4(to_tf32(fmaxf(v[j], 0.f)), to_tf32(fmaxf(v[j + 1], 0.f)), to_tf32(fmaxf(v[j + 2], 0.f)),
+                        to_tf32(fmaxf(v[j + 3], 0.f)));
+    }
+    fence_async_smem_mlp();
+    tc_fence_before();
+    __syncthreads();
+    // ---- layer 3: D3[128 x 16] = A3[128 x 32] . W3^T -------------------------------------------------------
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < kMlpC / 8; ++k)
+        umma_tf32(tmem + 96, umma_desc(sbase + kOffA1 + k * 32), umma_desc(sbase + kOffW3 + k * 32), kI3, k > 0);
+      umma_commit(mbar);
+    }
+    mbar_wait(mbar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    {
+      float v[16];
+      tmem_ld16(t_lane + 96, v);
+      if (qv) {
+        float* o = P.logits + (int64_t)b * P.ncls * P.Q + q;
+#pragma unroll
+        for (int c = 0; c < kMlpNOut; ++c)
+          if (c < P.ncls) st_cs_f1(o + (int64_t)c * P.Q, v[c]);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // every warp has read D3 / the A tiles before the next tile overwrites them
+  }
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+  }
+}
+
+}  // namespace tp
+
+using namespace tp;
+
+extern "C" int tp_mlp_head_tf32(const float* feats, int64_t Q, int32_t batch, int32_t C, const float* w1,
+                                const float* w2, const float* w3, int32_t num_classes, float* logits, void* stream) {
+  if (C != kMlpC) return fail(TP_E_SHAPE, "tp_mlp_head_tf32: input_dim=%d (this build: %d, configs/triplane_occ.py)", C, kMlpC);
+  if (num_classes <= 0 || num_classes > kMlpNOut) return fail(TP_E_SHAPE, "tp_mlp_head_tf32: num_classes=%d must be in 1..%d", num_classes, kMlpNOut);
+  if (batch <= 0 || Q < 0) return fail(TP_E_SHAPE, "tp_mlp_head_tf32: bad B=%d Q=%lld", batch, (long long)Q);
+  if (Q == 0) return 0;
+  if (!feats || !w1 || !w2 || !w3 || !logits) return fail(TP_E_NULL, "tp_mlp_head_tf32: null argument");
+  if (((uintptr_t)w1 | (uintptr_t)w2 | (uintptr_t)w3) & 15) return fail(TP_E_SHAPE, "tp_mlp_head_tf32: weights must be 16-byte aligned");
+  MlpParams P;
+  P.feats = feats; P.w1 = w1; P.w2 = w2; P.w3 = w3; P.logits = logits;
+  P.Q = Q; P.ncls = num_classes;
+  P.tiles_per_sample = (Q + 127) / 128;
+  P.tiles = P.tiles_per_sample * batch;
+  static bool opted_in[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !opted_in[dev]) {
+    TP_CUDA(cudaFuncSetAttribute(mlp_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMlpSmem));
+    if (dev >= 0 && dev < 64) opted_in[dev] = true;
+  }
+  const int64_t cap = (int64_t)kSMs * 3;  // 68 KB of shared memory and 128 TMEM columns per CTA: 3 per SM
+  const int grid = (int)(P.tiles < cap ? P.tiles : cap);
+  mlp_head_kernel<<<grid, kMlpThreads, kMlpSmem, (cudaStream_t)stream>>>(P);
+  TP_LAUNCH_CHECK("mlp_head_kernel");
+  return 0;
+}

@@ -487,3 +487,30 @@ def lift_cam_backward(grad_out: torch.Tensor, points: torch.Tensor, offsets: tor
                                              _stream(grad_out)), "tp_lift_cam_backward_f32")
     launch_count += 1 if n else 0
     return channels_last_to_nchw(g).view(B, ncam, Cf, Hf, Wf)
+
+
+# ------------------------------------------------------------------------------------------------
+# occupancy head
+# ------------------------------------------------------------------------------------------------
+def mlp_head(feats: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor, w3: torch.Tensor) -> torch.Tensor:
+    """The reference's Mlp head (dense_heads/mlp.py:57-70) on decode output: feats [B, C, Q] (or [B,C,X,Y,Z]),
+    Conv3d weights w1 [2C,C,1,1,1], w2 [C,2C,1,1,1], w3 [ncls,C,1,1,1] (or already 2-D) -> logits [B, ncls, ...].
+    Three layers fused on the tensor cores (TF32 inputs, fp32 accumulation, like cuDNN's default for Conv3d)."""
+    global launch_count
+    _need_cuda(feats, "feats")
+    shape = feats.shape
+    B, Cc = shape[0], shape[1]
+    f = feats.reshape(B, Cc, -1).contiguous()
+    ws = []
+    for k, w in enumerate((w1, w2, w3)):
+        _need_cuda(w, f"w{k + 1}")
+        ws.append(w.reshape(w.shape[0], w.shape[1]).contiguous())
+    ncls = ws[2].shape[0]
+    if tuple(ws[0].shape) != (2 * Cc, Cc) or tuple(ws[1].shape) != (Cc, 2 * Cc) or ws[2].shape[1] != Cc:
+        raise TriplaneError(f"mlp_head: weights {[tuple(w.shape) for w in ws]} do not form C -> 2C -> C -> ncls with C={Cc}")
+    Q = f.shape[2]
+    out = torch.empty((B, ncls, Q), dtype=torch.float32, device=f.device)
+    L.check(L.lib().tp_mlp_head_tf32(f.data_ptr(), Q, B, Cc, ws[0].data_ptr(), ws[1].data_ptr(), ws[2].data_ptr(), ncls,
+                                     out.data_ptr(), _stream(f)), "tp_mlp_head_tf32")
+    launch_count += 1 if Q else 0
+    return out.view(B, ncls, *shape[2:])

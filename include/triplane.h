@@ -246,6 +246,17 @@ TP_API int tp_lift_cam_backward_f32(const float* points, int32_t point_stride, i
                              const float* grad_out, float* grad_feats_nhwc, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * a6 / 8f#3  occupancy head on the decode output — mmdet3d/models/dense_heads/mlp.py:25-70 (Mlp.forward):
+ *     conv1 (C -> 2C, 1x1x1, no bias) + ReLU, conv2 (2C -> C) + ReLU, conv3 (C -> num_classes), fused for tiles
+ *     of 128 queries on the tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM). TF32 inputs, fp32
+ *     accumulation: the precision cuDNN gives the reference's Conv3d by default.
+ * feats [B, C, Q] (the decode output), w1 [2C, C], w2 [C, 2C], w3 [num_classes, C] (the Conv3d weights with the
+ * 1x1x1 kernel dims dropped), logits [B, num_classes, Q]. C == 32, num_classes <= 16 in this build.
+ * ------------------------------------------------------------------------------------------- */
+TP_API int tp_mlp_head_tf32(const float* feats, int64_t Q, int32_t batch, int32_t C, const float* w1,
+                     const float* w2, const float* w3, int32_t num_classes, float* logits, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Host-buffer entry points (what a non-PyTorch caller binds; bench.py's `e2e` leg).
  * All pointers are HOST memory (pinned recommended). They allocate a per-thread cached device
  * arena, copy in, run the kernels above, copy out and synchronise the internal stream.

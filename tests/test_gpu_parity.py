@@ -567,3 +567,37 @@ def test_host_entry_points_chunked_pipeline(dims):
     ref = ops.sample3(cu(tri), cu(q), lo, vs, [64.0] * 3)
     assert torch.equal(out, ref.cpu())
     lib.tp_host_arena_release()
+
+
+@pytest.mark.parametrize("B,Q,ncls", [(1, 156816, 5), (2, 1000, 5), (1, 77, 16), (1, 128, 1)])
+def test_mlp_head_tensor_core_kernel_vs_torch(B, Q, ncls):
+    """tp_mlp_head_tf32 (tcgen05, TF32 inputs / fp32 accumulate) vs the reference head's three bias-free 1x1x1 convs
+    (dense_heads/mlp.py:57-70) in fp32: within TF32 rounding, and no worse than torch's own TF32 path."""
+    g = torch.Generator().manual_seed(B * 1000 + Q + ncls)
+    C_ = 32
+    x = cu(torch.randn(B, C_, Q, generator=g))
+    w1 = cu(torch.randn(2 * C_, C_, 1, 1, 1, generator=g) / C_ ** 0.5)
+    w2 = cu(torch.randn(C_, 2 * C_, 1, 1, 1, generator=g) / (2 * C_) ** 0.5)
+    w3 = cu(torch.randn(ncls, C_, 1, 1, 1, generator=g) / C_ ** 0.5)
+
+    def chain(xx, prec):
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = prec == "tf32"
+        try:
+            h = torch.relu(torch.einsum("oc,bcq->boq", w1.view(2 * C_, C_).to(xx.dtype), xx))
+            h = torch.relu(torch.einsum("oc,bcq->boq", w2.view(C_, 2 * C_).to(xx.dtype), h))
+            return torch.einsum("oc,bcq->boq", w3.view(ncls, C_).to(xx.dtype), h)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = old
+
+    ref64 = chain(x.double(), "fp64")
+    got = ops.mlp_head(x, w1, w2, w3)
+    assert got.shape == (B, ncls, Q)
+    err = normwise(got, ref64)
+    err_tf32 = normwise(chain(x, "tf32"), ref64)
+    print(f"\n[mlp head B={B} Q={Q} ncls={ncls}] normwise error vs fp64: ours {err:.2e}, torch TF32 {err_tf32:.2e}")
+    assert err <= 3e-3 and err <= max(2 * err_tf32, 1e-3)
+    # 5-D input as the detector passes it (triplane_occ.py:182-186)
+    if Q == 1000:
+        got5 = ops.mlp_head(x.view(B, C_, 10, 10, 10), w1, w2, w3)
+        assert got5.shape == (B, ncls, 10, 10, 10) and torch.equal(got5.reshape(B, ncls, Q), got)

@@ -148,26 +148,33 @@ mlp_head_kernel(const MlpParams P) {
   uint32_t phase = 0;
   const int row = tid;  // tile row = TMEM lane = query inside the tile
 
+  // the 32 channel values of this thread's query for one tile, coalesced over q for every channel
+  auto load_rows = [&](int64_t tile, float* x) {
+    const int b = (int)(tile / P.tiles_per_sample);
+    const int64_t q = (tile - (int64_t)b * P.tiles_per_sample) * 128 + row;
+    if (tile < P.tiles && q < P.Q) {
+      const float* f = P.feats + (int64_t)b * kMlpC * P.Q + q;
+#pragma unroll
+      for (int c = 0; c < kMlpC; ++c) x[c] = __ldg(f + (int64_t)c * P.Q);
+    } else {
+#pragma unroll
+      for (int c = 0; c < kMlpC; ++c) x[c] = 0.f;
+    }
+  };
+  float xn[kMlpC];  // next tile's rows: loaded while this tile's three MMAs run
+  load_rows(blockIdx.x, xn);
+
   for (int64_t tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
     const int b = (int)(tile / P.tiles_per_sample);
     const int64_t q0 = (tile - (int64_t)b * P.tiles_per_sample) * 128;
     const int64_t q = q0 + row;
     const bool qv = q < P.Q;
-    // ---- A1: 128 queries x 32 channels, coalesced over q for every channel ------------------------------
-    {
-      const float* f = P.feats + (int64_t)b * kMlpC * P.Q + q;
+    // ---- A1: 128 queries x 32 channels --------------------------------------------------------------------
 #pragma unroll
-      for (int c16 = 0; c16 < kMlpC / 4; ++c16) {
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (qv) {
-          x.x = __ldg(f + (int64_t)(c16 * 4 + 0) * P.Q);
-          x.y = __ldg(f + (int64_t)(c16 * 4 + 1) * P.Q);
-          x.z = __ldg(f + (int64_t)(c16 * 4 + 2) * P.Q);
-          x.w = __ldg(f + (int64_t)(c16 * 4 + 3) * P.Q);
-        }
-        *reinterpret_cast<float4*>(smem + kOffA1 + swz128(row, c16)) = make_float4(to_tf32(x.x), to_tf32(x.y), to_tf32(x.z), to_tf32(x.w));
-      }
-    }
+    for (int c16 = 0; c16 < kMlpC / 4; ++c16)
+      *reinterpret_cast<float4*>(smem + kOffA1 + swz128(row, c16)) =
+          make_float4(to_tf32(xn[c16 * 4]), to_tf32(xn[c16 * 4 + 1]), to_tf32(xn[c16 * 4 + 2]), to_tf32(xn[c16 * 4 + 3]));
+    load_rows(tile + gridDim.x, xn);  // in flight until the next iteration
     fence_async_smem_mlp();
     tc_fence_before();
     __syncthreads();

@@ -459,6 +459,43 @@ def bench_lift(args, dev, barrier, sampler):
                 bytes=B * n * (12 + 4 * Cf) + B * ncam * Cf * Hf * Wf * 4)
 
 
+def bench_occ_head(args, dev, barrier, sampler):
+    """configs/triplane_occ.py occupancy pipeline on the BASELINE lattice: decode (conversion + gather) followed by the
+    Mlp head (dense_heads/mlp.py: 32 -> 64 -> 32 -> 5, three bias-free 1x1x1 convs) as ONE tensor-core kernel."""
+    from efficient_multimodal_perception_b200 import ops, synth
+    q = synth.occ_gt_lattice().reshape(1, -1, 3).contiguous().to(dev)
+    tri = synth.triplane_stacked(1, C_DEC, PLANE, seed=1002).to(dev)
+    g = torch.Generator().manual_seed(7)
+    w1 = (torch.randn(2 * C_DEC, C_DEC, 1, 1, 1, generator=g) / C_DEC ** 0.5).to(dev)
+    w2 = (torch.randn(C_DEC, 2 * C_DEC, 1, 1, 1, generator=g) / (2 * C_DEC) ** 0.5).to(dev)
+    w3 = (torch.randn(5, C_DEC, 1, 1, 1, generator=g) / C_DEC ** 0.5).to(dev)
+    feats = ops.sample3(tri, q, OCC_LO, OCC_VS, OCC_HALF, grid_dims=QUERY_DIMS["lattice640k"])
+
+    def head():
+        return ops.mlp_head(feats, w1, w2, w3)
+
+    def both():
+        f = ops.sample3(tri, q, OCC_LO, OCC_VS, OCC_HALF, grid_dims=QUERY_DIMS["lattice640k"])
+        return ops.mlp_head(f, w1, w2, w3)
+
+    steps = max(10, min(args.steps, 100))
+    out = {}
+    sampler.active.set()
+    for name, fn in (("head", head), ("decode_plus_head", both)):
+        for _ in range(3):
+            fn()
+
+        def run(fn=fn):
+            for _ in range(steps):
+                fn()
+
+        out[name] = time_region(run, barrier) / steps
+    sampler.active.clear()
+    Q = q.shape[1]
+    return dict(Q=Q, steps=steps, head_ms=out["head"], both_ms=out["decode_plus_head"],
+                head_bytes=Q * (4 * C_DEC + 4 * 5), flops=2 * Q * (C_DEC * 2 * C_DEC * 2 + C_DEC * 5))
+
+
 def bench_encode_point_sharded(args, dev, barrier, rank, world):
     """N > 1 only: ONE 10-sweep sample (350 000 raw points) point-sharded over the ranks:
     partial planes (-inf empties) -> NCCL all-reduce(max) of the 430 MB dense planes -> finalise."""
@@ -559,6 +596,7 @@ def run_b200(args):
     enc = bench_encode_device(args, dev, barrier, sampler)
     encd = bench_encode_dense(args, dev, barrier, sampler)
     lift = bench_lift(args, dev, barrier, sampler)
+    occ = bench_occ_head(args, dev, barrier, sampler)
     eps = bench_encode_point_sharded(args, dev, barrier, rank, world) if world > 1 else None
     # max over ranks (device time)
     t = torch.tensor([dec["ms_total"], enc["ms_per_step"], dec["kernel_ms_avg"], eps["ms_per_step"] if eps else 0.0,
@@ -661,6 +699,19 @@ def run_b200(args):
                          "frac": lift["bytes"] / (lift_k_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": lift["bytes"],
                          "note": "lift kernel alone (events around the loop of launches)"},
             "steps": lift["steps"], "gpu_launches": lift["launches"]}
+        line["occupancy_head"] = {
+            "metric": "Mlp occupancy head queries/s (32 -> 64 -> 32 -> 5 per query, fused on the tensor cores: tcgen05 "
+                      "kind::tf32, TMEM accumulators) and decode + head",
+            "value": world * occ["Q"] / (occ["head_ms"] * 1e-3), "unit": "queries/s", "ms_per_step": occ["head_ms"],
+            "decode_plus_head_ms": occ["both_ms"], "decode_plus_head_queries_per_s": world * occ["Q"] / (occ["both_ms"] * 1e-3),
+            "workload": f"{occ['Q']} queries (640k lattice), C=32, 5 classes; per-rank numbers, no cross-rank max",
+            "roofline": {"bound": "hbm", "achieved": occ["head_bytes"] / (occ["head_ms"] * 1e-3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": occ["head_bytes"] / (occ["head_ms"] * 1e-3) / 1e9 / peak,
+                         "algorithmic_bytes": occ["head_bytes"],
+                         "tensor_tflops": occ["flops"] / (occ["head_ms"] * 1e-3) / 1e12,
+                         "note": "HBM-bound by a wide margin: 8.5 kflop per 148 bytes; the tensor cores are there to keep "
+                                 "the 2C / C wide intermediates on the SM, not for their peak"},
+            "steps": occ["steps"], "gpu_launches": occ["steps"]}
         if eps:
             line["encode_point_sharded"] = {
                 "workload": f"ONE 10-sweep sample ({eps['n']} raw pts) point-sharded over {world} GPUs, geometry "

@@ -94,6 +94,30 @@ class PointTriplaneProjector(nn.Module):
                 self.mlp_xz(xz).permute(0, 3, 1, 2)]
 
 
+class Mlp(nn.Module):
+    """The occupancy head of the reference (mmdet3d/models/dense_heads/mlp.py:10-88): same constructor,
+    parameter names (``conv1.0.weight`` [2C,C,1,1,1], ``conv2.0.weight`` [C,2C,1,1,1], ``conv3.0.weight``
+    [ncls,C,1,1,1]) and ``loss``. Without gradients (evaluation, tools/test.py) the three 1x1x1 convolutions run
+    as ONE tensor-core kernel on the decode output (tp_mlp_head_tf32); with gradients the PyTorch convolutions —
+    the reference's own code — are used, so training is unchanged."""
+
+    def __init__(self, input_dim, num_classes, train_cfg=None, test_cfg=None):
+        super().__init__()
+        self.conv1 = nn.Sequential(nn.Conv3d(input_dim, 2 * input_dim, kernel_size=1, stride=1, bias=False),
+                                   nn.ReLU(inplace=True))
+        self.conv2 = nn.Sequential(nn.Conv3d(2 * input_dim, input_dim, kernel_size=1, bias=False), nn.ReLU(inplace=True))
+        self.conv3 = nn.Sequential(nn.Conv3d(input_dim, num_classes, kernel_size=1, bias=False))
+
+    def forward(self, x):
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if x.is_cuda and not needs_grad and x.shape[1] == 32 and self.conv3[0].out_channels <= 16:
+            return ops.mlp_head(x, self.conv1[0].weight, self.conv2[0].weight, self.conv3[0].weight)
+        return self.conv3(self.conv2(self.conv1(x)))
+
+    def loss(self, pred, target):
+        return {"loss": torch.nn.functional.cross_entropy(pred, target, ignore_index=255)}
+
+
 def _offsets(sizes: Sequence[int], device) -> torch.Tensor:
     off = [0]
     for s in sizes:
@@ -224,4 +248,9 @@ def register_with_mmdet() -> bool:
     except Exception:
         return False
     BACKBONES.register_module(name="PointTriplaneProjector", force=True)(PointTriplaneProjector)
+    try:
+        from mmdet.models import HEADS  # type: ignore
+        HEADS.register_module(name="Mlp", force=True)(Mlp)
+    except Exception:
+        pass
     return True

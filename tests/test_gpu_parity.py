@@ -601,3 +601,20 @@ def test_mlp_head_tensor_core_kernel_vs_torch(B, Q, ncls):
     if Q == 1000:
         got5 = ops.mlp_head(x.view(B, C_, 10, 10, 10), w1, w2, w3)
         assert got5.shape == (B, ncls, 10, 10, 10) and torch.equal(got5.reshape(B, ncls, Q), got)
+
+
+def test_mlp_module_eval_uses_the_fused_kernel_and_trains_with_torch():
+    from efficient_multimodal_perception_b200 import Mlp
+    torch.manual_seed(0)
+    m = Mlp(32, 5).to(DEV)
+    x = torch.randn(2, 32, 9, 9, 16, device=DEV)
+    ref = m.conv3(m.conv2(m.conv1(x))).detach()
+    before = ops.launch_count
+    with torch.no_grad():
+        got = m.eval()(x)
+    assert ops.launch_count == before + 1 and got.shape == ref.shape
+    assert normwise(got, ref) <= 3e-3
+    out = m.train()(x)  # gradients required: PyTorch path, trainable
+    assert ops.launch_count == before + 1
+    out.square().mean().backward()
+    assert m.conv1[0].weight.grad is not None

@@ -75,3 +75,15 @@ def test_synth_shapes():
     lat = synth.occ_gt_lattice().reshape(-1, 3)
     inside = ((lat[:, :2].abs() < 25).all(1)).float().mean()
     assert abs(float(inside) - 0.25) < 0.01  # 3/4 of BASELINE's 640k lattice is outside the planes
+
+
+def test_mlp_head_module_keeps_reference_parameter_names():
+    """dense_heads/mlp.py:25-53: conv1 / conv2 / conv3 are nn.Sequential(Conv3d[, ReLU]) -> keys convN.0.weight."""
+    from efficient_multimodal_perception_b200 import Mlp
+    m = Mlp(32, 5)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {
+        "conv1.0.weight": (64, 32, 1, 1, 1), "conv2.0.weight": (32, 64, 1, 1, 1), "conv3.0.weight": (5, 32, 1, 1, 1)}
+    x = torch.randn(1, 32, 3, 4, 5)
+    assert m(x).shape == (1, 5, 3, 4, 5)  # CPU tensors: the reference's own convolutions
+    loss = m.loss(m(x), torch.randint(0, 5, (1, 3, 4, 5)))
+    assert set(loss) == {"loss"} and loss["loss"].requires_grad

@@ -4,7 +4,7 @@
 // GEMM-shaped piece next to the hot path. Here the three layers run back to back on the 5th-gen
 // tensor cores for a tile of 128 queries: A (activations) and B (weights) in shared memory in the canonical
 // K-major SWIZZLE_128B layout, tcgen05.mma kind::tf32 issued by one thread, accumulators in TMEM, read back with
-// tcgen05.ld for the ReLU, written straight into the next layer's A tile. The 2C and C wide intermediates never
+// tcgen05.ld for the ReLU and written back with tcgen05.st: the next layer's MMA takes its A operand from TMEM. The 2C and C wide intermediates never
 // leave the SM: 4C bytes in and 4*num_classes bytes out per query instead of three passes over [B,2C,Q] tensors.
 // Precision: TF32 inputs with fp32 accumulation — what cuDNN gives the reference's Conv3d by default
 // (torch.backends.cudnn.allow_tf32 = True); inputs are rounded to nearest TF32 (cvt.rna), not truncated.
@@ -18,10 +18,11 @@ constexpr int kMlpH = 64;          // hidden = 2C
 constexpr int kMlpNOut = 16;       // num_classes padded to the next multiple of 16 (UMMA N for M = 128)
 constexpr int kTmemCols = 128;     // D1 [0,64) | D2 [64,96) | D3 [96,112)
 
-// shared-memory map (bytes, every operand tile 1024-byte aligned for the 128-byte swizzle)
-constexpr int kOffA1 = 0;                       // [128 x 32]  16 KB   (layer-1 A, reused as layer-3 A)
-constexpr int kOffA2 = 16384;                   // [128 x 64]  2 K-blocks of 16 KB
-constexpr int kOffW1 = kOffA2 + 32768;          // [64 x 32]   8 KB
+// shared-memory map (bytes, every operand tile 1024-byte aligned for the 128-byte swizzle). Only the layer-1
+// activations and the weights live here: the hidden activations stay in TMEM (below). 35 KB per CTA; the CTA count
+// per SM is set by TMEM, 4 x 128 columns.
+constexpr int kOffA1 = 0;                       // [128 x 32]  layer-1 A, 16 KB
+constexpr int kOffW1 = 16384;                   // [64 x 32]   8 KB
 constexpr int kOffW2 = kOffW1 + 8192;           // [32 x 64]   2 K-blocks of 4 KB
 constexpr int kOffW3 = kOffW2 + 8192;           // [16 x 32]   2 KB
 constexpr int kMlpSmem = kOffW3 + 2048 + 1024;  // + slack to align the base to 1024 B
@@ -55,6 +56,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same, A operand read from TMEM (lane = row, one 32-bit column per K element): an accumulator tile that went
+// through ReLU in place is the next layer's A without a trip through shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
 }
@@ -85,6 +95,41 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 32 columns at once, load and wait in one statement so that no use of the registers can be scheduled before the wait
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,"
+      "%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\ttcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,"
+      "%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31};" ::"r"(r[0]),
+      "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+      "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]),
+      "r"(r[29]), "r"(r[30]), "r"(r[31]), "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// Round to nearest TF32, ties away from zero — what cvt.rna.tf32.f32 returns for every finite input, but two integer
+// instructions instead of the ~8 (NaN test, select, ...) that cvt.rna expands to in SASS: add half a TF32 ulp to the
+// magnitude and clear the 13 low mantissa bits. Inf stays Inf, NaN stays NaN, the largest finite values round to Inf.
+__device__ __forceinline__ uint32_t rna_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+// ReLU + round to nearest TF32 of 32 accumulator columns, in place in TMEM
+__device__ __forceinline__ void relu_tf32_inplace(uint32_t taddr) {
+  uint32_t r[32];
+  tmem_ld32(taddr, r);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) r[i] = rna_tf32(fmaxf(__uint_as_float(r[i]), 0.f));
+  tmem_st32(taddr, r);
+}
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -102,7 +147,7 @@ struct MlpParams {
   int ncls;
 };
 
-__global__ void __launch_bounds__(kMlpThreads)
+__global__ void __launch_bounds__(kMlpThreads, 4)
 mlp_head_kernel(const MlpParams P) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t s_mbar;
@@ -111,6 +156,24 @@ mlp_head_kernel(const MlpParams P) {
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
   const uint32_t mbar = smem_u32(&s_mbar);
+
+  const int row = tid;  // tile row = TMEM lane = query inside the tile
+
+  // the 32 channel values of this thread's query for one tile, coalesced over q for every channel
+  auto load_rows = [&](int64_t tile, float* x) {
+    const int b = (int)(tile / P.tiles_per_sample);
+    const int64_t q = (tile - (int64_t)b * P.tiles_per_sample) * 128 + row;
+    if (tile < P.tiles && q < P.Q) {
+      const float* f = P.feats + (int64_t)b * kMlpC * P.Q + q;
+#pragma unroll
+      for (int c = 0; c < kMlpC; ++c) x[c] = __ldg(f + (int64_t)c * P.Q);
+    } else {
+#pragma unroll
+      for (int c = 0; c < kMlpC; ++c) x[c] = 0.f;
+    }
+  };
+  float xn[kMlpC];  // next tile's rows: loaded while this tile's three MMAs run (the first: during the setup below)
+  load_rows(blockIdx.x, xn);
 
   // ---- one-time setup: weights into their swizzled tiles, TMEM, mbarrier ---------------------------------
   for (int i = tid; i < kMlpH * kMlpC / 4; i += kMlpThreads) {  // W1 [64][32]: row n, chunk k/4
@@ -146,24 +209,6 @@ mlp_head_kernel(const MlpParams P) {
   const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's lane quadrant
   constexpr uint32_t kI1 = umma_idesc_tf32(128, kMlpH), kI2 = umma_idesc_tf32(128, kMlpC), kI3 = umma_idesc_tf32(128, kMlpNOut);
   uint32_t phase = 0;
-  const int row = tid;  // tile row = TMEM lane = query inside the tile
-
-  // the 32 channel values of this thread's query for one tile, coalesced over q for every channel
-  auto load_rows = [&](int64_t tile, float* x) {
-    const int b = (int)(tile / P.tiles_per_sample);
-    const int64_t q = (tile - (int64_t)b * P.tiles_per_sample) * 128 + row;
-    if (tile < P.tiles && q < P.Q) {
-      const float* f = P.feats + (int64_t)b * kMlpC * P.Q + q;
-#pragma unroll
-      for (int c = 0; c < kMlpC; ++c) x[c] = __ldg(f + (int64_t)c * P.Q);
-    } else {
-#pragma unroll
-      for (int c = 0; c < kMlpC; ++c) x[c] = 0.f;
-    }
-  };
-  float xn[kMlpC];  // next tile's rows: loaded while this tile's three MMAs run
-  load_rows(blockIdx.x, xn);
-
   for (int64_t tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
     const int b = (int)(tile / P.tiles_per_sample);
     const int64_t q0 = (tile - (int64_t)b * P.tiles_per_sample) * 128;
@@ -172,8 +217,8 @@ mlp_head_kernel(const MlpParams P) {
     // ---- A1: 128 queries x 32 channels --------------------------------------------------------------------
 #pragma unroll
     for (int c16 = 0; c16 < kMlpC / 4; ++c16)
-      *reinterpret_cast<float4*>(smem + kOffA1 + swz128(row, c16)) =
-          make_float4(to_tf32(xn[c16 * 4]), to_tf32(xn[c16 * 4 + 1]), to_tf32(xn[c16 * 4 + 2]), to_tf32(xn[c16 * 4 + 3]));
+      *reinterpret_cast<uint4*>(smem + kOffA1 + swz128(row, c16)) =
+          make_uint4(rna_tf32(xn[c16 * 4]), rna_tf32(xn[c16 * 4 + 1]), rna_tf32(xn[c16 * 4 + 2]), rna_tf32(xn[c16 * 4 + 3]));
     load_rows(tile + gridDim.x, xn);  // in flight until the next iteration
     fence_async_smem_mlp();
     tc_fence_before();
@@ -189,52 +234,32 @@ mlp_head_kernel(const MlpParams P) {
     mbar_wait(mbar, phase);
     phase ^= 1;
     tc_fence_after();
-#pragma unroll
-    for (int n0 = 0; n0 < kMlpH; n0 += 16) {  // ReLU, straight into the layer-2 A tile (two K blocks)
-      float v[16];
-      tmem_ld16(t_lane + n0, v);
-#pragma unroll
-      for (int j = 0; j < 16; j += 4) {
-        const int n = n0 + j;
-        *reinterpret_cast<float4*>(smem + kOffA2 + (n >> 5) * 16384 + swz128(row, (n & 31) >> 2)) =
-            make_float4(to_tf32(fmaxf(v[j], 0.f)), to_tf32(fmaxf(v[j + 1], 0.f)), to_tf32(fmaxf(v[j + 2], 0.f)),
-                        to_tf32(fmaxf(v[j + 3], 0.f)));
-      }
-    }
-    fence_async_smem_mlp();
+    relu_tf32_inplace(t_lane + 0);  // ReLU in place: D1 becomes the layer-2 A operand, still in TMEM
+    relu_tf32_inplace(t_lane + 32);
+    tmem_wait_st();
     tc_fence_before();
     __syncthreads();
-    // ---- layer 2: D2[128 x 32] = A2[128 x 64] . W2^T -------------------------------------------------------
+    // ---- layer 2: D2[128 x 32] = relu(D1)[128 x 64] . W2^T -------------------------------------------------
     if (tid == 0) {
       tc_fence_after();
 #pragma unroll
       for (int k = 0; k < kMlpH / 8; ++k)
-        umma_tf32(tmem + 64, umma_desc(sbase + kOffA2 + (k >> 2) * 16384 + (k & 3) * 32),
-                  umma_desc(sbase + kOffW2 + (k >> 2) * 4096 + (k & 3) * 32), kI2, k > 0);
+        umma_tf32_ts(tmem + 64, tmem + k * 8, umma_desc(sbase + kOffW2 + (k >> 2) * 4096 + (k & 3) * 32), kI2, k > 0);
       umma_commit(mbar);
     }
     mbar_wait(mbar, phase);
     phase ^= 1;
     tc_fence_after();
-#pragma unroll
-    for (int n0 = 0; n0 < kMlpC; n0 += 16) {  // ReLU -> layer-3 A tile (the A1 buffer: layer 1 has consumed it)
-      float v[16];
-      tmem_ld16(t_lane + 64 + n0, v);
-#pragma unroll
-      for (int j = 0; j < 16; j += 4)
-        *reinterpret_cast<float4*>(smem + kOffA1 + swz128(row, (n0 + j) >> 2)) =
-            make_float4(to_tf32(fmaxf(v[j], 0.f)), to_tf32(fmaxf(v[j + 1], 0.f)), to_tf32(fmaxf(v[j + 2], 0.f)),
-                        to_tf32(fmaxf(v[j + 3], 0.f)));
-    }
-    fence_async_smem_mlp();
+    relu_tf32_inplace(t_lane + 64);
+    tmem_wait_st();
     tc_fence_before();
     __syncthreads();
-    // ---- layer 3: D3[128 x 16] = A3[128 x 32] . W3^T -------------------------------------------------------
+    // ---- layer 3: D3[128 x 16] = relu(D2)[128 x 32] . W3^T -------------------------------------------------
     if (tid == 0) {
       tc_fence_after();
 #pragma unroll
       for (int k = 0; k < kMlpC / 8; ++k)
-        umma_tf32(tmem + 96, umma_desc(sbase + kOffA1 + k * 32), umma_desc(sbase + kOffW3 + k * 32), kI3, k > 0);
+        umma_tf32_ts(tmem + 96, tmem + 64 + k * 8, umma_desc(sbase + kOffW3 + k * 32), kI3, k > 0);
       umma_commit(mbar);
     }
     mbar_wait(mbar, phase);
@@ -283,7 +308,7 @@ extern "C" int tp_mlp_head_tf32(const float* feats, int64_t Q, int32_t batch, in
     TP_CUDA(cudaFuncSetAttribute(mlp_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMlpSmem));
     if (dev >= 0 && dev < 64) opted_in[dev] = true;
   }
-  const int64_t cap = (int64_t)kSMs * 3;  // 68 KB of shared memory and 128 TMEM columns per CTA: 3 per SM
+  const int64_t cap = (int64_t)kSMs * 4;  // 128 of the 512 TMEM columns per CTA: 4 per SM
   const int grid = (int)(P.tiles < cap ? P.tiles : cap);
   mlp_head_kernel<<<grid, kMlpThreads, kMlpSmem, (cudaStream_t)stream>>>(P);
   TP_LAUNCH_CHECK("mlp_head_kernel");

@@ -569,7 +569,8 @@ def test_host_entry_points_chunked_pipeline(dims):
     lib.tp_host_arena_release()
 
 
-@pytest.mark.parametrize("B,Q,ncls", [(1, 156816, 5), (2, 1000, 5), (1, 77, 16), (1, 128, 1)])
+@pytest.mark.parametrize("B,Q,ncls", [(1, 156816, 5), (2, 1000, 5), (1, 77, 16), (1, 128, 1), (3, 1283, 7), (2, 40004, 5),
+                                      (5, 30001, 3)])
 def test_mlp_head_tensor_core_kernel_vs_torch(B, Q, ncls):
     """tp_mlp_head_tf32 (tcgen05, TF32 inputs / fp32 accumulate) vs the reference head's three bias-free 1x1x1 convs
     (dense_heads/mlp.py:57-70) in fp32: within TF32 rounding, and no worse than torch's own TF32 path."""

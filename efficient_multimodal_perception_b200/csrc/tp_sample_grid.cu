@@ -26,6 +26,14 @@ struct GridParams {
   int vec_ok;
 };
 
+#ifdef TP_GRID_TRACE  // tools/micro/grid_trace.cu: per-CTA timeline (not part of the library build)
+__device__ unsigned long long g_grid_cta[4 * 1024];
+__device__ __forceinline__ unsigned long long grid_gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define GRID_G(n) do { if (threadIdx.x == 0 && blockIdx.x < 1024) g_grid_cta[blockIdx.x * 4 + (n)] = grid_gtimer(); } while (0)
+#else
+#define GRID_G(n) do {} while (0)
+#endif
+
 constexpr int kGridThreads = 256;
 // resident CTAs per SM: 4 (64 registers). 3 (85 registers, no spills in the block loop) is a little faster when the
 // planes are warm in L2 (roi 9.9 vs 10.5 us, elev 28.7 vs 30.3) but slower in bench.py's rotation over cold plane
@@ -180,7 +188,9 @@ sample3_grid_kernel(const __grid_constant__ GridParams G) {
   // output phase: lane -> (j, 4 consecutive k)
   const int kg = lane & 3, jj = lane >> 2;
 
+  GRID_G(0);
   for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    if (blk != (int)blockIdx.x) GRID_G(1);
     const BlockPos bp = block_pos<BI>(G, blk);  // recomputed per block: carrying it across the loop spills
     const int b = bp.b, i0 = bp.i0, j0 = bp.j0, k0 = bp.k0;
     const int ni = min(BI, G.h - i0), nj = min(BJ, G.w - j0), nk = min(kBK, G.d - k0);
@@ -320,6 +330,7 @@ sample3_grid_kernel(const __grid_constant__ GridParams G) {
       }
     }
   }
+  GRID_G(2);
 }
 
 template <int ARITH, int C4T, int BI>

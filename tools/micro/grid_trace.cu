@@ -1,0 +1,44 @@
+// Per-CTA timeline (globaltimer at entry / start of the second block / exit) of the lattice decode kernel on the
+// 640k-query occupancy lattice (200 x 200 x 16, C = 32, three 128 x 128 planes).
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -DTP_GRID_TRACE -I efficient_multimodal_perception_b200/csrc \
+//        -I include -o build/micro/grid_trace tools/micro/grid_trace.cu build/csrc/tp_{sample,api,voxelize,encode,lift,backward,mlp}.o
+#include <cstdarg>
+#include <cstdio>
+#include <vector>
+#include <algorithm>
+#include "../../efficient_multimodal_perception_b200/csrc/tp_sample_grid.cu"
+int main() {
+  const int h = 200, w = 200, d = 16, C = 32, S = 128;
+  const int64_t Q = (int64_t)h * w * d;
+  std::vector<float> hq(Q * 3), hp(3 * S * S * C);
+  for (int i = 0; i < h; ++i) for (int j = 0; j < w; ++j) for (int k = 0; k < d; ++k) {
+    float* q = &hq[((int64_t)(i * w + j) * d + k) * 3];
+    q[0] = (i + 0.5f) * 0.5f - 50.f; q[1] = (j + 0.5f) * 0.5f - 50.f; q[2] = (k + 0.5f) * 0.5f - 5.f;
+  }
+  unsigned s = 12345; for (auto& v : hp) { s = s * 1664525u + 1013904223u; v = (s >> 8) * (1.f / 16777216.f) - 0.5f; }
+  float *q, *p, *o;
+  cudaMalloc(&q, Q * 12); cudaMalloc(&p, hp.size() * 4); cudaMalloc(&o, Q * C * 4);
+  cudaMemcpy(q, hq.data(), Q * 12, cudaMemcpyHostToDevice); cudaMemcpy(p, hp.data(), hp.size() * 4, cudaMemcpyHostToDevice);
+  tp_plane pl[3]; for (int k = 0; k < 3; ++k) { pl[k].data = p + (size_t)k * S * S * C; pl[k].batch_stride = 3 * S * S * C; pl[k].H = S; pl[k].W = S; }
+  tp_sample_geom sg = {{-25.f, -25.f, -5.f}, {0.4f, 0.4f, 0.1f}, {64.f, 64.f, 64.f}};  // z plane axis: 80 cells of 0.1 in a 128 grid
+  int dims[3] = {h, w, d};
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int r = 0; r < 5; ++r) {
+    if (r == 4) cudaEventRecord(e0);
+    if (tp_sample3_grid_nhwc_f32(pl, C, q, dims, 1, &sg, 0, o, nullptr)) { printf("%s\n", tp_last_error()); return 1; }
+  }
+  cudaEventRecord(e1);
+  if (cudaDeviceSynchronize() != cudaSuccess) { printf("kernel failed\n"); return 1; }
+  float ms; cudaEventElapsedTime(&ms, e0, e1); printf("last launch (events): %.1f us\n", ms * 1e3);
+  static unsigned long long g[4096];
+  cudaMemcpyFromSymbol(g, tp::g_grid_cta, sizeof(g));
+  const int n = 592;
+  unsigned long long s0 = ~0ull;
+  for (int i = 0; i < n; ++i) s0 = std::min(s0, g[4 * i]);
+  std::vector<unsigned long long> st, e1v, e2v;
+  for (int i = 0; i < n; ++i) { st.push_back(g[4*i] - s0); if (g[4*i+1] >= g[4*i]) e2v.push_back(g[4*i+2] - s0); else e1v.push_back(g[4*i+2] - s0); }
+  auto pr = [](const char* nm, std::vector<unsigned long long>& v) { if (v.empty()) return; std::sort(v.begin(), v.end());
+    printf("%-28s n=%4zu  min %6llu  p10 %6llu  median %6llu  p90 %6llu  max %6llu ns\n", nm, v.size(), v[0], v[v.size()/10], v[v.size()/2], v[v.size()*9/10], v.back()); };
+  pr("CTA start", st); pr("end (CTAs with 1 block)", e1v); pr("end (CTAs with 2 blocks)", e2v);
+  return 0;
+}

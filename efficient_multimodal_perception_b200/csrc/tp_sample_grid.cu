@@ -27,9 +27,9 @@ struct GridParams {
 };
 
 #ifdef TP_GRID_TRACE  // tools/micro/grid_trace.cu: per-CTA timeline (not part of the library build)
-__device__ unsigned long long g_grid_cta[4 * 1024];
+__device__ unsigned long long g_grid_cta[8 * 1024];
 __device__ __forceinline__ unsigned long long grid_gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-#define GRID_G(n) do { if (threadIdx.x == 0 && blockIdx.x < 1024) g_grid_cta[blockIdx.x * 4 + (n)] = grid_gtimer(); } while (0)
+#define GRID_G(n) do { if (threadIdx.x == 0 && blockIdx.x < 1024) g_grid_cta[blockIdx.x * 8 + (n)] = grid_gtimer(); } while (0)
 #else
 #define GRID_G(n) do {} while (0)
 #endif
@@ -114,6 +114,53 @@ __device__ __forceinline__ float4 accum_taps(const Taps& t, float4 w, int mk) {
   return a;
 }
 
+// One 2-D table (NR rounds of 32 entries) for this thread's 4 channels: two entries in flight, i.e. 8 independent
+// 16-byte loads before the first fma. `live` and `zero` are block-uniform: a plane with no in-bounds tap in the whole
+// block costs nothing (its table keeps, or is set to, the +0 the masked accumulation would have produced).
+template <int NR>
+__device__ __forceinline__ void build_table(bool live, bool zero, const float4* __restrict__ pl, int C4, int WC4,
+                                            const float4* s_w, const int2* s_om, float* t, int stride, bool cvalid,
+                                            unsigned long long pol) {
+  if (!live) {
+    if (!zero) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        t[r * 32] = 0.f;
+        t[r * 32 + stride] = 0.f;
+        t[r * 32 + 2 * stride] = 0.f;
+        t[r * 32 + 3 * stride] = 0.f;
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int r = 0; r < NR; r += 2) {
+    float4 wgt[2];
+    int mk[2];
+    Taps tp[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (r + u < NR) {
+        wgt[u] = s_w[(r + u) * 32];
+        const int2 om = s_om[(r + u) * 32];
+        mk[u] = cvalid ? om.y : 0;
+        tp[u] = load_taps(pl, om.x, C4, WC4, mk[u], pol);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (r + u < NR) {
+        const float4 a = accum_taps(tp[u], wgt[u], mk[u]);
+        float* tt = t + (r + u) * 32;
+        tt[0] = a.x;
+        tt[stride] = a.y;
+        tt[2 * stride] = a.z;
+        tt[3 * stride] = a.w;
+      }
+    }
+  }
+}
+
 // lattice block -> coordinates. nblk = nib * njb * nkb blocks per sample, k fastest.
 struct BlockPos {
   int b, i0, j0, k0;
@@ -188,6 +235,11 @@ sample3_grid_kernel(const __grid_constant__ GridParams G) {
   // output phase: lane -> (j, 4 consecutive k)
   const int kg = lane & 3, jj = lane >> 2;
 
+  int zeroed = 0;  // bit p: table p holds zeros from an earlier block / chunk
+  __shared__ int s_vote[2];
+  int nblk_done = 0;
+  if (tid == 0) s_vote[0] = 0;
+  __syncthreads();
   GRID_G(0);
   for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
     if (blk != (int)blockIdx.x) GRID_G(1);
@@ -214,6 +266,7 @@ sample3_grid_kernel(const __grid_constant__ GridParams G) {
       }
     }
     // ---- B: one bilinear footprint per table entry (index pair), from the representative queries -
+    int live = 0;  // bit p: this thread saw an entry of plane p with an in-bounds tap
     for (int e = tid; e < Cfg::E; e += kGridThreads) {
       int pl, a0, a1, e0i, e1i, n0, n1, s0, s1;  // s: query stride of the two lattice indices
       if (e < Cfg::E0) {                      // xy(i,j): x -> W, y -> H of plane 0
@@ -234,9 +287,21 @@ sample3_grid_kernel(const __grid_constant__ GridParams G) {
       }
       s_w[e] = wgt;
       s_om[e] = make_int2(base * C4, mask);
+      if (mask) live |= 1 << pl;
     }
+    if (blk == (int)blockIdx.x) GRID_G(3);
     // every warp is past the previous block's output phase once it arrives here
-    const bool separable = __syncthreads_and(ok);
+    // one barrier for both votes: bit 3 = some query broke the lattice, bits 0-2 = planes with something to gather
+    {
+      const int bits = __reduce_or_sync(0xffffffffu, live | (ok ? 0 : 8));
+      if (lane == 0 && bits) atomicOr(&s_vote[nblk_done & 1], bits);
+      if (tid == 0) s_vote[(nblk_done + 1) & 1] = 0;  // last read before the previous block's table barrier
+    }
+    __syncthreads();
+    const int vote = s_vote[nblk_done & 1];
+    ++nblk_done;
+    const bool separable = !(vote & 8);
+    if (blk == (int)blockIdx.x) GRID_G(4);
 
     // ---- prefetch the next block's queries (DRAM -> L2) behind this block's gathers and stores ---
     const int next = blk + gridDim.x;
@@ -258,6 +323,7 @@ sample3_grid_kernel(const __grid_constant__ GridParams G) {
     if (!separable) {
       // ---- per-query fallback: the flat kernel's tile routine on pairs of (i,j) columns ---------
       grid_fallback<ARITH, C4T, BI>(G, b, i0, j0, k0, smem);
+      zeroed = 0;
       __syncthreads();  // the fallback tiles alias the next block's tables
     } else {
       const float4* const pl0 = reinterpret_cast<const float4*>(P.plane[0] + (int64_t)b * P.bstride[0]) + l8;
@@ -270,44 +336,24 @@ sample3_grid_kernel(const __grid_constant__ GridParams G) {
         // ---- C: the three 2-D tables for 32 channels: 8 lanes x 16 B per bilinear tap -----------
         // two entries per thread in flight: 8 independent 16-byte loads before the first fma
         const bool cvalid = ch * 32 + l8 * 4 < C;
-        constexpr int R = Cfg::E / 32;
-#pragma unroll
-        for (int r = 0; r < R; r += 2) {
-          float4 wgt[2];
-          int mk[2];
-          Taps tp[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            if (r + u < R) {
-              const int e = (r + u) * 32 + ent;
-              wgt[u] = s_w[e];
-              const int2 om = s_om[e];
-              mk[u] = cvalid ? om.y : 0;
-              if ((r + u) * 32 < Cfg::E0) tp[u] = load_taps(pl0 + ch * 8, om.x, C4, WC4_0, mk[u], pol_planes);
-              else if ((r + u) * 32 < Cfg::E0 + Cfg::E1) tp[u] = load_taps(pl1 + ch * 8, om.x, C4, WC4_1, mk[u], pol_planes);
-              else tp[u] = load_taps(pl2 + ch * 8, om.x, C4, WC4_2, mk[u], pol_planes);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            if (r + u < R) {
-              const float4 a = accum_taps(tp[u], wgt[u], mk[u]);
-              float* t;
-              int stride;
-              if ((r + u) * 32 < Cfg::E0) { t = w0 + (r + u) * 32; stride = Cfg::S0; }
-              else if ((r + u) * 32 < Cfg::E0 + Cfg::E1) { t = w1 + ((r + u) * 32 - Cfg::E0); stride = Cfg::S1; }
-              else { t = w2 + ((r + u) * 32 - Cfg::E0 - Cfg::E1); stride = Cfg::S2; }
-              t[0] = a.x;
-              t[stride] = a.y;
-              t[2 * stride] = a.z;
-              t[3 * stride] = a.w;
-            }
-          }
-        }
+        // block-uniform: a plane nothing of which is in range is not touched at all
+        build_table<Cfg::E0 / 32>(vote & 1, zeroed & 1, pl0 + ch * 8, C4, WC4_0, s_w + ent, s_om + ent, w0, Cfg::S0, cvalid, pol_planes);
+        build_table<Cfg::E1 / 32>(vote & 2, zeroed & 2, pl1 + ch * 8, C4, WC4_1, s_w + Cfg::E0 + ent, s_om + Cfg::E0 + ent, w1, Cfg::S1, cvalid, pol_planes);
+        build_table<Cfg::E2 / 32>(vote & 4, zeroed & 4, pl2 + ch * 8, C4, WC4_2, s_w + Cfg::E0 + Cfg::E1 + ent, s_om + Cfg::E0 + Cfg::E1 + ent, w2, Cfg::S2, cvalid, pol_planes);
+        zeroed = ~vote & 7;  // tables that hold zeros now (and keep them while their plane stays out of range)
         __syncthreads();
+        if (blk == (int)blockIdx.x) GRID_G(5);
 
         // ---- D: out[c, i, j, k..k+3] = (xy[c,i,j] + yz[c,j,k..]) + xz[c,i,k..], 16-byte stores ---
         const int cmax = min(32, C - ch * 32);
+        if ((vote & 7) == 0) {  // (0 + 0) + 0: the whole block lies outside all three planes
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int c = warp; c < cmax; c += kGridThreads / 32) {
+            float* o = o_jk + (int64_t)(ch * 32 + c) * P.Q;
+#pragma unroll
+            for (int ii = 0; ii < BI; ++ii, o += wd) st_out_f4(o, z4, pol_out, jk_ok && ii < ni);
+          }
+        } else
         for (int c = warp; c < cmax; c += kGridThreads / 32) {
           const int xk = (kg * 4) ^ swz_bits(c);
           const float4 s1 = *reinterpret_cast<const float4*>(T1 + c * Cfg::S1 + jj * kBK + xk);
@@ -327,6 +373,7 @@ sample3_grid_kernel(const __grid_constant__ GridParams G) {
           }
         }
         if (ch + 1 < nchunk) __syncthreads();
+        if (blk == (int)blockIdx.x) GRID_G(6);
       }
     }
   }

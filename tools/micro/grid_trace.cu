@@ -30,15 +30,31 @@ int main() {
   cudaEventRecord(e1);
   if (cudaDeviceSynchronize() != cudaSuccess) { printf("kernel failed\n"); return 1; }
   float ms; cudaEventElapsedTime(&ms, e0, e1); printf("last launch (events): %.1f us\n", ms * 1e3);
-  static unsigned long long g[4096];
+  static unsigned long long g[8192];
   cudaMemcpyFromSymbol(g, tp::g_grid_cta, sizeof(g));
   const int n = 592;
   unsigned long long s0 = ~0ull;
-  for (int i = 0; i < n; ++i) s0 = std::min(s0, g[4 * i]);
+  for (int i = 0; i < n; ++i) s0 = std::min(s0, g[8 * i]);
   std::vector<unsigned long long> st, e1v, e2v;
-  for (int i = 0; i < n; ++i) { st.push_back(g[4*i] - s0); if (g[4*i+1] >= g[4*i]) e2v.push_back(g[4*i+2] - s0); else e1v.push_back(g[4*i+2] - s0); }
+  for (int i = 0; i < n; ++i) { st.push_back(g[8*i] - s0); if (g[8*i+1] >= g[8*i]) e2v.push_back(g[8*i+2] - s0); else e1v.push_back(g[8*i+2] - s0); }
   auto pr = [](const char* nm, std::vector<unsigned long long>& v) { if (v.empty()) return; std::sort(v.begin(), v.end());
     printf("%-28s n=%4zu  min %6llu  p10 %6llu  median %6llu  p90 %6llu  max %6llu ns\n", nm, v.size(), v[0], v[v.size()/10], v[v.size()/2], v[v.size()*9/10], v.back()); };
+  {  // phases of every CTA's first block, split by whether the table phase gathered anything
+    std::vector<unsigned long long> ab[3], bar[3], c[3], dd[3], tot[3];
+    for (int i = 0; i < n; ++i) {
+      const unsigned long long* t = g + 8 * i;
+      const int ib = i / 25, jb = i % 25;  // BI = 8 on the 200 x 200 x 16 lattice: planes cover lattice indices [50, 150)
+      const bool xin = ib * 8 + 7 >= 50 && ib * 8 < 150, yin = jb * 8 + 7 >= 50 && jb * 8 < 150;
+      const int cls = (xin ? 1 : 0) + (yin ? 1 : 0);
+      ab[cls].push_back(t[3] - t[0]); bar[cls].push_back(t[4] - t[3]); c[cls].push_back(t[5] - t[4]); dd[cls].push_back(t[6] - t[5]);
+      tot[cls].push_back(t[6] - t[0]);
+    }
+    const char* cname[3] = {"no plane in range (store-only)", "one plane in range (xz or yz)", "all three planes in range"};
+    for (int cls = 0; cls < 3; ++cls) {
+      printf("-- first block, %s (BI = 8 only)\n", cname[cls]);
+      pr("  A+B (queries, footprints)", ab[cls]); pr("  barrier", bar[cls]); pr("  C (tables)", c[cls]); pr("  D (stores)", dd[cls]); pr("  whole block", tot[cls]);
+    }
+  }
   pr("CTA start", st); pr("end (CTAs with 1 block)", e1v); pr("end (CTAs with 2 blocks)", e2v);
   return 0;
 }

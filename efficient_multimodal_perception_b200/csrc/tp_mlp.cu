@@ -46,6 +46,23 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                  // layout type SWIZZLE_128B
   return d;
 }
+// MN-major operand (rows of the tile contiguous in memory, cute's make_umma_desc<Major::MN>). For 32-bit types the only
+// MN-major layout is SWIZZLE_128B_BASE32B: 512-byte atoms of 4 K-rows x 128 B (32 MN elements), the 32-byte chunk index
+// XORed with the K-row (Swizzle<2,5,2>); `lbo` bytes between atoms along MN, `sbo` bytes between atoms along K
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B
+  return d;
+}
+// byte offset of (K-row c, 16-byte chunk u of the 128 MN elements = 32 chunks) in a [32 x 128] tile of such atoms laid out
+// with lbo = 512 (4 atoms side by side along MN) and sbo = 2048
+__device__ __forceinline__ uint32_t mn_tile_off(int c, int u) {
+  return (uint32_t)((c >> 2) * 2048 + (u >> 3) * 512 + (c & 3) * 128 + ((((u & 7) >> 1) ^ (c & 3)) << 5) + (u & 1) * 16);
+}
 // UMMA instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, dense
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -197,13 +214,12 @@ mlp_head_kernel(const MlpParams P) {
   const uint32_t mbar1 = smem_u32(&s_mbar[0]), mbar2 = mbar1 + 8, mbar3 = mbar1 + 16;
 
   const int lane = tid & 31;
-  // Tile row (= TMEM lane = thread) <-> query. VEC (Q % 4 == 0, 16-byte aligned feats): a lane loads, for 8 channels,
-  // the float4 of 4 consecutive queries 4g..4g+3 (g = lane & 7; channel 4i + (lane >> 3)) — 8 requests of 4 full
-  // lines per warp instead of 32 of one line — and element j of it goes to row 8j + g of the warp's 32 rows: with that
-  // permutation the 32 lanes of every 4-byte store into the swizzled A1 tile hit 32 different banks. So row r of a warp
-  // holds query 4 (r & 7) + (r >> 3) of the warp's 32; the logits store inverts it (still one full line per warp).
+  // Tile row (= TMEM lane = thread) = query inside the tile. VEC (Q % 4 == 0, 16-byte aligned feats): a lane loads, for 8
+  // channels, the float4 of 4 consecutive queries 4g..4g+3 (g = lane & 7; channel 4i + (lane >> 3)) — 8 requests of 4
+  // full lines per warp instead of 32 of one line — and stores it as one 16-byte chunk of an MN-major A tile (the layout
+  // the features have in memory: queries contiguous per channel), so staging is 8 conflict-free 16-byte stores.
   const int g8 = lane & 7, cl = lane >> 3;
-  const int qrow = VEC ? (warp * 32 + 4 * g8 + cl) : tid;  // query (inside the tile) of this thread's TMEM lane
+  const int qrow = tid;  // query (inside the tile) of this thread's TMEM lane
 
   // (sample, tile inside the sample) of this CTA's tiles, advanced without divisions
   auto advance = [&](int& b, int& t, int by) {
@@ -292,12 +308,13 @@ mlp_head_kernel(const MlpParams P) {
   // barriers and one exposed MMA latency instead of four and three.
   auto stage_a1 = [&]() {  // xn -> swizzled K-major A1 tile, then request the following tile's rows
     if (VEC) {
-      unsigned char* a = smem + kOffA1 + warp * 4096 + g8 * 128 + cl * 4;  // rows 32 warp + 8 j + g8: group 4 warp + j
+      // MN-major A1: this lane's 4 queries are 16-byte chunk 8 warp + g8 of K-row (channel) c
 #pragma unroll
-      for (int i = 0; i < kMlpC / 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint32_t*>(a + j * 1024 + ((i ^ g8) << 4)) = rna_tf32(xn[4 * i + j]);
+      for (int i = 0; i < kMlpC / 4; ++i) {
+        const int c = 4 * i + cl;
+        *reinterpret_cast<uint4*>(smem + kOffA1 + mn_tile_off(c, warp * 8 + g8)) =
+            make_uint4(rna_tf32(xn[4 * i]), rna_tf32(xn[4 * i + 1]), rna_tf32(xn[4 * i + 2]), rna_tf32(xn[4 * i + 3]));
+      }
     } else {
 #pragma unroll
       for (int c16 = 0; c16 < kMlpC / 4; ++c16)
@@ -309,7 +326,8 @@ mlp_head_kernel(const MlpParams P) {
   auto issue_layer1 = [&]() {  // D1[128 x 64] = A1[128 x 32] . W1^T
 #pragma unroll
     for (int k = 0; k < kMlpC / 8; ++k)
-      umma_tf32(tmem + 0, umma_desc(sbase + kOffA1 + k * 32), umma_desc(sbase + kOffW1 + k * 32), kI1, k > 0);
+      umma_tf32(tmem + 0, VEC ? umma_desc_mn(sbase + kOffA1 + k * 4096, 512, 2048) : umma_desc(sbase + kOffA1 + k * 32),
+                umma_desc(sbase + kOffW1 + k * 32), VEC ? (kI1 | (1u << 15)) : kI1, k > 0);
     umma_commit(mbar1);
   };
   uint32_t phase = 0;  // all three mbarriers complete once per tile

@@ -14,168 +14,9 @@
 // same launch, to the per-query tile routine of tp_sample.cu.
 #include <cstdlib>
 
-#include "tp_sample_dev.cuh"
+#include "tp_sample_grid.cuh"
 
 namespace tp {
-
-struct GridParams {
-  SampleParams S;  // S.Q = h*w*d
-  int h, w, d;
-  int nib, njb, nkb;  // blocks along h, w, d
-  int nblocks;        // batch * nib * njb * nkb
-  int vec_ok;
-};
-
-#ifdef TP_GRID_TRACE  // tools/micro/grid_trace.cu: per-CTA timeline (not part of the library build)
-__device__ unsigned long long g_grid_cta[8 * 1024];
-__device__ __forceinline__ unsigned long long grid_gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-#define GRID_G(n) do { if (threadIdx.x == 0 && blockIdx.x < 1024) g_grid_cta[blockIdx.x * 8 + (n)] = grid_gtimer(); } while (0)
-#else
-#define GRID_G(n) do {} while (0)
-#endif
-
-constexpr int kGridThreads = 256;
-// resident CTAs per SM: 4 (64 registers). 3 (85 registers, no spills in the block loop) is a little faster when the
-// planes are warm in L2 (roi 9.9 vs 10.5 us, elev 28.7 vs 30.3) but slower in bench.py's rotation over cold plane
-// sets (640k lattice 24.8 vs 23.8 us): the fourth CTA hides the DRAM latency of first touches.
-#ifndef TP_GRID_CTAS_PER_SM
-#define TP_GRID_CTAS_PER_SM 4
-#endif
-constexpr int kGridCtasPerSm = TP_GRID_CTAS_PER_SM;
-constexpr int kBK = 16;  // lattice block extent along d
-constexpr int kBJ = 8;   // ... along w: a warp-wide 16-byte store covers 8 (j) x 4 (k/4) = 512 contiguous bytes when d == 16
-constexpr int kFallbackWarps = 4;
-
-template <int BI>
-struct GridCfg {
-  static constexpr int E0 = BI * kBJ, E1 = kBJ * kBK, E2 = BI * kBK;  // table entries (xy, yz, xz)
-  static constexpr int E = E0 + E1 + E2;
-  // Table rows are channels. xy rows are read with 4-byte loads: stride == 1 (mod 32) makes the
-  // channel-major writes conflict-free. yz / xz rows are read as 16-byte k-runs: stride == 4 (mod 32)
-  // plus the column swizzle below does the same while keeping every run aligned.
-  static constexpr int S0 = E0 + 1, S1 = E1 + 4, S2 = E2 + 4;
-  static constexpr int kTableWords = 32 * (S0 + S1 + S2);
-  static constexpr int kFallbackWords = kFallbackWarps * (kParamWords + kTileWords);
-  static constexpr int kWords = kTableWords > kFallbackWords ? kTableWords : kFallbackWords;
-  static constexpr int kSmemBytes = kWords * 4 + E * (16 + 8);
-  static_assert(kWords % 4 == 0, "entry records are 16-byte aligned");
-  static_assert(E0 % 32 == 0 && E1 % 32 == 0 && E2 % 32 == 0, "one plane per warp-round of 32 entries");
-  static_assert(BI * kBJ * kBK % kGridThreads == 0, "whole queries per thread");
-};
-
-// column swizzle of the yz / xz tables: XOR bits 2-3 of the column with bits 3-4 of the channel.
-// Keeps every aligned 4-column group (one float4 of 4 consecutive k) intact.
-__device__ __forceinline__ int swz_bits(int c) { return ((c >> 3) & 3) << 2; }
-
-// loads without side effects: not volatile, so the scheduler may batch the taps of several table
-// entries ahead of the fmas that consume them (planes are read-only for the whole launch)
-__device__ __forceinline__ float4 ld_plane_f4(const float4* p, unsigned long long pol) {
-  float4 r;
-  asm("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-      : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-      : "l"(p), "l"(pol));
-  return r;
-}
-// predicated streaming store; no "memory" clobber: nothing in this kernel reads the output, and the
-// clobber would pin every later shared-memory load behind the store
-__device__ __forceinline__ void st_out_f4(float* p, float4 v, unsigned long long pol, bool pred) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %6, 0;\n\t"
-      "@p st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;\n\t}" ::"l"(p),
-      "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol), "r"((int)pred));
-}
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-
-struct Taps {
-  float4 v00, v01, v10, v11;
-};
-// the four taps of one table entry, this lane's 4 channels; out-of-bounds taps are not touched
-__device__ __forceinline__ Taps load_taps(const float4* __restrict__ pl, int off, int C4, int WC4, int mk,
-                                          unsigned long long pol) {
-  const float4* t0 = pl + off;
-  const float4* t1 = t0 + WC4;
-  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  Taps t;
-  t.v00 = (mk & 1) ? ld_plane_f4(t0, pol) : z;
-  t.v01 = (mk & 2) ? ld_plane_f4(t0 + C4, pol) : z;
-  t.v10 = (mk & 4) ? ld_plane_f4(t1, pol) : z;
-  t.v11 = (mk & 8) ? ld_plane_f4(t1 + C4, pol) : z;
-  return t;
-}
-// same accumulation as plane_taps<true>: nw, ne, sw, se in order, out-of-bounds taps skipped
-__device__ __forceinline__ float4 accum_taps(const Taps& t, float4 w, int mk) {
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (mk & 1) a = fma4(t.v00, w.x, a);
-  if (mk & 2) a = fma4(t.v01, w.y, a);
-  if (mk & 4) a = fma4(t.v10, w.z, a);
-  if (mk & 8) a = fma4(t.v11, w.w, a);
-  return a;
-}
-
-// One 2-D table (NR rounds of 32 entries) for this thread's 4 channels: two entries in flight, i.e. 8 independent
-// 16-byte loads before the first fma. `live` and `zero` are block-uniform: a plane with no in-bounds tap in the whole
-// block costs nothing (its table keeps, or is set to, the +0 the masked accumulation would have produced).
-template <int NR>
-__device__ __forceinline__ void build_table(bool live, bool zero, const float4* __restrict__ pl, int C4, int WC4,
-                                            const float4* s_w, const int2* s_om, float* t, int stride, bool cvalid,
-                                            unsigned long long pol) {
-  if (!live) {
-    if (!zero) {
-#pragma unroll
-      for (int r = 0; r < NR; ++r) {
-        t[r * 32] = 0.f;
-        t[r * 32 + stride] = 0.f;
-        t[r * 32 + 2 * stride] = 0.f;
-        t[r * 32 + 3 * stride] = 0.f;
-      }
-    }
-    return;
-  }
-#pragma unroll
-  for (int r = 0; r < NR; r += 2) {
-    float4 wgt[2];
-    int mk[2];
-    Taps tp[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (r + u < NR) {
-        wgt[u] = s_w[(r + u) * 32];
-        const int2 om = s_om[(r + u) * 32];
-        mk[u] = cvalid ? om.y : 0;
-        tp[u] = load_taps(pl, om.x, C4, WC4, mk[u], pol);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (r + u < NR) {
-        const float4 a = accum_taps(tp[u], wgt[u], mk[u]);
-        float* tt = t + (r + u) * 32;
-        tt[0] = a.x;
-        tt[stride] = a.y;
-        tt[2 * stride] = a.z;
-        tt[3 * stride] = a.w;
-      }
-    }
-  }
-}
-
-// lattice block -> coordinates. nblk = nib * njb * nkb blocks per sample, k fastest.
-struct BlockPos {
-  int b, i0, j0, k0;
-};
-template <int BI>
-__device__ __forceinline__ BlockPos block_pos(const GridParams& G, int blk) {
-  BlockPos p;
-  const int kb = blk % G.nkb; blk /= G.nkb;
-  const int jb = blk % G.njb; blk /= G.njb;
-  p.i0 = (blk % G.nib) * BI;
-  p.b = blk / G.nib;
-  p.j0 = jb * kBJ;
-  p.k0 = kb * kBK;
-  return p;
-}
 
 // The per-query path for a block that is not a lattice. Kept out of line: its register needs (the flat kernel's
 // tile routine) must not shape the register allocation of the table path.

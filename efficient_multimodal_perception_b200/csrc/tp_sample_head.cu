@@ -1,0 +1,414 @@
+// Occupancy decode + head in ONE kernel: TriplaneOcc samples the three planes on the voxel lattice
+// (sample_points_triplane, triplane_occ.py:321-348) and feeds the [B,32,X,Y,Z] features straight into the `Mlp`
+// head (triplane_occ.py:182-186, dense_heads/mlp.py:57-70). Run as two kernels that is 128 B/query written and read
+// again; here a lattice block's features go from the decode tables (tp_sample_grid.cuh) into the tensor-core A tile
+// in shared memory and only the num_classes logits leave the SM: 12 + 4*ncls bytes per query.
+//
+// Per CTA (256 threads, 3 per SM): blocks of 4 x 8 x 16 queries. Phases A-C are the lattice decode's (query check,
+// footprints, the three 2-D tables). Then, per lattice row of the block (= one tile of 128 queries):
+//   stage : (xy + yz) + xz for 32 channels, rounded to TF32, 16-byte stores into the MN-major A tile
+//   layer 1..3 : the tcgen05 chain of tp_mlp.cu (A of layers 2 / 3 in TMEM), two warps per TMEM lane quadrant
+//   logits: 4*ncls bytes per query
+// pipelined like tp_mlp.cu: the next row is staged while layer 2 runs, its layer 1 is issued behind layer 3.
+// A block that is not a lattice (checked bit for bit, as in the decode kernel) stages its rows per query instead.
+// The features fed to the head are, bit for bit, what tp_sample3_grid_nhwc_f32 writes; the logits equal
+// tp_mlp_head_tf32 on that tensor.
+#include "tp_sample_grid.cuh"
+#include "tp_umma.cuh"
+
+namespace tp {
+
+constexpr int kHeadBI = 4;
+constexpr int kHeadCtasPerSm = 3;
+constexpr int kHeadTmemCols = 128;  // D1 [0,64) | D2 [64,96) | D3 [96,112)
+using HeadCfg = GridCfg<kHeadBI>;
+
+// shared-memory map (bytes from a 1024-aligned base)
+constexpr int kHOffA = 0;                      // [32 ch x 128 q] MN-major A tile, 16 KB
+constexpr int kHOffW1 = 16384;                 // K-major SWIZZLE_128B weights, as in tp_mlp.cu
+constexpr int kHOffW2 = kHOffW1 + 8192;
+constexpr int kHOffW3 = kHOffW2 + 8192;
+constexpr int kHOffTab = kHOffW3 + 2048;       // decode tables, then the entry records
+constexpr int kHTabBytes = HeadCfg::kTableWords * 4;
+constexpr int kHeadSmem = kHOffTab + kHTabBytes + HeadCfg::E * (16 + 8) + 1024;
+
+struct HeadParams {
+  GridParams G;  // G.S.out unused
+  const float* w1;
+  const float* w2;
+  const float* w3;
+  float* logits;  // [B, ncls, Q]
+  int ncls;
+};
+
+template <int ARITH>
+__global__ void __launch_bounds__(kGridThreads, kHeadCtasPerSm)
+sample3_grid_head_kernel(const __grid_constant__ HeadParams HP) {
+  using Cfg = HeadCfg;
+  constexpr int BI = kHeadBI, BJ = kBJ, C4 = 8, C = 32;
+  constexpr int QPT = BI * BJ * kBK / kGridThreads;
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t s_mbar[3];
+  __shared__ uint32_t s_tmem;
+  __shared__ int s_vote[2];
+  const GridParams& G = HP.G;
+  const SampleParams& P = G.S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // TMEM first (see tp_mlp.cu: the SM holds back the next CTA until this one has given up the allocation permit)
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kHeadTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t mbar1 = smem_u32(&s_mbar[0]), mbar2 = mbar1 + 8, mbar3 = mbar1 + 16;
+  float* const T0 = reinterpret_cast<float*>(smem + kHOffTab);
+  float* const T1 = T0 + 32 * Cfg::S0;
+  float* const T2 = T1 + 32 * Cfg::S1;
+  float4* const s_w = reinterpret_cast<float4*>(smem + kHOffTab + kHTabBytes);
+  int2* const s_om = reinterpret_cast<int2*>(s_w + Cfg::E);
+
+  // ---- one-time setup: weights (TF32, K-major SWIZZLE_128B), mbarriers ---------------------------------------
+  for (int i = tid; i < kMlpH * kMlpC / 4; i += kGridThreads) {  // W1 [64][32]
+    const float4 w = __ldg(reinterpret_cast<const float4*>(HP.w1) + i);
+    *reinterpret_cast<float4*>(smem + kHOffW1 + swz128(i / (kMlpC / 4), i % (kMlpC / 4))) =
+        make_float4(to_tf32(w.x), to_tf32(w.y), to_tf32(w.z), to_tf32(w.w));
+  }
+  for (int i = tid; i < kMlpC * kMlpH / 4; i += kGridThreads) {  // W2 [32][64]: two K blocks of [32][32]
+    const int n = i / (kMlpH / 4), c = i % (kMlpH / 4);
+    const float4 w = __ldg(reinterpret_cast<const float4*>(HP.w2) + i);
+    *reinterpret_cast<float4*>(smem + kHOffW2 + (c >> 3) * 4096 + swz128(n, c & 7)) =
+        make_float4(to_tf32(w.x), to_tf32(w.y), to_tf32(w.z), to_tf32(w.w));
+  }
+  for (int i = tid; i < kMlpNOut * kMlpC / 4; i += kGridThreads) {  // W3 [16][32], rows >= ncls are zero
+    const int n = i / (kMlpC / 4);
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < HP.ncls) w = __ldg(reinterpret_cast<const float4*>(HP.w3) + i);
+    *reinterpret_cast<float4*>(smem + kHOffW3 + swz128(n, i % (kMlpC / 4))) =
+        make_float4(to_tf32(w.x), to_tf32(w.y), to_tf32(w.z), to_tf32(w.w));
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar1), "r"(1) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar2), "r"(1) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar3), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_vote[0] = 0;
+  }
+  fence_async_smem_mlp();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  const uint32_t t_quad = tmem + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's lane quadrant
+  const int half = warp >> 2;                                           // two warps per quadrant split the columns
+  constexpr uint32_t kI1 = umma_idesc_tf32(128, kMlpH) | (1u << 15);   // A MN-major
+  constexpr uint32_t kI2 = umma_idesc_tf32(128, kMlpC), kI3 = umma_idesc_tf32(128, kMlpNOut);
+  uint32_t phase = 0;
+
+  const unsigned long long pol_planes = policy_evict_last();
+  const int wd = G.w * G.d;
+  const int nblocks = G.nblocks;
+  const int l8 = tid & 7, ent = tid >> 3;
+  const int WC4_0 = P.W[0] * C4, WC4_1 = P.W[1] * C4, WC4_2 = P.W[2] * C4;
+  float* const w0 = T0 + (4 * l8) * Cfg::S0 + ent;
+  float* const w1t = T1 + (4 * l8) * Cfg::S1 + (ent ^ swz_bits(4 * l8));
+  float* const w2t = T2 + (4 * l8) * Cfg::S2 + (ent ^ swz_bits(4 * l8));
+  const int ak = tid & (kBK - 1), aj = (tid / kBK) % BJ, ia = tid / (kBK * BJ);
+  const int kg = lane & 3, jj = lane >> 2;  // staging: lane -> (j, 4 consecutive k) = 16-byte chunk `lane` of a channel row
+  // epilogue: TMEM lane m = (warp & 3) * 32 + lane <-> query (j = m >> 4, k = m & 15) of the tile's lattice row
+  const int em = (warp & 3) * 32 + lane, ej = em >> 4, ek = em & 15;
+  int zeroed = 0, nblk_done = 0;
+
+  for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const BlockPos bp = block_pos<BI>(G, blk);
+    const int b = bp.b, i0 = bp.i0, j0 = bp.j0, k0 = bp.k0;
+    const int ni = min(BI, G.h - i0), nj = min(BJ, G.w - j0), nk = min(kBK, G.d - k0);
+    const float* q00 = P.queries + ((int64_t)b * P.Q + ((int64_t)i0 * G.w + j0) * G.d + k0) * 3;
+
+    // ---- A: the block's queries, separability vote (tp_sample_grid.cu) -----------------------------------------
+    bool ok = true;
+    if (aj < nj && ak < nk) {
+      const unsigned yr = __float_as_uint(__ldg(q00 + aj * G.d * 3 + 1));
+      const unsigned zr = __float_as_uint(__ldg(q00 + ak * 3 + 2));
+#pragma unroll
+      for (int t = 0; t < QPT; ++t) {
+        const int ii = ia + t * (kGridThreads / (kBK * BJ));
+        if (ii < ni) {
+          const float* qi = q00 + ii * wd * 3;
+          const float* qp = qi + (aj * G.d + ak) * 3;
+          const unsigned x = __float_as_uint(__ldg(qp)), y = __float_as_uint(__ldg(qp + 1)),
+                         z = __float_as_uint(__ldg(qp + 2));
+          ok &= (x == __float_as_uint(__ldg(qi))) & (y == yr) & (z == zr);
+        }
+      }
+    }
+    // ---- B: one bilinear footprint per table entry ------------------------------------------------------------
+    int live = 0;
+    for (int e = tid; e < Cfg::E; e += kGridThreads) {
+      int pl, a0, a1, e0i, e1i, n0, n1, s0, s1;
+      if (e < Cfg::E0) {
+        pl = 0; a0 = 0; a1 = 1; e0i = e / BJ; e1i = e % BJ; n0 = ni; n1 = nj; s0 = wd; s1 = G.d;
+      } else if (e < Cfg::E0 + Cfg::E1) {
+        const int r = e - Cfg::E0;
+        pl = 1; a0 = 1; a1 = 2; e0i = r / kBK; e1i = r % kBK; n0 = nj; n1 = nk; s0 = G.d; s1 = 1;
+      } else {
+        const int r = e - Cfg::E0 - Cfg::E1;
+        pl = 2; a0 = 0; a1 = 2; e0i = r / kBK; e1i = r % kBK; n0 = ni; n1 = nk; s0 = wd; s1 = 1;
+      }
+      float4 wgt = make_float4(0.f, 0.f, 0.f, 0.f);
+      int base = 0, mask = 0;
+      if (e0i < n0 && e1i < n1) {
+        const float g0 = grid_coord<ARITH>(P, __ldg(q00 + e0i * s0 * 3 + a0), a0);
+        const float g1 = grid_coord<ARITH>(P, __ldg(q00 + e1i * s1 * 3 + a1), a1);
+        plane_setup<ARITH>(g0, g1, P.W[pl], P.H[pl], wgt, base, mask);
+      }
+      s_w[e] = wgt;
+      s_om[e] = make_int2(base * C4, mask);
+      if (mask) live |= 1 << pl;
+    }
+    {
+      const int bits = __reduce_or_sync(0xffffffffu, live | (ok ? 0 : 8));
+      if (lane == 0 && bits) atomicOr(&s_vote[nblk_done & 1], bits);
+      if (tid == 0) s_vote[(nblk_done + 1) & 1] = 0;
+    }
+    __syncthreads();
+    const int vote = s_vote[nblk_done & 1];
+    ++nblk_done;
+    const bool separable = !(vote & 8);
+
+    const int next = blk + gridDim.x;
+    if (next < nblocks) {  // next block's queries: DRAM -> L2 behind this block's work
+      const BlockPos np = block_pos<BI>(G, next);
+      if (np.j0 + aj < G.w && np.k0 + ak < G.d && (ak & 1) == 0) {
+        const float* n00 = P.queries + ((int64_t)np.b * P.Q + ((int64_t)np.i0 * G.w + np.j0) * G.d + np.k0) * 3;
+#pragma unroll
+        for (int t = 0; t < QPT; ++t) {
+          const int ii = ia + t * (kGridThreads / (kBK * BJ));
+          if (np.i0 + ii < G.h) prefetch_l2(n00 + (ii * wd + aj * G.d + ak) * 3);
+        }
+      }
+    }
+
+    const float4* const pl0 = reinterpret_cast<const float4*>(P.plane[0] + (int64_t)b * P.bstride[0]);
+    const float4* const pl1 = reinterpret_cast<const float4*>(P.plane[1] + (int64_t)b * P.bstride[1]);
+    const float4* const pl2 = reinterpret_cast<const float4*>(P.plane[2] + (int64_t)b * P.bstride[2]);
+    float* const lg = HP.logits + (int64_t)b * HP.ncls * P.Q + ((int64_t)i0 * G.w + j0 + ej) * G.d + k0 + ek;
+    const bool e_ok = ej < nj && ek < nk;  // this thread's epilogue query exists
+
+    if (separable && (vote & 7) == 0) {
+      // the whole block lies outside all three planes: features 0, and the bias-free head maps 0 to 0
+      if (warp < 4 && e_ok)
+        for (int ii = 0; ii < ni; ++ii)
+          for (int c = 0; c < HP.ncls; ++c) st_cs_f1(lg + (int64_t)c * P.Q + ii * wd, 0.f);
+      continue;
+    }
+    if (separable) {
+      // ---- C: the three 2-D tables (32 channels = one chunk) ------------------------------------------------
+      build_table<Cfg::E0 / 32>(vote & 1, zeroed & 1, pl0 + l8, C4, WC4_0, s_w + ent, s_om + ent, w0, Cfg::S0, true, pol_planes);
+      build_table<Cfg::E1 / 32>(vote & 2, zeroed & 2, pl1 + l8, C4, WC4_1, s_w + Cfg::E0 + ent, s_om + Cfg::E0 + ent, w1t, Cfg::S1, true, pol_planes);
+      build_table<Cfg::E2 / 32>(vote & 4, zeroed & 4, pl2 + l8, C4, WC4_2, s_w + Cfg::E0 + Cfg::E1 + ent, s_om + Cfg::E0 + Cfg::E1 + ent, w2t, Cfg::S2, true, pol_planes);
+      zeroed = ~vote & 7;
+      __syncthreads();
+    }
+
+    // features of lattice row ii -> A tile (MN-major: channel rows of 128 queries, 16-byte chunk = 4 consecutive k)
+    auto stage = [&](int ii) {
+      if (separable) {
+        const bool jk_ok = (jj < nj) && (kg * 4 < nk);
+#pragma unroll
+        for (int n = 0; n < C / 8; ++n) {
+          const int c = warp + 8 * n;
+          const int xk = (kg * 4) ^ swz_bits(c);
+          const float4 s1 = *reinterpret_cast<const float4*>(T1 + c * Cfg::S1 + jj * kBK + xk);
+          const float s0 = T0[c * Cfg::S0 + ii * BJ + jj];
+          const float4 s2 = *reinterpret_cast<const float4*>(T2 + c * Cfg::S2 + ii * kBK + xk);
+          uint4 r = make_uint4(0u, 0u, 0u, 0u);
+          if (jk_ok) {
+            r.x = rna_tf32(__fadd_rn(__fadd_rn(s0, s1.x), s2.x));  // (xy + yz) + xz  (triplane_occ.py:345)
+            r.y = rna_tf32(__fadd_rn(__fadd_rn(s0, s1.y), s2.y));
+            r.z = rna_tf32(__fadd_rn(__fadd_rn(s0, s1.z), s2.z));
+            r.w = rna_tf32(__fadd_rn(__fadd_rn(s0, s1.w), s2.w));
+          }
+          *reinterpret_cast<uint4*>(smem + kHOffA + mn_tile_off(c, lane)) = r;
+        }
+      } else {
+        // per-query path: thread -> (query m = tid >> 1, 16 channels); the flat kernel's arithmetic
+        const int m = tid >> 1, h16 = tid & 1, mj = m >> 4, mk = m & 15;
+        float4 f[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) f[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (mj < nj && mk < nk) {
+          const float* qp = q00 + ((int64_t)ii * wd + mj * G.d + mk) * 3;
+          const float px = __ldg(qp), py = __ldg(qp + 1), pz = __ldg(qp + 2);
+          const float gx = grid_coord<ARITH>(P, px, 0), gy = grid_coord<ARITH>(P, py, 1), gz = grid_coord<ARITH>(P, pz, 2);
+          float4 wgt[3];
+          int base[3], msk[3];
+          plane_setup<ARITH>(gx, gy, P.W[0], P.H[0], wgt[0], base[0], msk[0]);
+          plane_setup<ARITH>(gy, gz, P.W[1], P.H[1], wgt[1], base[1], msk[1]);
+          plane_setup<ARITH>(gx, gz, P.W[2], P.H[2], wgt[2], base[2], msk[2]);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int c4 = h16 * 4 + g;
+            const float4 a0 = plane_taps<true>(pl0 + c4, base[0] * C4, C4, WC4_0, wgt[0], msk[0], pol_planes);
+            const float4 a1 = plane_taps<true>(pl1 + c4, base[1] * C4, C4, WC4_1, wgt[1], msk[1], pol_planes);
+            const float4 a2 = plane_taps<true>(pl2 + c4, base[2] * C4, C4, WC4_2, wgt[2], msk[2], pol_planes);
+            f[g].x = __fadd_rn(__fadd_rn(a0.x, a1.x), a2.x);
+            f[g].y = __fadd_rn(__fadd_rn(a0.y, a1.y), a2.y);
+            f[g].z = __fadd_rn(__fadd_rn(a0.z, a1.z), a2.z);
+            f[g].w = __fadd_rn(__fadd_rn(a0.w, a1.w), a2.w);
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int c = h16 * 16 + g * 4;
+          unsigned char* a = smem + kHOffA + (m & 3) * 4;
+          *reinterpret_cast<uint32_t*>(a + mn_tile_off(c, m >> 2)) = rna_tf32(f[g].x);
+          *reinterpret_cast<uint32_t*>(a + mn_tile_off(c + 1, m >> 2)) = rna_tf32(f[g].y);
+          *reinterpret_cast<uint32_t*>(a + mn_tile_off(c + 2, m >> 2)) = rna_tf32(f[g].z);
+          *reinterpret_cast<uint32_t*>(a + mn_tile_off(c + 3, m >> 2)) = rna_tf32(f[g].w);
+        }
+      }
+      fence_async_smem_mlp();
+    };
+    auto issue_layer1 = [&]() {  // D1[128 x 64] = A[128 x 32] . W1^T, A MN-major: one 4096-byte pair of K atoms per step
+#pragma unroll
+      for (int k = 0; k < kMlpC / 8; ++k)
+        umma_tf32(tmem + 0, umma_desc_mn(sbase + kHOffA + k * 4096, 512, 2048), umma_desc(sbase + kHOffW1 + k * 32), kI1, k > 0);
+      umma_commit(mbar1);
+    };
+
+    stage(0);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0 && elect_one()) {
+      tc_fence_after();
+      issue_layer1();
+    }
+    for (int ii = 0; ii < ni; ++ii) {
+      const bool has_next = ii + 1 < ni;
+      mbar_wait(mbar1, phase);
+      tc_fence_after();
+      relu_tf32_inplace(t_quad + half * 32);  // D1 -> layer-2 A operand, in place in TMEM
+      tmem_wait_st();
+      tc_fence_before();
+      __syncthreads();
+      if (warp == 0 && elect_one()) {  // layer 2: D2[128 x 32] = relu(D1)[128 x 64] . W2^T
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < kMlpH / 8; ++k)
+          umma_tf32_ts(tmem + 64, tmem + k * 8, umma_desc(sbase + kHOffW2 + (k >> 2) * 4096 + (k & 3) * 32), kI2, k > 0);
+        umma_commit(mbar2);
+      }
+      if (has_next) stage(ii + 1);  // layer 1 of this row has consumed the A tile
+      mbar_wait(mbar2, phase);
+      tc_fence_after();
+      relu_tf32_inplace16(t_quad + 64 + half * 16);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncthreads();  // also publishes the staged A tile
+      if (warp == 0 && elect_one()) {  // layer 3: D3[128 x 16] = relu(D2)[128 x 32] . W3^T, then layer 1 of the next row
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < kMlpC / 8; ++k)
+          umma_tf32_ts(tmem + 96, tmem + 64 + k * 8, umma_desc(sbase + kHOffW3 + k * 32), kI3, k > 0);
+        umma_commit(mbar3);
+        if (has_next) issue_layer1();
+      }
+      mbar_wait(mbar3, phase);
+      phase ^= 1;
+      tc_fence_after();
+      if (warp < 4) {
+        float v[16];
+        tmem_ld16(t_quad + 96, v);
+        if (e_ok) {
+#pragma unroll
+          for (int c = 0; c < kMlpNOut; ++c)
+            if (c < HP.ncls) st_cs_f1(lg + (int64_t)c * P.Q + ii * wd, v[c]);
+        }
+      }
+      tc_fence_before();
+    }
+    if (!separable) zeroed = 0;
+    __syncthreads();  // tables and records are rewritten by the next block
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kHeadTmemCols) : "memory");
+  }
+}
+
+}  // namespace tp
+
+using namespace tp;
+
+extern "C" int tp_sample3_grid_head_tf32(const tp_plane planes[3], const float* queries, const int32_t dims[3],
+                                         int32_t batch, const tp_sample_geom* sg, int32_t arith, const float* w1,
+                                         const float* w2, const float* w3, int32_t num_classes, float* logits,
+                                         void* stream) {
+  constexpr int C = kMlpC;
+  if (!dims) return fail(TP_E_NULL, "tp_sample3_grid_head_tf32: null dims");
+  const int h = dims[0], w = dims[1], d = dims[2];
+  if (h < 0 || w < 0 || d < 0) return fail(TP_E_SHAPE, "tp_sample3_grid_head_tf32: bad dims %d %d %d", h, w, d);
+  if (num_classes <= 0 || num_classes > kMlpNOut) return fail(TP_E_SHAPE, "tp_sample3_grid_head_tf32: num_classes=%d must be in 1..%d", num_classes, kMlpNOut);
+  if (batch <= 0) return fail(TP_E_SHAPE, "tp_sample3_grid_head_tf32: bad B=%d", batch);
+  const int64_t Q = (int64_t)h * w * d;
+  if (Q == 0) return 0;
+  if (d & 3) return fail(TP_E_SHAPE, "tp_sample3_grid_head_tf32: d=%d must be a multiple of 4 (use tp_sample3_nhwc_f32 + tp_mlp_head_tf32)", d);
+  if (Q * 3 >= ((int64_t)1 << 31)) return fail(TP_E_SHAPE, "tp_sample3_grid_head_tf32: too many queries per sample");
+  if (arith != TP_ARITH_TORCH_CUDA && arith != TP_ARITH_TORCH_CPU) return fail(TP_E_ENUM, "tp_sample3_grid_head_tf32: unknown arith %d", arith);
+  if (!planes || !queries || !sg || !w1 || !w2 || !w3 || !logits) return fail(TP_E_NULL, "tp_sample3_grid_head_tf32: null argument");
+  if (((uintptr_t)w1 | (uintptr_t)w2 | (uintptr_t)w3) & 15) return fail(TP_E_SHAPE, "tp_sample3_grid_head_tf32: weights must be 16-byte aligned");
+  HeadParams HP;
+  GridParams& G = HP.G;
+  SampleParams& P = G.S;
+  for (int k = 0; k < 3; ++k) {
+    if (!planes[k].data) return fail(TP_E_NULL, "tp_sample3_grid_head_tf32: plane %d is null", k);
+    if (planes[k].H <= 0 || planes[k].W <= 0 || (int64_t)planes[k].H * planes[k].W * C >= (int64_t)1 << 31 ||
+        planes[k].H >= (1 << 20) || planes[k].W >= (1 << 20))
+      return fail(TP_E_SHAPE, "tp_sample3_grid_head_tf32: plane %d H=%d W=%d unsupported", k, planes[k].H, planes[k].W);
+    if ((uintptr_t)planes[k].data & 15 || (planes[k].batch_stride & 3))
+      return fail(TP_E_SHAPE, "tp_sample3_grid_head_tf32: plane %d not 16-byte aligned", k);
+    P.plane[k] = planes[k].data;
+    P.bstride[k] = planes[k].batch_stride;
+    P.H[k] = planes[k].H;
+    P.W[k] = planes[k].W;
+    P.lo[k] = sg->lo[k];
+    P.vs[k] = sg->vs[k];
+    P.rcp_vs[k] = 1.0f / sg->vs[k];
+    P.half[k] = sg->half[k];
+    P.rcp_half[k] = 1.0f / sg->half[k];
+  }
+  P.queries = queries;
+  P.out = nullptr;
+  P.Q = Q;
+  P.C = C;
+  P.tiles_per_sample = 0;
+  P.tiles = 0;
+  G.h = h; G.w = w; G.d = d;
+  G.vec_ok = 1;
+  G.nkb = (d + kBK - 1) / kBK;
+  G.nib = (h + kHeadBI - 1) / kHeadBI;
+  G.njb = (w + kBJ - 1) / kBJ;
+  const int64_t nb = (int64_t)batch * G.nib * G.njb * G.nkb;
+  if (nb >= ((int64_t)1 << 30)) return fail(TP_E_SHAPE, "tp_sample3_grid_head_tf32: too many queries");
+  G.nblocks = (int)nb;
+  HP.w1 = w1; HP.w2 = w2; HP.w3 = w3; HP.logits = logits; HP.ncls = num_classes;
+  static bool opted_in[64][2] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int64_t cap = (int64_t)kHeadCtasPerSm * kSMs;
+  const unsigned grid = (unsigned)(nb < cap ? nb : cap);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int ai = arith == TP_ARITH_TORCH_CUDA ? 0 : 1;
+  if (dev < 0 || dev >= 64 || !opted_in[dev][ai]) {
+    if (ai == 0) TP_CUDA(cudaFuncSetAttribute(sample3_grid_head_kernel<TP_ARITH_TORCH_CUDA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem));
+    else TP_CUDA(cudaFuncSetAttribute(sample3_grid_head_kernel<TP_ARITH_TORCH_CPU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem));
+    if (dev >= 0 && dev < 64) opted_in[dev][ai] = true;
+  }
+  if (ai == 0) sample3_grid_head_kernel<TP_ARITH_TORCH_CUDA><<<grid, kGridThreads, kHeadSmem, s>>>(HP);
+  else sample3_grid_head_kernel<TP_ARITH_TORCH_CPU><<<grid, kGridThreads, kHeadSmem, s>>>(HP);
+  TP_LAUNCH_CHECK("sample3_grid_head_kernel");
+  return 0;
+}

@@ -492,6 +492,49 @@ def lift_cam_backward(grad_out: torch.Tensor, points: torch.Tensor, offsets: tor
 # ------------------------------------------------------------------------------------------------
 # occupancy head
 # ------------------------------------------------------------------------------------------------
+def sample3_head(planes, queries: torch.Tensor, lo, vs, half, w1: torch.Tensor, w2: torch.Tensor, w3: torch.Tensor, *,
+                 grid_dims: Sequence[int], arith: str = "cuda", channels_last: bool = False) -> torch.Tensor:
+    """TriplaneOcc's decode + occupancy head in one kernel (triplane_occ.py:182-186 after :321-348): the [B,32,Q]
+    feature tensor never exists. planes / queries / grid_dims as in sample3 (C = 32), weights as in mlp_head.
+    Returns logits [B, ncls, Q], equal to mlp_head(sample3(...))."""
+    global launch_count
+    if isinstance(planes, torch.Tensor):
+        if planes.dim() != 5 or planes.shape[1] != 3:
+            raise TriplaneError(f"stacked triplane must be [B,3,C,H,W], got {tuple(planes.shape)}")
+        planes = [planes[:, 0], planes[:, 1], planes[:, 2]]
+    _need_cuda(queries, "queries")
+    queries = queries.contiguous()
+    B, Q, _ = queries.shape
+    h, w, d = (int(v) for v in grid_dims)
+    if h * w * d != Q:
+        raise TriplaneError(f"sample3_head: grid_dims {tuple(grid_dims)} do not multiply to Q={Q}")
+    nhwc = list(planes) if channels_last else planes_to_channels_last(planes)
+    ws = []
+    for k, wt in enumerate((w1, w2, w3)):
+        _need_cuda(wt, f"w{k + 1}")
+        ws.append(wt.reshape(wt.shape[0], wt.shape[1]).contiguous())
+    Cc, ncls = nhwc[0].shape[-1], ws[2].shape[0]
+    if Cc != 32 or tuple(ws[0].shape) != (64, 32) or tuple(ws[1].shape) != (32, 64) or ws[2].shape[1] != 32:
+        raise TriplaneError(f"sample3_head: this build fuses C=32 -> 64 -> 32 -> ncls; got C={Cc}, weights "
+                            f"{[tuple(x.shape) for x in ws]}")
+    arr = (L.tp_plane * 3)()
+    for k, p in enumerate(nhwc):
+        _need_cuda(p, f"plane {k}")
+        if p.shape[0] != B or p.shape[-1] != Cc or not p.is_contiguous():
+            raise TriplaneError(f"plane {k}: expected contiguous [B={B},H,W,C={Cc}], got {tuple(p.shape)}")
+        arr[k].data = p.data_ptr()
+        arr[k].batch_stride = p.stride(0)
+        arr[k].H, arr[k].W = p.shape[1], p.shape[2]
+    sg = L.make_sample_geom(lo, vs, half)
+    dims = (C.c_int32 * 3)(h, w, d)
+    out = torch.empty((B, ncls, Q), dtype=torch.float32, device=queries.device)
+    L.check(L.lib().tp_sample3_grid_head_tf32(C.byref(arr), queries.data_ptr(), C.byref(dims), B, C.byref(sg), _ARITH[arith],
+                                              ws[0].data_ptr(), ws[1].data_ptr(), ws[2].data_ptr(), ncls, out.data_ptr(),
+                                              _stream(queries)), "tp_sample3_grid_head_tf32")
+    launch_count += 1 if Q else 0
+    return out
+
+
 def mlp_head(feats: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor, w3: torch.Tensor) -> torch.Tensor:
     """The reference's Mlp head (dense_heads/mlp.py:57-70) on decode output: feats [B, C, Q] (or [B,C,X,Y,Z]),
     Conv3d weights w1 [2C,C,1,1,1], w2 [C,2C,1,1,1], w3 [ncls,C,1,1,1] (or already 2-D) -> logits [B, ncls, ...].

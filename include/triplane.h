@@ -256,6 +256,16 @@ TP_API int tp_lift_cam_backward_f32(const float* points, int32_t point_stride, i
 TP_API int tp_mlp_head_tf32(const float* feats, int64_t Q, int32_t batch, int32_t C, const float* w1,
                      const float* w2, const float* w3, int32_t num_classes, float* logits, void* stream);
 
+/* 8f#3 (ii)  occupancy decode + head in one kernel: tp_sample3_grid_nhwc_f32 (C = 32) followed by tp_mlp_head_tf32
+ *     without the [B,32,Q] feature tensor in between (TriplaneOcc: sample_points_triplane, triplane_occ.py:321-348,
+ *     then occ_head, triplane_occ.py:182-186). planes_nhwc: three channels-last [B,H,W,32] planes; queries
+ *     [B,h,w,d,3] (d % 4 == 0); logits [B, num_classes, h*w*d]. The features fed to the head are bit for bit the
+ *     decode kernel's, the logits equal tp_mlp_head_tf32 on them. Blocks of the query tensor that are not a
+ *     lattice are evaluated per query inside the same launch. */
+TP_API int tp_sample3_grid_head_tf32(const tp_plane planes_nhwc[3], const float* queries, const int32_t dims[3],
+                              int32_t batch, const tp_sample_geom* sg, int32_t arith, const float* w1,
+                              const float* w2, const float* w3, int32_t num_classes, float* logits, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Host-buffer entry points (what a non-PyTorch caller binds; bench.py's `e2e` leg).
  * All pointers are HOST memory (pinned recommended). They allocate a per-thread cached device

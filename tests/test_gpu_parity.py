@@ -619,3 +619,48 @@ def test_mlp_module_eval_uses_the_fused_kernel_and_trains_with_torch():
     assert ops.launch_count == before + 1
     out.square().mean().backward()
     assert m.conv1[0].weight.grad is not None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,dims,ncls,kind", [
+    (1, (200, 200, 16), 5, "occ640k"),      # BASELINE lattice: 3/4 of it outside the planes
+    (2, (99, 99, 16), 5, "roi"),            # config-exact roi lattice, ragged blocks in h and w
+    (1, (10, 13, 8), 16, "small"),          # d < 16, 16 classes
+    (2, (7, 9, 20), 3, "ragged_d"),         # two k-blocks, the second partial
+    (1, (12, 16, 16), 5, "jitter"),         # not a lattice: every block takes the per-query path
+    (1, (12, 16, 16), 5, "mixed"),          # one corner jittered: lattice and per-query blocks in one launch
+])
+def test_decode_plus_head_fused_equals_two_kernels(B, dims, ncls, kind):
+    """tp_sample3_grid_head_tf32 == tp_mlp_head_tf32(tp_sample3_grid_nhwc_f32(...)) (triplane_occ.py:182-186 after
+    :321-348): same features bit for bit, same TF32 tensor-core chain; and within TF32 rounding of the fp64 head."""
+    from efficient_multimodal_perception_b200 import synth
+    g = torch.Generator().manual_seed(77 + dims[0])
+    h, w, d = dims
+    lo, vs, half = [-25.0, -25.0, -5.0], (0.4, 0.4, 0.1), [64.0] * 3
+    if kind == "occ640k":
+        q = synth.occ_gt_lattice()
+    elif kind == "roi":
+        q = synth.roi_lattice()
+    else:
+        q = synth.lattice(dims, (0.9, 0.7, 0.35), (-4.0, -5.0, -4.5))
+    assert tuple(q.shape[:3]) == dims
+    q = q.unsqueeze(0).repeat(B, 1, 1, 1, 1)
+    if kind == "jitter":
+        q = q + 0.05 * torch.randn(q.shape, generator=g)
+    if kind == "mixed":
+        q[:, :4, :8] += 0.05 * torch.randn(q[:, :4, :8].shape, generator=g)
+    tri = cu(torch.randn(B, 3, 32, 128, 128, generator=g))
+    w1 = cu(torch.randn(64, 32, 1, 1, 1, generator=g) / 32 ** 0.5)
+    w2 = cu(torch.randn(32, 64, 1, 1, 1, generator=g) / 64 ** 0.5)
+    w3 = cu(torch.randn(ncls, 32, 1, 1, 1, generator=g) / 32 ** 0.5)
+    qd = cu(q.reshape(B, -1, 3))
+    feats = ops.sample3(tri, qd, lo, vs, half, grid_dims=dims)
+    two = ops.mlp_head(feats, w1, w2, w3)
+    before = ops.launch_count
+    one = ops.sample3_head(tri, qd, lo, vs, half, w1, w2, w3, grid_dims=dims)
+    assert ops.launch_count == before + 2  # layout conversion + the fused kernel
+    assert one.shape == two.shape == (B, ncls, h * w * d)
+    ref64 = torch.einsum("oc,bcq->boq", w3.view(ncls, 32).double(), torch.relu(torch.einsum(
+        "oc,bcq->boq", w2.view(32, 64).double(), torch.relu(torch.einsum("oc,bcq->boq", w1.view(64, 32).double(), feats.double())))))
+    assert normwise(one, ref64) <= 3e-3
+    assert torch.equal(one, two), f"fused vs two-kernel logits differ: max abs {float((one - two).abs().max())}"

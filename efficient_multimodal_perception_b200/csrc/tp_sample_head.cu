@@ -13,6 +13,8 @@
 // A block that is not a lattice (checked bit for bit, as in the decode kernel) stages its rows per query instead.
 // The features fed to the head are, bit for bit, what tp_sample3_grid_nhwc_f32 writes; the logits equal
 // tp_mlp_head_tf32 on that tensor.
+#include <atomic>
+
 #include "tp_sample_grid.cuh"
 #include "tp_umma.cuh"
 
@@ -32,14 +34,149 @@ constexpr int kHOffTab = kHOffW3 + 2048;       // decode tables, then the entry 
 constexpr int kHTabBytes = HeadCfg::kTableWords * 4;
 constexpr int kHeadSmem = kHOffTab + kHTabBytes + HeadCfg::E * (16 + 8) + 1024;
 
+// Blocks cost between nothing (outside all planes: zero logits) and four tensor-core tile chains, and a CTA only gets
+// about three of them: they are handed out by an atomic ticket counter (first block by CTA index), claimed one block
+// ahead so the next block's queries can be prefetched. The CTA that draws the last ticket of the launch (every CTA
+// draws exactly one ticket past the end) resets the counter; concurrent launches use different counters.
+constexpr int kHeadTicketSlots = 64;
+__device__ unsigned int g_head_ticket[kHeadTicketSlots];
+
+#ifdef TP_HEAD_TRACE  // tools/micro/head_trace.cu: phase timeline of every CTA's first gathering block (not in the library build)
+__device__ unsigned long long g_head_cta[16 * 1024];
+__device__ __forceinline__ unsigned long long head_gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define HEAD_G(n) do { if (threadIdx.x == 0 && blockIdx.x < 1024) g_head_cta[blockIdx.x * 16 + (n)] = head_gtimer(); } while (0)
+#else
+#define HEAD_G(n) do {} while (0)
+#endif
+
 struct HeadParams {
   GridParams G;  // G.S.out unused
+  int slot;
   const float* w1;
   const float* w2;
   const float* w3;
   float* logits;  // [B, ncls, Q]
   int ncls;
 };
+
+// Per-query staging of one lattice row for a block that is not a lattice: thread -> (query m = tid >> 1, 16 channels),
+// the flat kernel's arithmetic (tp_sample_dev.cuh).
+template <int ARITH>
+__device__ __forceinline__ void stage_per_query(const SampleParams& P, const float* qrow, int d, int nj, int nk,
+                                             const float4* pl0, const float4* pl1, const float4* pl2,
+                                             unsigned char* atile) {
+  constexpr int C4 = 8;
+  const int tid = threadIdx.x;
+  const int WC4_0 = P.W[0] * C4, WC4_1 = P.W[1] * C4, WC4_2 = P.W[2] * C4;
+  const unsigned long long pol_planes = policy_evict_last();
+  const int m = tid >> 1, h16 = tid & 1, mj = m >> 4, mk = m & 15;
+  float4 f[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) f[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (mj < nj && mk < nk) {
+    const float* qp = qrow + (mj * d + mk) * 3;
+    const float px = __ldg(qp), py = __ldg(qp + 1), pz = __ldg(qp + 2);
+    const float gx = grid_coord<ARITH>(P, px, 0), gy = grid_coord<ARITH>(P, py, 1), gz = grid_coord<ARITH>(P, pz, 2);
+    float4 wgt[3];
+    int base[3], msk[3];
+    plane_setup<ARITH>(gx, gy, P.W[0], P.H[0], wgt[0], base[0], msk[0]);
+    plane_setup<ARITH>(gy, gz, P.W[1], P.H[1], wgt[1], base[1], msk[1]);
+    plane_setup<ARITH>(gx, gz, P.W[2], P.H[2], wgt[2], base[2], msk[2]);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int c4 = h16 * 4 + g;
+      const float4 a0 = plane_taps<true>(pl0 + c4, base[0] * C4, C4, WC4_0, wgt[0], msk[0], pol_planes);
+      const float4 a1 = plane_taps<true>(pl1 + c4, base[1] * C4, C4, WC4_1, wgt[1], msk[1], pol_planes);
+      const float4 a2 = plane_taps<true>(pl2 + c4, base[2] * C4, C4, WC4_2, wgt[2], msk[2], pol_planes);
+      f[g].x = __fadd_rn(__fadd_rn(a0.x, a1.x), a2.x);
+      f[g].y = __fadd_rn(__fadd_rn(a0.y, a1.y), a2.y);
+      f[g].z = __fadd_rn(__fadd_rn(a0.z, a1.z), a2.z);
+      f[g].w = __fadd_rn(__fadd_rn(a0.w, a1.w), a2.w);
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int c = h16 * 16 + g * 4;
+    unsigned char* a = atile + (m & 3) * 4;
+    *reinterpret_cast<uint32_t*>(a + mn_tile_off(c, m >> 2)) = rna_tf32(f[g].x);
+    *reinterpret_cast<uint32_t*>(a + mn_tile_off(c + 1, m >> 2)) = rna_tf32(f[g].y);
+    *reinterpret_cast<uint32_t*>(a + mn_tile_off(c + 2, m >> 2)) = rna_tf32(f[g].z);
+    *reinterpret_cast<uint32_t*>(a + mn_tile_off(c + 3, m >> 2)) = rna_tf32(f[g].w);
+  }
+}
+
+// Layer 2 and 3 issue (A operand in TMEM), shared by the lattice path and the per-query path
+__device__ __forceinline__ void issue_layer2(uint32_t tmem, uint32_t sbase, uint32_t mbar) {
+  constexpr uint32_t kI2 = umma_idesc_tf32(128, kMlpC);
+#pragma unroll
+  for (int k = 0; k < kMlpH / 8; ++k)
+    umma_tf32_ts(tmem + 64, tmem + k * 8, umma_desc(sbase + kHOffW2 + (k >> 2) * 4096 + (k & 3) * 32), kI2, k > 0);
+  umma_commit(mbar);
+}
+__device__ __forceinline__ void issue_layer3(uint32_t tmem, uint32_t sbase, uint32_t mbar) {
+  constexpr uint32_t kI3 = umma_idesc_tf32(128, kMlpNOut);
+#pragma unroll
+  for (int k = 0; k < kMlpC / 8; ++k)
+    umma_tf32_ts(tmem + 96, tmem + 64 + k * 8, umma_desc(sbase + kHOffW3 + k * 32), kI3, k > 0);
+  umma_commit(mbar);
+}
+__device__ __forceinline__ void issue_layer1(uint32_t tmem, uint32_t sbase, uint32_t mbar) {
+  // D1[128 x 64] = A[128 x 32] . W1^T, A MN-major: one 4096-byte pair of K atoms per step
+  constexpr uint32_t kI1 = umma_idesc_tf32(128, kMlpH) | (1u << 15);
+#pragma unroll
+  for (int k = 0; k < kMlpC / 8; ++k)
+    umma_tf32(tmem + 0, umma_desc_mn(sbase + kHOffA + k * 4096, 512, 2048), umma_desc(sbase + kHOffW1 + k * 32), kI1, k > 0);
+  umma_commit(mbar);
+}
+
+// A block that is not a lattice: every row staged per query, the three layers one after the other (no pipelining:
+// this is the rare path). Out of line so that its registers do not shape the lattice path. Returns the mbarrier phase.
+template <int ARITH>
+__device__ __noinline__ uint32_t fallback_block(const SampleParams& P, const float* q00, int wd, int d, int ni, int nj,
+                                                int nk, const float4* pl0, const float4* pl1, const float4* pl2,
+                                                unsigned char* smem, uint32_t tmem, uint32_t mbar1, uint32_t phase,
+                                                float* lg, int ncls, bool e_ok) {
+  const int warp = threadIdx.x >> 5;
+  const uint32_t sbase = smem_u32(smem), mbar2 = mbar1 + 8, mbar3 = mbar1 + 16;
+  const uint32_t t_quad = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const int half = warp >> 2;
+  for (int ii = 0; ii < ni; ++ii) {
+    stage_per_query<ARITH>(P, q00 + (int64_t)ii * wd * 3, d, nj, nk, pl0, pl1, pl2, smem + kHOffA);
+    fence_async_smem_mlp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0 && elect_one()) { tc_fence_after(); issue_layer1(tmem, sbase, mbar1); }
+    mbar_wait(mbar1, phase);
+    tc_fence_after();
+    relu_tf32_inplace(t_quad + half * 32);
+    tmem_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0 && elect_one()) { tc_fence_after(); issue_layer2(tmem, sbase, mbar2); }
+    mbar_wait(mbar2, phase);
+    tc_fence_after();
+    relu_tf32_inplace16(t_quad + 64 + half * 16);
+    tmem_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0 && elect_one()) { tc_fence_after(); issue_layer3(tmem, sbase, mbar3); }
+    mbar_wait(mbar3, phase);
+    phase ^= 1;
+    tc_fence_after();
+    if (warp < 4) {
+      float v[16];
+      tmem_ld16(t_quad + 96, v);
+      if (e_ok) {
+#pragma unroll
+        for (int c = 0; c < kMlpNOut; ++c)
+          if (c < ncls) st_cs_f1(lg + (int64_t)c * P.Q + ii * wd, v[c]);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  return phase;
+}
 
 template <int ARITH>
 __global__ void __launch_bounds__(kGridThreads, kHeadCtasPerSm)
@@ -51,6 +188,7 @@ sample3_grid_head_kernel(const __grid_constant__ HeadParams HP) {
   __shared__ __align__(8) uint64_t s_mbar[3];
   __shared__ uint32_t s_tmem;
   __shared__ int s_vote[2];
+  __shared__ int s_next;
   const GridParams& G = HP.G;
   const SampleParams& P = G.S;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -102,8 +240,6 @@ sample3_grid_head_kernel(const __grid_constant__ HeadParams HP) {
   const uint32_t tmem = s_tmem;
   const uint32_t t_quad = tmem + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's lane quadrant
   const int half = warp >> 2;                                           // two warps per quadrant split the columns
-  constexpr uint32_t kI1 = umma_idesc_tf32(128, kMlpH) | (1u << 15);   // A MN-major
-  constexpr uint32_t kI2 = umma_idesc_tf32(128, kMlpC), kI3 = umma_idesc_tf32(128, kMlpNOut);
   uint32_t phase = 0;
 
   const unsigned long long pol_planes = policy_evict_last();
@@ -120,7 +256,16 @@ sample3_grid_head_kernel(const __grid_constant__ HeadParams HP) {
   const int em = (warp & 3) * 32 + lane, ej = em >> 4, ek = em & 15;
   int zeroed = 0, nblk_done = 0;
 
-  for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+  unsigned int ticket = 0;
+  int blk = blockIdx.x;
+  bool traced = false;
+  HEAD_G(0);
+  while (blk < nblocks) {
+    if (!traced) HEAD_G(1);
+    if (tid == 0) {  // consumed after the barrier that ends phase B
+      ticket = atomicAdd(&g_head_ticket[HP.slot], 1u);
+      s_next = (int)(gridDim.x + ticket);
+    }
     const BlockPos bp = block_pos<BI>(G, blk);
     const int b = bp.b, i0 = bp.i0, j0 = bp.j0, k0 = bp.k0;
     const int ni = min(BI, G.h - i0), nj = min(BJ, G.w - j0), nk = min(kBK, G.d - k0);
@@ -173,11 +318,12 @@ sample3_grid_head_kernel(const __grid_constant__ HeadParams HP) {
       if (tid == 0) s_vote[(nblk_done + 1) & 1] = 0;
     }
     __syncthreads();
+    if (!traced) HEAD_G(2);
     const int vote = s_vote[nblk_done & 1];
     ++nblk_done;
     const bool separable = !(vote & 8);
 
-    const int next = blk + gridDim.x;
+    const int next = s_next;
     if (next < nblocks) {  // next block's queries: DRAM -> L2 behind this block's work
       const BlockPos np = block_pos<BI>(G, next);
       if (np.j0 + aj < G.w && np.k0 + ak < G.d && (ak & 1) == 0) {
@@ -201,9 +347,17 @@ sample3_grid_head_kernel(const __grid_constant__ HeadParams HP) {
       if (warp < 4 && e_ok)
         for (int ii = 0; ii < ni; ++ii)
           for (int c = 0; c < HP.ncls; ++c) st_cs_f1(lg + (int64_t)c * P.Q + ii * wd, 0.f);
+      __syncthreads();  // s_next is rewritten at the top of the next block
+      blk = next;
       continue;
     }
-    if (separable) {
+    if (!separable) {
+      phase = fallback_block<ARITH>(P, q00, wd, G.d, ni, nj, nk, pl0, pl1, pl2, smem, tmem, mbar1, phase, lg, HP.ncls, e_ok);
+      zeroed = 0;  // (the tables themselves are untouched, but keep the invariant simple)
+      blk = next;
+      continue;
+    }
+    {
       // ---- C: the three 2-D tables (32 channels = one chunk) ------------------------------------------------
       build_table<Cfg::E0 / 32>(vote & 1, zeroed & 1, pl0 + l8, C4, WC4_0, s_w + ent, s_om + ent, w0, Cfg::S0, true, pol_planes);
       build_table<Cfg::E1 / 32>(vote & 2, zeroed & 2, pl1 + l8, C4, WC4_1, s_w + Cfg::E0 + ent, s_om + Cfg::E0 + ent, w1t, Cfg::S1, true, pol_planes);
@@ -211,10 +365,36 @@ sample3_grid_head_kernel(const __grid_constant__ HeadParams HP) {
       zeroed = ~vote & 7;
       __syncthreads();
     }
+    if (!traced) HEAD_G(3);
 
+    // A block with one live plane has far fewer distinct queries than lattice points: with only yz in range the features
+    // do not depend on i (one tile serves all rows of the block), with only xz they do not depend on j (the block's
+    // BI x 16 (i, k) pairs fit one tile: tile row = i * 16 + k). Same features bit for bit, 4x fewer tile chains: on the
+    // 640k occupancy lattice half of the blocks are of these two kinds.
+    const bool only_yz = (vote & 7) == 2, only_xz = (vote & 7) == 4;
+    const int ntiles = (only_yz || only_xz) ? 1 : ni;
     // features of lattice row ii -> A tile (MN-major: channel rows of 128 queries, 16-byte chunk = 4 consecutive k)
     auto stage = [&](int ii) {
-      if (separable) {
+      if (only_xz) {
+        // lane >> 2 plays i here: chunk `lane` of a channel row = tile rows (lane >> 2) * 16 + 4 kg .. + 3
+        const bool ik_ok = (jj < ni) && (kg * 4 < nk);
+#pragma unroll
+        for (int n = 0; n < C / 8; ++n) {
+          const int c = warp + 8 * n;
+          const int xk = (kg * 4) ^ swz_bits(c);
+          uint4 r = make_uint4(0u, 0u, 0u, 0u);
+          if (jj < BI) {
+            const float4 s2 = *reinterpret_cast<const float4*>(T2 + c * Cfg::S2 + jj * kBK + xk);
+            if (ik_ok) {  // (0 + 0) + xz, as the general path computes it
+              r.x = rna_tf32(__fadd_rn(0.f, s2.x));
+              r.y = rna_tf32(__fadd_rn(0.f, s2.y));
+              r.z = rna_tf32(__fadd_rn(0.f, s2.z));
+              r.w = rna_tf32(__fadd_rn(0.f, s2.w));
+            }
+          }
+          *reinterpret_cast<uint4*>(smem + kHOffA + mn_tile_off(c, lane)) = r;
+        }
+      } else {
         const bool jk_ok = (jj < nj) && (kg * 4 < nk);
 #pragma unroll
         for (int n = 0; n < C / 8; ++n) {
@@ -232,73 +412,29 @@ sample3_grid_head_kernel(const __grid_constant__ HeadParams HP) {
           }
           *reinterpret_cast<uint4*>(smem + kHOffA + mn_tile_off(c, lane)) = r;
         }
-      } else {
-        // per-query path: thread -> (query m = tid >> 1, 16 channels); the flat kernel's arithmetic
-        const int m = tid >> 1, h16 = tid & 1, mj = m >> 4, mk = m & 15;
-        float4 f[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) f[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (mj < nj && mk < nk) {
-          const float* qp = q00 + ((int64_t)ii * wd + mj * G.d + mk) * 3;
-          const float px = __ldg(qp), py = __ldg(qp + 1), pz = __ldg(qp + 2);
-          const float gx = grid_coord<ARITH>(P, px, 0), gy = grid_coord<ARITH>(P, py, 1), gz = grid_coord<ARITH>(P, pz, 2);
-          float4 wgt[3];
-          int base[3], msk[3];
-          plane_setup<ARITH>(gx, gy, P.W[0], P.H[0], wgt[0], base[0], msk[0]);
-          plane_setup<ARITH>(gy, gz, P.W[1], P.H[1], wgt[1], base[1], msk[1]);
-          plane_setup<ARITH>(gx, gz, P.W[2], P.H[2], wgt[2], base[2], msk[2]);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int c4 = h16 * 4 + g;
-            const float4 a0 = plane_taps<true>(pl0 + c4, base[0] * C4, C4, WC4_0, wgt[0], msk[0], pol_planes);
-            const float4 a1 = plane_taps<true>(pl1 + c4, base[1] * C4, C4, WC4_1, wgt[1], msk[1], pol_planes);
-            const float4 a2 = plane_taps<true>(pl2 + c4, base[2] * C4, C4, WC4_2, wgt[2], msk[2], pol_planes);
-            f[g].x = __fadd_rn(__fadd_rn(a0.x, a1.x), a2.x);
-            f[g].y = __fadd_rn(__fadd_rn(a0.y, a1.y), a2.y);
-            f[g].z = __fadd_rn(__fadd_rn(a0.z, a1.z), a2.z);
-            f[g].w = __fadd_rn(__fadd_rn(a0.w, a1.w), a2.w);
-          }
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int c = h16 * 16 + g * 4;
-          unsigned char* a = smem + kHOffA + (m & 3) * 4;
-          *reinterpret_cast<uint32_t*>(a + mn_tile_off(c, m >> 2)) = rna_tf32(f[g].x);
-          *reinterpret_cast<uint32_t*>(a + mn_tile_off(c + 1, m >> 2)) = rna_tf32(f[g].y);
-          *reinterpret_cast<uint32_t*>(a + mn_tile_off(c + 2, m >> 2)) = rna_tf32(f[g].z);
-          *reinterpret_cast<uint32_t*>(a + mn_tile_off(c + 3, m >> 2)) = rna_tf32(f[g].w);
-        }
       }
       fence_async_smem_mlp();
     };
-    auto issue_layer1 = [&]() {  // D1[128 x 64] = A[128 x 32] . W1^T, A MN-major: one 4096-byte pair of K atoms per step
-#pragma unroll
-      for (int k = 0; k < kMlpC / 8; ++k)
-        umma_tf32(tmem + 0, umma_desc_mn(sbase + kHOffA + k * 4096, 512, 2048), umma_desc(sbase + kHOffW1 + k * 32), kI1, k > 0);
-      umma_commit(mbar1);
-    };
-
     stage(0);
     tc_fence_before();
     __syncthreads();
+    if (!traced) HEAD_G(4);
     if (warp == 0 && elect_one()) {
       tc_fence_after();
-      issue_layer1();
+      issue_layer1(tmem, sbase, mbar1);
     }
-    for (int ii = 0; ii < ni; ++ii) {
-      const bool has_next = ii + 1 < ni;
+    for (int ii = 0; ii < ntiles; ++ii) {
+      const bool has_next = ii + 1 < ntiles;
       mbar_wait(mbar1, phase);
       tc_fence_after();
-      relu_tf32_inplace(t_quad + half * 32);  // D1 -> layer-2 A operand, in place in TMEM
+      relu_tf32_inplace16(t_quad + half * 32);  // D1 -> layer-2 A operand, in place in TMEM (16 columns at a time:
+      relu_tf32_inplace16(t_quad + half * 32 + 16);  //  80 registers per thread at 3 CTAs per SM)
       tmem_wait_st();
       tc_fence_before();
       __syncthreads();
       if (warp == 0 && elect_one()) {  // layer 2: D2[128 x 32] = relu(D1)[128 x 64] . W2^T
         tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < kMlpH / 8; ++k)
-          umma_tf32_ts(tmem + 64, tmem + k * 8, umma_desc(sbase + kHOffW2 + (k >> 2) * 4096 + (k & 3) * 32), kI2, k > 0);
-        umma_commit(mbar2);
+        issue_layer2(tmem, sbase, mbar2);
       }
       if (has_next) stage(ii + 1);  // layer 1 of this row has consumed the A tile
       mbar_wait(mbar2, phase);
@@ -309,11 +445,8 @@ sample3_grid_head_kernel(const __grid_constant__ HeadParams HP) {
       __syncthreads();  // also publishes the staged A tile
       if (warp == 0 && elect_one()) {  // layer 3: D3[128 x 16] = relu(D2)[128 x 32] . W3^T, then layer 1 of the next row
         tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < kMlpC / 8; ++k)
-          umma_tf32_ts(tmem + 96, tmem + 64 + k * 8, umma_desc(sbase + kHOffW3 + k * 32), kI3, k > 0);
-        umma_commit(mbar3);
-        if (has_next) issue_layer1();
+        issue_layer3(tmem, sbase, mbar3);
+        if (has_next) issue_layer1(tmem, sbase, mbar1);
       }
       mbar_wait(mbar3, phase);
       phase ^= 1;
@@ -321,17 +454,35 @@ sample3_grid_head_kernel(const __grid_constant__ HeadParams HP) {
       if (warp < 4) {
         float v[16];
         tmem_ld16(t_quad + 96, v);
-        if (e_ok) {
+        if (only_yz) {  // the same logits for every lattice row of the block
+          if (e_ok)
+            for (int r = 0; r < ni; ++r)
+#pragma unroll
+              for (int c = 0; c < kMlpNOut; ++c)
+                if (c < HP.ncls) st_cs_f1(lg + (int64_t)c * P.Q + r * wd, v[c]);
+        } else if (only_xz) {  // tile row em = i * 16 + k: the same logits for every j of the block
+          if (ej < ni && ek < nk) {
+            float* lx = HP.logits + (int64_t)b * HP.ncls * P.Q + ((int64_t)(i0 + ej) * G.w + j0) * G.d + k0 + ek;
+            for (int r = 0; r < nj; ++r)
+#pragma unroll
+              for (int c = 0; c < kMlpNOut; ++c)
+                if (c < HP.ncls) st_cs_f1(lx + (int64_t)c * P.Q + r * G.d, v[c]);
+          }
+        } else if (e_ok) {
 #pragma unroll
           for (int c = 0; c < kMlpNOut; ++c)
             if (c < HP.ncls) st_cs_f1(lg + (int64_t)c * P.Q + ii * wd, v[c]);
         }
       }
       tc_fence_before();
+      if (!traced && ntiles == BI) HEAD_G(5 + ii);
     }
-    if (!separable) zeroed = 0;
+    if (!traced && ntiles == BI) { HEAD_G(9); traced = true; }
     __syncthreads();  // tables and records are rewritten by the next block
+    blk = next;
   }
+  if (tid == 0 && ticket == (unsigned)(nblocks - 1)) g_head_ticket[HP.slot] = 0u;  // nobody draws after the last ticket
+  HEAD_G(10);
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
@@ -394,6 +545,8 @@ extern "C" int tp_sample3_grid_head_tf32(const tp_plane planes[3], const float* 
   const int64_t nb = (int64_t)batch * G.nib * G.njb * G.nkb;
   if (nb >= ((int64_t)1 << 30)) return fail(TP_E_SHAPE, "tp_sample3_grid_head_tf32: too many queries");
   G.nblocks = (int)nb;
+  static std::atomic<unsigned> launch_seq{0};
+  HP.slot = (int)(launch_seq.fetch_add(1, std::memory_order_relaxed) % kHeadTicketSlots);
   HP.w1 = w1; HP.w2 = w2; HP.w3 = w3; HP.logits = logits; HP.ncls = num_classes;
   static bool opted_in[64][2] = {};
   int dev = 0;

@@ -8,9 +8,9 @@ method names. There is no CPU or PyTorch fallback: a missing library raises Trip
 from ._lib import LIB_PATH, TriplaneError, lib
 from . import ops, synth
 from .modules import (Mlp, PointTriplaneProjector, TriplaneHotPathMixin, point_to_cam, register_with_mmdet, roi,
-                      sample_points_triplane, voxelize_points)
+                      sample_and_decode, sample_points_triplane, voxelize_points)
 
 __all__ = ["LIB_PATH", "TriplaneError", "lib", "ops", "synth", "Mlp", "PointTriplaneProjector",
-           "TriplaneHotPathMixin", "point_to_cam", "register_with_mmdet", "roi", "sample_points_triplane", "voxelize_points"]
+           "TriplaneHotPathMixin", "point_to_cam", "register_with_mmdet", "roi", "sample_and_decode", "sample_points_triplane", "voxelize_points"]
 
 register_with_mmdet()

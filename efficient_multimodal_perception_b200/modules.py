@@ -189,6 +189,25 @@ def sample_points_triplane(triplane: Union[torch.Tensor, Sequence[torch.Tensor]]
     return out.view(B, -1, *points.shape[1:-1])
 
 
+def sample_and_decode(triplane: torch.Tensor, points: torch.Tensor, lo, vs, head: "Mlp", arith: str = "cuda") -> torch.Tensor:
+    """TriplaneOcc's `pred = self.decoder(self.sample_points_triplane(triplane, ref_3d))` (triplane_occ.py:182-186):
+    stacked triplane [B,3,32,H,W], points [B,h,w,d,3], head = the Mlp occupancy head -> logits [B,ncls,h,w,d].
+    Evaluation (no gradients) runs ONE kernel from planes and queries to logits (tp_sample3_grid_head_tf32): the
+    [B,32,h,w,d] feature tensor is never written. Anything else (training, other shapes) takes the two calls."""
+    needs_grad = torch.is_grad_enabled() and (triplane.requires_grad or points.requires_grad or
+                                              any(p.requires_grad for p in head.parameters()))
+    fusable = (isinstance(triplane, torch.Tensor) and triplane.is_cuda and triplane.dim() == 5 and triplane.shape[2] == 32
+               and points.dim() == 5 and points.shape[3] % 4 == 0 and head.conv1[0].in_channels == 32
+               and head.conv3[0].out_channels <= 16 and not needs_grad)
+    if not fusable:
+        return head(sample_points_triplane(triplane, points, lo, vs, None, arith))
+    B = points.shape[0]
+    half = [triplane.shape[-1] / 2] * 3
+    out = ops.sample3_head(triplane, points.reshape(B, -1, 3), lo, vs, half, head.conv1[0].weight, head.conv2[0].weight,
+                           head.conv3[0].weight, grid_dims=tuple(points.shape[1:4]), arith=arith)
+    return out.view(B, -1, *points.shape[1:-1])
+
+
 def roi(occ_range, voxel_size):
     """triplane_occ.py:291-318 — bounds into the 200x200x16 GT and the voxel-centre query lattice
     (host-side constants; built once)."""
@@ -235,6 +254,11 @@ class TriplaneHotPathMixin:
         if not isinstance(triplane, torch.Tensor):
             grid_size = self.point_triplane_projector.grid_size
         return sample_points_triplane(triplane, points, lo, vs, grid_size, self.tp_arith)
+
+    def sample_and_decode(self, triplane, points):
+        """`self.decoder(self.sample_points_triplane(triplane, points))` in one kernel when no gradients are needed."""
+        lo, vs = self._tp_geometry()
+        return sample_and_decode(triplane, points, lo, vs, self.decoder, self.tp_arith)
 
     def roi(self):
         return roi(self.occ_range, self.voxel_size)

@@ -87,6 +87,18 @@ def test_new_entry_points_validate_arguments_without_a_device():
     assert rc == -1
     rc = lib.tp_sample3_backward_nhwc_f32(C.byref(planes), 32, 16, 10, 1, C.byref(sg), 9, 16, None)
     assert rc == -3
+    # decode + head: class count, lattice depth, null planes, arithmetic mode
+    rc = lib.tp_sample3_grid_head_tf32(C.byref(planes), 16, C.byref(dims), 1, C.byref(sg), 0, 16, 16, 16, 17, 16, None)
+    assert rc == -2 and b"num_classes" in lib.tp_last_error()
+    odd = (C.c_int32 * 3)(4, 4, 6)
+    rc = lib.tp_sample3_grid_head_tf32(C.byref(planes), 16, C.byref(odd), 1, C.byref(sg), 0, 16, 16, 16, 5, 16, None)
+    assert rc == -2 and b"multiple of 4" in lib.tp_last_error()
+    rc = lib.tp_sample3_grid_head_tf32(C.byref(planes), 16, C.byref(dims), 1, C.byref(sg), 0, 16, 16, 16, 5, 16, None)
+    assert rc == -1 and b"plane 0 is null" in lib.tp_last_error()
+    rc = lib.tp_sample3_grid_head_tf32(C.byref(planes), 16, C.byref(dims), 1, C.byref(sg), 7, 16, 16, 16, 5, 16, None)
+    assert rc == -3
+    empty = (C.c_int32 * 3)(0, 4, 16)
+    assert lib.tp_sample3_grid_head_tf32(C.byref(planes), None, C.byref(empty), 1, C.byref(sg), 0, None, None, None, 5, None, None) == 0
 
 
 def test_cell_and_workspace_sizes():

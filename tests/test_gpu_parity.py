@@ -664,3 +664,40 @@ def test_decode_plus_head_fused_equals_two_kernels(B, dims, ncls, kind):
         "oc,bcq->boq", w2.view(32, 64).double(), torch.relu(torch.einsum("oc,bcq->boq", w1.view(64, 32).double(), feats.double())))))
     assert normwise(one, ref64) <= 3e-3
     assert torch.equal(one, two), f"fused vs two-kernel logits differ: max abs {float((one - two).abs().max())}"
+
+
+@pytest.mark.gpu
+def test_mixin_sample_and_decode_matches_reference_two_step():
+    """TriplaneOcc's `pred = self.decoder(self.sample_points_triplane(triplane, ref_3d))` (triplane_occ.py:182-186)
+    through TriplaneHotPathMixin.sample_and_decode: one kernel without gradients, the two calls with them; both match
+    the oracle's grid_sample chain followed by the reference head in fp32 within TF32 rounding."""
+    from efficient_multimodal_perception_b200 import Mlp, TriplaneHotPathMixin, synth
+
+    class Occ(TriplaneHotPathMixin, torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.triplane_range = [-25.0, -25.0, -5.0, 25.0, 25.0, 3.0]
+            self.triplane_voxel_size = (0.4, 0.4, 0.1)
+            self.occ_range, self.voxel_size = [-25.0, -25.0, -5.0, 25.0, 25.0, 3.0], (0.5, 0.5, 0.5)
+            self.decoder = Mlp(32, 5)
+
+    torch.manual_seed(3)
+    m = Occ().cuda()
+    tri = cu(torch.randn(2, 3, 32, 128, 128))
+    _, ref_3d = m.roi()
+    pts = cu(ref_3d).unsqueeze(0).repeat(2, 1, 1, 1, 1)
+    with torch.no_grad():
+        before = ops.launch_count
+        pred = m.sample_and_decode(tri, pts)
+        assert ops.launch_count == before + 2  # layout conversion + fused kernel
+        two = m.decoder(m.sample_points_triplane(tri, pts))
+    assert pred.shape == (2, 5, 99, 99, 16) and torch.equal(pred, two)
+    feats = O.sample_points_triplane_stacked(tri.cpu(), pts.cpu(), m.triplane_range, m.triplane_voxel_size)
+    with torch.no_grad():
+        ref = m.decoder.cpu()(feats.float())
+    m.decoder.cuda()
+    assert normwise(pred.cpu(), ref) <= 3e-3
+    tri.requires_grad_(True)
+    out = m.sample_and_decode(tri, pts)  # training path: autograd through both steps
+    out.square().mean().backward()
+    assert tri.grad is not None and normwise(out.detach().cpu(), ref) <= 3e-3

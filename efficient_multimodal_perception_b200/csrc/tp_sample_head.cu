@@ -255,6 +255,12 @@ sample3_grid_head_kernel(const __grid_constant__ HeadParams HP) {
   // epilogue: TMEM lane m = (warp & 3) * 32 + lane <-> query (j = m >> 4, k = m & 15) of the tile's lattice row
   const int em = (warp & 3) * 32 + lane, ej = em >> 4, ek = em & 15;
   int zeroed = 0, nblk_done = 0;
+  // staging bases of this thread (see `stage` below)
+  unsigned char* const st_a = smem + kHOffA + mn_tile_off(warp, lane);
+  const float* const st_t0 = T0 + warp * Cfg::S0 + jj;
+  const float* const st_t1 = T1 + warp * Cfg::S1 + jj * kBK;
+  const float* const st_t2 = T2 + warp * Cfg::S2;
+  static_assert(kGridThreads / 32 == 8, "stage: 8 warps, channel = warp + 8 n");
 
   unsigned int ticket = 0;
   int blk = blockIdx.x;
@@ -374,35 +380,37 @@ sample3_grid_head_kernel(const __grid_constant__ HeadParams HP) {
     const bool only_yz = (vote & 7) == 2, only_xz = (vote & 7) == 4;
     const int ntiles = (only_yz || only_xz) ? 1 : ni;
     // features of lattice row ii -> A tile (MN-major: channel rows of 128 queries, 16-byte chunk = 4 consecutive k)
+    // Warp w stages channels w, w + 8, w + 16, w + 24: everything that depends on the channel is (per-thread constant)
+    // + n * (compile-time stride) — the A-tile chunk moves by two K atoms (4096 B), the table rows by 8 rows, and the
+    // column swizzle of the yz / xz tables is ((n & 3) << 2) for warps 0-7.
     auto stage = [&](int ii) {
       if (only_xz) {
         // lane >> 2 plays i here: chunk `lane` of a channel row = tile rows (lane >> 2) * 16 + 4 kg .. + 3
         const bool ik_ok = (jj < ni) && (kg * 4 < nk);
+        const float* t2p = st_t2 + (jj < BI ? jj : 0) * kBK;
 #pragma unroll
         for (int n = 0; n < C / 8; ++n) {
-          const int c = warp + 8 * n;
-          const int xk = (kg * 4) ^ swz_bits(c);
+          const int xk = (kg * 4) ^ ((n & 3) << 2);
           uint4 r = make_uint4(0u, 0u, 0u, 0u);
-          if (jj < BI) {
-            const float4 s2 = *reinterpret_cast<const float4*>(T2 + c * Cfg::S2 + jj * kBK + xk);
-            if (ik_ok) {  // (0 + 0) + xz, as the general path computes it
-              r.x = rna_tf32(__fadd_rn(0.f, s2.x));
-              r.y = rna_tf32(__fadd_rn(0.f, s2.y));
-              r.z = rna_tf32(__fadd_rn(0.f, s2.z));
-              r.w = rna_tf32(__fadd_rn(0.f, s2.w));
-            }
+          if (ik_ok) {  // (0 + 0) + xz, as the general path computes it
+            const float4 s2 = *reinterpret_cast<const float4*>(t2p + n * 8 * Cfg::S2 + xk);
+            r.x = rna_tf32(__fadd_rn(0.f, s2.x));
+            r.y = rna_tf32(__fadd_rn(0.f, s2.y));
+            r.z = rna_tf32(__fadd_rn(0.f, s2.z));
+            r.w = rna_tf32(__fadd_rn(0.f, s2.w));
           }
-          *reinterpret_cast<uint4*>(smem + kHOffA + mn_tile_off(c, lane)) = r;
+          *reinterpret_cast<uint4*>(st_a + n * 4096) = r;
         }
       } else {
         const bool jk_ok = (jj < nj) && (kg * 4 < nk);
+        const float* t0p = st_t0 + ii * BJ;
+        const float* t2p = st_t2 + ii * kBK;
 #pragma unroll
         for (int n = 0; n < C / 8; ++n) {
-          const int c = warp + 8 * n;
-          const int xk = (kg * 4) ^ swz_bits(c);
-          const float4 s1 = *reinterpret_cast<const float4*>(T1 + c * Cfg::S1 + jj * kBK + xk);
-          const float s0 = T0[c * Cfg::S0 + ii * BJ + jj];
-          const float4 s2 = *reinterpret_cast<const float4*>(T2 + c * Cfg::S2 + ii * kBK + xk);
+          const int xk = (kg * 4) ^ ((n & 3) << 2);
+          const float4 s1 = *reinterpret_cast<const float4*>(st_t1 + n * 8 * Cfg::S1 + xk);
+          const float s0 = t0p[n * 8 * Cfg::S0];
+          const float4 s2 = *reinterpret_cast<const float4*>(t2p + n * 8 * Cfg::S2 + xk);
           uint4 r = make_uint4(0u, 0u, 0u, 0u);
           if (jk_ok) {
             r.x = rna_tf32(__fadd_rn(__fadd_rn(s0, s1.x), s2.x));  // (xy + yz) + xz  (triplane_occ.py:345)
@@ -410,7 +418,7 @@ sample3_grid_head_kernel(const __grid_constant__ HeadParams HP) {
             r.z = rna_tf32(__fadd_rn(__fadd_rn(s0, s1.z), s2.z));
             r.w = rna_tf32(__fadd_rn(__fadd_rn(s0, s1.w), s2.w));
           }
-          *reinterpret_cast<uint4*>(smem + kHOffA + mn_tile_off(c, lane)) = r;
+          *reinterpret_cast<uint4*>(st_a + n * 4096) = r;
         }
       }
       fence_async_smem_mlp();

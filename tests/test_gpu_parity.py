@@ -701,3 +701,43 @@ def test_mixin_sample_and_decode_matches_reference_two_step():
     out = m.sample_and_decode(tri, pts)  # training path: autograd through both steps
     out.square().mean().backward()
     assert tri.grad is not None and normwise(out.detach().cpu(), ref) <= 3e-3
+
+
+@pytest.mark.gpu
+def test_decode_plus_head_concurrent_streams_and_graph_replay():
+    """The fused kernel hands out blocks from a device-side ticket counter that resets itself: launches that overlap
+    on different streams must not share a counter, and a captured launch must be replayable."""
+    from efficient_multimodal_perception_b200 import synth
+    g = torch.Generator().manual_seed(11)
+    lo, vs, half = [-25.0, -25.0, -5.0], (0.4, 0.4, 0.1), [64.0] * 3
+    q = cu(synth.roi_lattice().reshape(1, -1, 3))
+    dims = (99, 99, 16)
+    w1 = cu(torch.randn(64, 32, generator=g) / 32 ** 0.5)
+    w2 = cu(torch.randn(32, 64, generator=g) / 8)
+    w3 = cu(torch.randn(5, 32, generator=g) / 32 ** 0.5)
+    tris = [cu(torch.randn(1, 3, 32, 128, 128, generator=g)) for _ in range(3)]
+    nhwc = [ops.planes_to_channels_last([t[:, 0], t[:, 1], t[:, 2]]) for t in tris]
+    want = [ops.mlp_head(ops.sample3(n, q, lo, vs, half, channels_last=True, grid_dims=dims), w1, w2, w3) for n in nhwc]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    got = [[] for _ in range(3)]
+    for rep in range(8):
+        for k, s in enumerate(streams):
+            with torch.cuda.stream(s):
+                got[k].append(ops.sample3_head(nhwc[k], q, lo, vs, half, w1, w2, w3, grid_dims=dims, channels_last=True))
+    torch.cuda.synchronize()
+    for k in range(3):
+        for o in got[k]:
+            assert torch.equal(o, want[k])
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        ops.sample3_head(nhwc[0], q, lo, vs, half, w1, w2, w3, grid_dims=dims, channels_last=True)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        outs = [ops.sample3_head(nhwc[k], q, lo, vs, half, w1, w2, w3, grid_dims=dims, channels_last=True) for k in range(3)]
+    for _ in range(5):
+        graph.replay()
+    torch.cuda.synchronize()
+    for k in range(3):
+        assert torch.equal(outs[k], want[k])

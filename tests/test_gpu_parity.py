@@ -741,3 +741,50 @@ def test_decode_plus_head_concurrent_streams_and_graph_replay():
     torch.cuda.synchronize()
     for k in range(3):
         assert torch.equal(outs[k], want[k])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", list(range(16)))
+def test_lattice_fuzz_grid_and_fused_equal_flat(seed):
+    """Random lattices that overlap the planes in random ways (fully inside, fully outside, only the x range inside,
+    only y, a corner, ...), random plane sizes / channel counts / batch: the lattice kernel (plane skip, zero fast
+    path) must equal the per-query kernel bit for bit, and for C = 32 the fused decode + head the two-kernel path."""
+    from efficient_multimodal_perception_b200 import synth
+    rs = np.random.RandomState(1000 + seed)
+    g = torch.Generator().manual_seed(2000 + seed)
+    B = int(rs.randint(1, 4))
+    C_ = int(rs.choice([4, 32, 32, 96]))
+    h, w = int(rs.randint(1, 41)), int(rs.randint(1, 41))
+    d = int(rs.choice([4, 8, 12, 16, 20, 32]))
+    sizes = [(int(rs.choice([16, 25, 128])), int(rs.choice([16, 80, 128]))) for _ in range(3)]  # (H, W) per plane
+    lo, vs = [-25.0, -25.0, -5.0], (0.4, 0.4, 0.1)
+    half = [float(rs.choice([8.0, 40.0, 64.0])) for _ in range(3)]
+    # lattice origin and step per axis: in range is [lo, lo + 2 * half * vs)
+    origin, step = [], []
+    for a in range(3):
+        span = 2 * half[a] * vs[a]
+        mode = rs.randint(0, 4)
+        n = (h, w, d)[a]
+        if mode == 0:    # inside
+            o, s = lo[a] + 0.1 * span, 0.7 * span / max(n, 1)
+        elif mode == 1:  # entirely below the range
+            o, s = lo[a] - 3.0 * span, 0.5 * span / max(n, 1)
+        elif mode == 2:  # entirely above
+            o, s = lo[a] + 1.5 * span, 0.5 * span / max(n, 1)
+        else:            # straddling both ends
+            o, s = lo[a] - 0.5 * span, 2.0 * span / max(n, 1)
+        origin.append(float(o)); step.append(float(s))
+    q = synth.lattice((h, w, d), step, origin).unsqueeze(0).repeat(B, 1, 1, 1, 1).reshape(B, -1, 3)
+    planes = [cu(torch.randn(B, C_, H, W, generator=g)) for H, W in sizes]
+    qd = cu(q)
+    arith = "cpu" if seed % 4 == 3 else "cuda"  # both replayed rounding chains
+    flat = ops.sample3(planes, qd, lo, vs, half, arith=arith)
+    grid = ops.sample3(planes, qd, lo, vs, half, grid_dims=(h, w, d), arith=arith)
+    assert torch.equal(grid, flat), f"seed {seed}: lattice kernel differs from the per-query kernel"
+    if C_ == 32:
+        w1 = cu(torch.randn(64, 32, generator=g) / 32 ** 0.5)
+        w2 = cu(torch.randn(32, 64, generator=g) / 8)
+        w3 = cu(torch.randn(7, 32, generator=g) / 32 ** 0.5)
+        two = ops.mlp_head(flat, w1, w2, w3)
+        one = ops.sample3_head(planes, qd, lo, vs, half, w1, w2, w3, grid_dims=(h, w, d), arith=arith)
+        assert torch.equal(one, two), f"seed {seed}: fused decode + head differs from the two-kernel path"

@@ -287,9 +287,9 @@ extern "C" int tp_sample3_grid_nhwc_f32(const tp_plane planes[3], int32_t C, con
   G.vec_ok = 1;
   G.nkb = (d + kBK - 1) / kBK;
   // block shape BI x 8 x 16: the larger one shares each yz footprint between 8 lattice rows instead
-  // of 4; the smaller one is for grids that would not give every resident CTA (4 per SM) a block
+  // of 4; the smaller one is for grids that would not give every resident CTA a block
   auto nblocks = [&](int bi) { return (int64_t)batch * ((h + bi - 1) / bi) * ((w + kBJ - 1) / kBJ) * G.nkb; };
-  int cfg = nblocks(8) >= 4 * kSMs ? 0 : 1;
+  int cfg = nblocks(8) >= kGridCtasPerSm * kSMs ? 0 : 1;
   if (const char* e = getenv("TP_GRID_TILE")) {  // experiments only: 0 = 8x8x16, 1 = 4x8x16
     const int v = atoi(e);
     if (v >= 0 && v <= 1) cfg = v;

@@ -22,11 +22,13 @@ __device__ __forceinline__ unsigned long long grid_gtimer() { unsigned long long
 #endif
 
 constexpr int kGridThreads = 256;
-// resident CTAs per SM: 4 (64 registers). 3 (85 registers, no spills in the block loop) is a little faster when the
-// planes are warm in L2 (roi 9.9 vs 10.5 us, elev 28.7 vs 30.3) but slower in bench.py's rotation over cold plane
-// sets (640k lattice 24.8 vs 23.8 us): the fourth CTA hides the DRAM latency of first touches.
+// resident CTAs per SM and table entries in flight per thread: 3 CTAs (80 registers) with 3 entries (12 independent
+// 16-byte loads) in flight. The table phase is a chain of dependent L2 round trips, (entries / 32) / in-flight of
+// them per block; 4 CTAs (64 registers) only leave room for 2 in flight. Measured after the plane-skip change, same
+// box: 640k lattice 21.4 vs 22.0 us, elev 26.4 vs 29.2, 8 x roi 42.9 vs 46.6, roi 9.9 vs 9.9 (3 CTAs with 2 in
+// flight: 22.3 / 27.5 / 45.3 / 10.2).
 #ifndef TP_GRID_CTAS_PER_SM
-#define TP_GRID_CTAS_PER_SM 4
+#define TP_GRID_CTAS_PER_SM 3
 #endif
 constexpr int kGridCtasPerSm = TP_GRID_CTAS_PER_SM;
 constexpr int kBK = 16;  // lattice block extent along d
@@ -104,6 +106,11 @@ __device__ __forceinline__ float4 accum_taps(const Taps& t, float4 w, int mk) {
 // One 2-D table (NR rounds of 32 entries) for this thread's 4 channels: two entries in flight, i.e. 8 independent
 // 16-byte loads before the first fma. `live` and `zero` are block-uniform: a plane with no in-bounds tap in the whole
 // block costs nothing (its table keeps, or is set to, the +0 the masked accumulation would have produced).
+#ifndef TP_TAB_IN_FLIGHT
+#define TP_TAB_IN_FLIGHT 3
+#endif
+constexpr int kTabInFlight = TP_TAB_IN_FLIGHT;  // table entries (x 4 taps x 16 B) a thread has in flight
+
 template <int NR>
 __device__ __forceinline__ void build_table(bool live, bool zero, const float4* __restrict__ pl, int C4, int WC4,
                                             const float4* s_w, const int2* s_om, float* t, int stride, bool cvalid,
@@ -121,12 +128,12 @@ __device__ __forceinline__ void build_table(bool live, bool zero, const float4* 
     return;
   }
 #pragma unroll
-  for (int r = 0; r < NR; r += 2) {
-    float4 wgt[2];
-    int mk[2];
-    Taps tp[2];
+  for (int r = 0; r < NR; r += kTabInFlight) {
+    float4 wgt[kTabInFlight];
+    int mk[kTabInFlight];
+    Taps tp[kTabInFlight];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < kTabInFlight; ++u) {
       if (r + u < NR) {
         wgt[u] = s_w[(r + u) * 32];
         const int2 om = s_om[(r + u) * 32];
@@ -135,7 +142,7 @@ __device__ __forceinline__ void build_table(bool live, bool zero, const float4* 
       }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < kTabInFlight; ++u) {
       if (r + u < NR) {
         const float4 a = accum_taps(tp[u], wgt[u], mk[u]);
         float* tt = t + (r + u) * 32;

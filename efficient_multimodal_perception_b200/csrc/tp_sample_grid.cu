@@ -223,7 +223,7 @@ sample3_grid_kernel(const __grid_constant__ GridParams G) {
 
 template <int ARITH, int C4T, int BI>
 static void launch_grid(const GridParams& G, int batch, cudaStream_t s) {
-  // persistent CTAs, 4 per SM; TP_GRID_CTAS (experiments) overrides the grid size
+  // persistent CTAs (kGridCtasPerSm per SM); TP_GRID_CTAS (experiments) overrides the grid size
   int64_t blocks = G.nblocks < kGridCtasPerSm * kSMs ? G.nblocks : kGridCtasPerSm * kSMs;
   if (const char* e = getenv("TP_GRID_CTAS")) {
     const int64_t v = atoll(e);

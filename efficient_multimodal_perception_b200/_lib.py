@@ -62,6 +62,8 @@ SIGNATURES = {
                                            C.POINTER(tp_sample_geom), _i32, _vp, _vp, _i64, _vp]),
     "tp_lift_cam_f32": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, C.c_float, C.c_float,
                                   _i32, _vp, _vp]),
+    "tp_sample3_grid_backward_nhwc_f32": (C.c_int, [C.POINTER(tp_plane * 3), _i32, _vp, C.POINTER(_i32 * 3), _i32,
+                                                    C.POINTER(tp_sample_geom), _i32, _vp, _vp]),
     "tp_sample3_backward_nhwc_f32": (C.c_int, [C.POINTER(tp_plane * 3), _i32, _vp, _i64, _i32,
                                                C.POINTER(tp_sample_geom), _i32, _vp, _vp]),
     "tp_encode_backward_f32": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _vp, _i32, C.POINTER(tp_geom), _i32, _i32,

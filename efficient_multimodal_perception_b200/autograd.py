@@ -63,14 +63,14 @@ class _Sample3(torch.autograd.Function):
     def forward(ctx, queries, lo, vs, half, arith, dims, p0, p1, p2):
         out = ops.sample3([p0, p1, p2], queries, lo, vs, half, arith=arith, grid_dims=dims)
         ctx.save_for_backward(queries)
-        ctx.cfg = (lo, vs, half, arith, [tuple(p.shape[-2:]) for p in (p0, p1, p2)])
+        ctx.cfg = (lo, vs, half, arith, [tuple(p.shape[-2:]) for p in (p0, p1, p2)], dims)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         (queries,) = ctx.saved_tensors
-        lo, vs, half, arith, shapes = ctx.cfg
-        g0, g1, g2 = ops.sample3_backward(grad_out, queries, shapes, lo, vs, half, arith=arith)
+        lo, vs, half, arith, shapes, dims = ctx.cfg
+        g0, g1, g2 = ops.sample3_backward(grad_out, queries, shapes, lo, vs, half, arith=arith, grid_dims=dims)
         need = ctx.needs_input_grad
         return (None, None, None, None, None, None, g0 if need[6] else None, g1 if need[7] else None,
                 g2 if need[8] else None)

@@ -423,9 +423,10 @@ def channels_last_to_nchw(x: torch.Tensor) -> torch.Tensor:
 
 
 def sample3_backward(grad_out: torch.Tensor, queries: torch.Tensor, plane_shapes, lo, vs, half, *,
-                     arith: str = "cuda") -> List[torch.Tensor]:
+                     arith: str = "cuda", grid_dims: Optional[Sequence[int]] = None) -> List[torch.Tensor]:
     """Gradient of sample3 w.r.t. the three planes. grad_out [B,C,Q], queries [B,Q,3], plane_shapes = three
-    (H, W). Returns three NCHW gradients [B,C,H,W]."""
+    (H, W). Returns three NCHW gradients [B,C,H,W]. grid_dims=(h, w, d): the queries are a flattened [B,h,w,d,3]
+    tensor; lattice blocks are reduced per index pair before the scatter (tp_sample3_grid_backward_nhwc_f32)."""
     global launch_count
     _need_cuda(grad_out, "grad_out")
     _need_cuda(queries, "queries")
@@ -438,8 +439,17 @@ def sample3_backward(grad_out: torch.Tensor, queries: torch.Tensor, plane_shapes
         arr[k].batch_stride = p.stride(0)
         arr[k].H, arr[k].W = p.shape[1], p.shape[2]
     sg = L.make_sample_geom(lo, vs, half)
-    L.check(L.lib().tp_sample3_backward_nhwc_f32(C.byref(arr), Cc, queries.data_ptr(), Q, B, C.byref(sg), _ARITH[arith],
-                                                 grad_out.data_ptr(), _stream(grad_out)), "tp_sample3_backward_nhwc_f32")
+    if grid_dims is not None:
+        h, w, d = (int(v) for v in grid_dims)
+        if h * w * d != Q:
+            raise TriplaneError(f"sample3_backward: grid_dims {tuple(grid_dims)} do not multiply to Q={Q}")
+        dims = (C.c_int32 * 3)(h, w, d)
+        L.check(L.lib().tp_sample3_grid_backward_nhwc_f32(C.byref(arr), Cc, queries.data_ptr(), C.byref(dims), B, C.byref(sg),
+                                                          _ARITH[arith], grad_out.data_ptr(), _stream(grad_out)),
+                "tp_sample3_grid_backward_nhwc_f32")
+    else:
+        L.check(L.lib().tp_sample3_backward_nhwc_f32(C.byref(arr), Cc, queries.data_ptr(), Q, B, C.byref(sg), _ARITH[arith],
+                                                     grad_out.data_ptr(), _stream(grad_out)), "tp_sample3_backward_nhwc_f32")
     launch_count += 1 if Q else 0
     return [channels_last_to_nchw(g) for g in g_nhwc]
 

@@ -235,6 +235,12 @@ TP_API int tp_lift_cam_f32(const float* points, int32_t point_stride, int64_t n_
 TP_API int tp_sample3_backward_nhwc_f32(const tp_plane gplanes_nhwc[3], int32_t C, const float* queries, int64_t Q,
                                  int32_t batch, const tp_sample_geom* sg, int32_t arith, const float* grad_out,
                                  void* stream);
+/* the same for [B,h,w,d,3] query tensors (dims = {h, w, d}): lattice blocks (checked on the device, as in
+ * tp_sample3_grid_nhwc_f32) first sum grad_out over the lattice index a plane does not depend on, then scatter one
+ * footprint per index pair: ~10x fewer reductions into the gradient planes. Other blocks scatter per query. */
+TP_API int tp_sample3_grid_backward_nhwc_f32(const tp_plane gplanes_nhwc[3], int32_t C, const float* queries,
+                                      const int32_t dims[3], int32_t batch, const tp_sample_geom* sg, int32_t arith,
+                                      const float* grad_out, void* stream);
 TP_API int tp_encode_backward_f32(const float* feats, int64_t feat_stride, int32_t C, const int32_t* idx,
                            int64_t n_total, const int64_t* offsets, int32_t batch, const tp_geom* geom,
                            int32_t reduce, int32_t clamp_zero, const float* out_xy, const float* out_yz,

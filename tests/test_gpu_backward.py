@@ -130,3 +130,44 @@ def test_projector_module_trains():
             assert float(p.grad.abs().max()) < 1e-6, name
             continue
         assert normwise(p.grad.cpu(), pc.grad) <= 1e-3, name  # cuBLAS vs CPU GEMMs + BatchNorm statistics
+
+
+@pytest.mark.parametrize("seed", list(range(8)))
+def test_sample_backward_lattice_kernel_matches_per_query_kernel(seed):
+    """tp_sample3_grid_backward_nhwc_f32 (sum over the free lattice index, then one scatter per index pair) vs the
+    per-query scatter kernel on random lattices / plane overlaps / shapes, incl. jittered (non-lattice) blocks:
+    same gradient planes to fp32 rounding (the association of the sums differs)."""
+    import numpy as np
+    from efficient_multimodal_perception_b200 import ops
+    rs = np.random.RandomState(500 + seed)
+    g = torch.Generator().manual_seed(600 + seed)
+    B = int(rs.randint(1, 3))
+    C_ = int(rs.choice([4, 32, 96]))
+    h, w = int(rs.randint(1, 30)), int(rs.randint(1, 30))
+    d = int(rs.choice([4, 8, 16, 20]))
+    shapes = [(int(rs.choice([16, 128])), int(rs.choice([16, 80, 128]))) for _ in range(3)]
+    lo, vs = [-25.0, -25.0, -5.0], (0.4, 0.4, 0.1)
+    half = [float(rs.choice([8.0, 40.0, 64.0])) for _ in range(3)]
+    origin, step = [], []
+    for a in range(3):
+        span = 2 * half[a] * vs[a]
+        n = (h, w, d)[a]
+        mode = rs.randint(0, 3)
+        o, s = [(lo[a] + 0.1 * span, 0.7 * span / n), (lo[a] + 1.5 * span, 0.5 * span / n), (lo[a] - 0.5 * span, 2.0 * span / n)][mode]
+        origin.append(float(o)); step.append(float(s))
+    q = synth.lattice((h, w, d), step, origin).unsqueeze(0).repeat(B, 1, 1, 1, 1)
+    if seed % 4 == 1:
+        q = q + 0.03 * torch.randn(q.shape, generator=g)        # nothing is a lattice
+    if seed % 4 == 2:
+        q[:, : max(1, h // 2)] += 0.03 * torch.randn(q[:, : max(1, h // 2)].shape, generator=g)  # some blocks are
+    qd = cu(q.reshape(B, -1, 3))
+    gout = cu(torch.randn(B, C_, h * w * d, generator=g))
+    arith = "cpu" if seed % 2 else "cuda"
+    flat = ops.sample3_backward(gout, qd, shapes, lo, vs, half, arith=arith)
+    grid = ops.sample3_backward(gout, qd, shapes, lo, vs, half, arith=arith, grid_dims=(h, w, d))
+    for a, b in zip(grid, flat):
+        assert a.shape == b.shape
+        if float(b.abs().max()) > 0:
+            assert normwise(a, b) <= TOL
+        else:
+            assert float(a.abs().max()) == 0

@@ -26,6 +26,9 @@ for name, q in (("lattice640k", synth.occ_gt_lattice().reshape(1, -1, 3)), ("uni
     tri = synth.triplane_stacked(1, 32, 128, seed=1).to(dev).requires_grad_()
     g = torch.randn(1, 32, q.shape[1], device=dev)
     t_ours = timeit(lambda: ops.sample3_backward(g, q, [(128, 128)] * 3, LO, VS, HALF))
+    if name == "lattice640k":
+        t_grid = timeit(lambda: ops.sample3_backward(g, q, [(128, 128)] * 3, LO, VS, HALF, grid_dims=(200, 200, 16)))
+        print(f"decode backward {name:12s}: lattice kernel {t_grid:8.1f} us (incl. zeroing + NHWC->NCHW of the gradient planes)")
     planes = [tri[:, 0], tri[:, 1], tri[:, 2]]
     def tb():
         out = torch_chain(planes, q)

@@ -171,11 +171,17 @@ sample3_grid_backward_kernel(const __grid_constant__ GridBwdParams BP) {
       for (int c = warp; c < 32; c += kGridThreads / 32) {
         const int xk = (kg * 4) ^ swz_bits(c);
         const float* go = BP.gout + ((int64_t)b * C + ch * 32 + c) * P.Q + qblk + jj * G.d + kg * 4;
+        // all BI rows of this channel in flight before the first reduction (the loop below is a chain of shuffles)
+        float4 gr[BI];
+#pragma unroll
+        for (int ii = 0; ii < BI; ++ii) {
+          gr[ii] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (jk_ok && ii < ni && c < cmax) gr[ii] = __ldcs(reinterpret_cast<const float4*>(go + (int64_t)ii * wd));
+        }
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int ii = 0; ii < BI; ++ii) {
-          float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (jk_ok && ii < ni && c < cmax) g = __ldcs(reinterpret_cast<const float4*>(go + (int64_t)ii * wd));
+          const float4 g = gr[ii];
           acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
           // xz(i, k): sum over the 8 j of the block = lanes that differ in bits 2-4
           float4 s = g;

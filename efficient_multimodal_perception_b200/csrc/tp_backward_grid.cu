@@ -45,7 +45,6 @@ __global__ void __launch_bounds__(kGridThreads, kBwdGridCtasPerSm)
 sample3_grid_backward_kernel(const __grid_constant__ GridBwdParams BP) {
   using Cfg = GridCfg<BI>;
   constexpr int BJ = kBJ;
-  constexpr int QPT = BI * BJ * kBK / kGridThreads;
   extern __shared__ __align__(16) float smem[];
   float4* const s_w = reinterpret_cast<float4*>(smem + Cfg::kWords);
   int2* const s_om = reinterpret_cast<int2*>(s_w + Cfg::E);
@@ -67,7 +66,6 @@ sample3_grid_backward_kernel(const __grid_constant__ GridBwdParams BP) {
   const float* const r0 = T0 + (4 * l8) * Cfg::S0 + ent;
   const float* const r1 = T1 + (4 * l8) * Cfg::S1 + (ent ^ swz_bits(4 * l8));
   const float* const r2 = T2 + (4 * l8) * Cfg::S2 + (ent ^ swz_bits(4 * l8));
-  const int ak = tid & (kBK - 1), aj = (tid / kBK) % BJ, ia = tid / (kBK * BJ);
   const int kg = lane & 3, jj = lane >> 2;
   int nblk_done = 0;
   if (tid == 0) s_vote[0] = 0;
@@ -80,51 +78,10 @@ sample3_grid_backward_kernel(const __grid_constant__ GridBwdParams BP) {
     const int64_t qblk = ((int64_t)i0 * G.w + j0) * G.d + k0;  // first query of the block inside its sample
     const float* q00 = P.queries + ((int64_t)b * P.Q + qblk) * 3;
 
-    // ---- A / B: as in the forward kernel ------------------------------------------------------------------------
-    bool ok = true;
-    if (aj < nj && ak < nk) {
-      const unsigned yr = __float_as_uint(__ldg(q00 + aj * G.d * 3 + 1));
-      const unsigned zr = __float_as_uint(__ldg(q00 + ak * 3 + 2));
-#pragma unroll
-      for (int t = 0; t < QPT; ++t) {
-        const int ii = ia + t * (kGridThreads / (kBK * BJ));
-        if (ii < ni) {
-          const float* qi = q00 + ii * wd * 3;
-          const float* qp = qi + (aj * G.d + ak) * 3;
-          const unsigned x = __float_as_uint(__ldg(qp)), y = __float_as_uint(__ldg(qp + 1)),
-                         z = __float_as_uint(__ldg(qp + 2));
-          ok &= (x == __float_as_uint(__ldg(qi))) & (y == yr) & (z == zr);
-        }
-      }
-    }
-    int live = 0;
-    for (int e = tid; e < Cfg::E; e += kGridThreads) {
-      int pl, a0, a1, e0i, e1i, n0, n1, s0, s1;
-      if (e < Cfg::E0) {
-        pl = 0; a0 = 0; a1 = 1; e0i = e / BJ; e1i = e % BJ; n0 = ni; n1 = nj; s0 = wd; s1 = G.d;
-      } else if (e < Cfg::E0 + Cfg::E1) {
-        const int r = e - Cfg::E0;
-        pl = 1; a0 = 1; a1 = 2; e0i = r / kBK; e1i = r % kBK; n0 = nj; n1 = nk; s0 = G.d; s1 = 1;
-      } else {
-        const int r = e - Cfg::E0 - Cfg::E1;
-        pl = 2; a0 = 0; a1 = 2; e0i = r / kBK; e1i = r % kBK; n0 = ni; n1 = nk; s0 = wd; s1 = 1;
-      }
-      float4 wgt = make_float4(0.f, 0.f, 0.f, 0.f);
-      int base = 0, mask = 0;
-      if (e0i < n0 && e1i < n1) {
-        const float g0 = grid_coord<ARITH>(P, __ldg(q00 + e0i * s0 * 3 + a0), a0);
-        const float g1 = grid_coord<ARITH>(P, __ldg(q00 + e1i * s1 * 3 + a1), a1);
-        plane_setup<ARITH>(g0, g1, P.W[pl], P.H[pl], wgt, base, mask);
-      }
-      s_w[e] = wgt;
-      s_om[e] = make_int2(base * C4, mask);
-      if (mask) live |= 1 << pl;
-    }
-    {
-      const int bits = __reduce_or_sync(0xffffffffu, live | (ok ? 0 : 8));
-      if (lane == 0 && bits) atomicOr(&s_vote[nblk_done & 1], bits);
-      if (tid == 0) s_vote[(nblk_done + 1) & 1] = 0;
-    }
+    // ---- A / B: as in the forward kernel (tp_sample_grid.cuh) ---------------------------------------------------
+    const bool ok = grid_block_is_lattice<BI>(G, q00, ni, nj, nk, wd, tid);
+    const int live = grid_build_records<ARITH, BI>(G, q00, ni, nj, nk, wd, C4, s_w, s_om, tid);
+    grid_cast_vote(s_vote, nblk_done, live, ok, tid);
     __syncthreads();
     const int vote = s_vote[nblk_done & 1];
     ++nblk_done;

@@ -90,54 +90,10 @@ sample3_grid_kernel(const __grid_constant__ GridParams G) {
     const float* q00 = P.queries + ((int64_t)b * P.Q + ((int64_t)i0 * G.w + j0) * G.d + k0) * 3;  // block origin
 
     // ---- A: read the block's queries once; is x = x(i), y = y(j), z = z(k) bit for bit? --------
-    bool ok = true;
-    if (aj < nj && ak < nk) {
-      const unsigned yr = __float_as_uint(__ldg(q00 + aj * G.d * 3 + 1));
-      const unsigned zr = __float_as_uint(__ldg(q00 + ak * 3 + 2));
-#pragma unroll
-      for (int t = 0; t < QPT; ++t) {
-        const int ii = ia + t * (kGridThreads / (kBK * BJ));
-        if (ii < ni) {
-          const float* qi = q00 + ii * wd * 3;
-          const float* qp = qi + (aj * G.d + ak) * 3;
-          const unsigned x = __float_as_uint(__ldg(qp)), y = __float_as_uint(__ldg(qp + 1)),
-                         z = __float_as_uint(__ldg(qp + 2));
-          ok &= (x == __float_as_uint(__ldg(qi))) & (y == yr) & (z == zr);
-        }
-      }
-    }
+    const bool ok = grid_block_is_lattice<BI>(G, q00, ni, nj, nk, wd, tid);
     // ---- B: one bilinear footprint per table entry (index pair), from the representative queries -
-    int live = 0;  // bit p: this thread saw an entry of plane p with an in-bounds tap
-    for (int e = tid; e < Cfg::E; e += kGridThreads) {
-      int pl, a0, a1, e0i, e1i, n0, n1, s0, s1;  // s: query stride of the two lattice indices
-      if (e < Cfg::E0) {                      // xy(i,j): x -> W, y -> H of plane 0
-        pl = 0; a0 = 0; a1 = 1; e0i = e / BJ; e1i = e % BJ; n0 = ni; n1 = nj; s0 = wd; s1 = G.d;
-      } else if (e < Cfg::E0 + Cfg::E1) {     // yz(j,k): y -> W, z -> H of plane 1
-        const int r = e - Cfg::E0;
-        pl = 1; a0 = 1; a1 = 2; e0i = r / kBK; e1i = r % kBK; n0 = nj; n1 = nk; s0 = G.d; s1 = 1;
-      } else {                                // xz(i,k): x -> W, z -> H of plane 2
-        const int r = e - Cfg::E0 - Cfg::E1;
-        pl = 2; a0 = 0; a1 = 2; e0i = r / kBK; e1i = r % kBK; n0 = ni; n1 = nk; s0 = wd; s1 = 1;
-      }
-      float4 wgt = make_float4(0.f, 0.f, 0.f, 0.f);
-      int base = 0, mask = 0;
-      if (e0i < n0 && e1i < n1) {
-        const float g0 = grid_coord<ARITH>(P, __ldg(q00 + e0i * s0 * 3 + a0), a0);
-        const float g1 = grid_coord<ARITH>(P, __ldg(q00 + e1i * s1 * 3 + a1), a1);
-        plane_setup<ARITH>(g0, g1, P.W[pl], P.H[pl], wgt, base, mask);
-      }
-      s_w[e] = wgt;
-      s_om[e] = make_int2(base * C4, mask);
-      if (mask) live |= 1 << pl;
-    }
-    if (blk == (int)blockIdx.x) GRID_G(3);
-    // every warp is past the previous block's output phase once it arrives here
-    // one barrier for both votes: bit 3 = some query broke the lattice, bits 0-2 = planes with something to gather
-    {
-      const int bits = __reduce_or_sync(0xffffffffu, live | (ok ? 0 : 8));
-      if (lane == 0 && bits) atomicOr(&s_vote[nblk_done & 1], bits);
-      if (tid == 0) s_vote[(nblk_done + 1) & 1] = 0;  // last read before the previous block's table barrier
-    }
+    const int live = grid_build_records<ARITH, BI>(G, q00, ni, nj, nk, wd, C4, s_w, s_om, tid);
+    grid_cast_vote(s_vote, nblk_done, live, ok, tid);
     __syncthreads();
     const int vote = s_vote[nblk_done & 1];
     ++nblk_done;

@@ -171,4 +171,76 @@ __device__ __forceinline__ BlockPos block_pos(const GridParams& G, int blk) {
   return p;
 }
 
+// ---- phases A and B of a lattice block, shared by the forward, backward and decode + head kernels ---------------
+
+// A: every thread reads its queries of the block (k and j fixed per thread, i strided) and compares them bit for bit
+// with the block's representatives: x with the row's first query, y with the column's, z with the depth's.
+template <int BI>
+__device__ __forceinline__ bool grid_block_is_lattice(const GridParams& G, const float* q00, int ni, int nj, int nk,
+                                                      int wd, int tid) {
+  constexpr int QPT = BI * kBJ * kBK / kGridThreads;
+  const int ak = tid & (kBK - 1), aj = (tid / kBK) % kBJ, ia = tid / (kBK * kBJ);
+  bool ok = true;
+  if (aj < nj && ak < nk) {
+    const unsigned yr = __float_as_uint(__ldg(q00 + aj * G.d * 3 + 1));
+    const unsigned zr = __float_as_uint(__ldg(q00 + ak * 3 + 2));
+#pragma unroll
+    for (int t = 0; t < QPT; ++t) {
+      const int ii = ia + t * (kGridThreads / (kBK * kBJ));
+      if (ii < ni) {
+        const float* qi = q00 + ii * wd * 3;
+        const float* qp = qi + (aj * G.d + ak) * 3;
+        const unsigned x = __float_as_uint(__ldg(qp)), y = __float_as_uint(__ldg(qp + 1)),
+                       z = __float_as_uint(__ldg(qp + 2));
+        ok &= (x == __float_as_uint(__ldg(qi))) & (y == yr) & (z == zr);
+      }
+    }
+  }
+  return ok;
+}
+
+// B: one record per table entry (index pair) from the block's representative queries: 4 bilinear weights, nw tap
+// offset in float4 units, in-bounds mask. Returns this thread's "plane p has an in-bounds tap" bits.
+// (Measured: computing the 2 (BI + 8 + 16) distinct 1-D taps once and combining pairs saves ~half of this phase's
+// instructions but needs a barrier in between — same time on the 640k lattice, 2 % slower on 8 x roi.)
+template <int ARITH, int BI>
+__device__ __forceinline__ int grid_build_records(const GridParams& G, const float* q00, int ni, int nj, int nk, int wd,
+                                                  int C4, float4* s_w, int2* s_om, int tid) {
+  using Cfg = GridCfg<BI>;
+  const SampleParams& P = G.S;
+  int live = 0;
+  for (int e = tid; e < Cfg::E; e += kGridThreads) {
+    int pl, a0, a1, e0i, e1i, n0, n1, s0, s1;  // s: query stride of the two lattice indices
+    if (e < Cfg::E0) {                      // xy(i,j): x -> W, y -> H of plane 0
+      pl = 0; a0 = 0; a1 = 1; e0i = e / kBJ; e1i = e % kBJ; n0 = ni; n1 = nj; s0 = wd; s1 = G.d;
+    } else if (e < Cfg::E0 + Cfg::E1) {     // yz(j,k): y -> W, z -> H of plane 1
+      const int r = e - Cfg::E0;
+      pl = 1; a0 = 1; a1 = 2; e0i = r / kBK; e1i = r % kBK; n0 = nj; n1 = nk; s0 = G.d; s1 = 1;
+    } else {                                // xz(i,k): x -> W, z -> H of plane 2
+      const int r = e - Cfg::E0 - Cfg::E1;
+      pl = 2; a0 = 0; a1 = 2; e0i = r / kBK; e1i = r % kBK; n0 = ni; n1 = nk; s0 = wd; s1 = 1;
+    }
+    float4 wgt = make_float4(0.f, 0.f, 0.f, 0.f);
+    int base = 0, mask = 0;
+    if (e0i < n0 && e1i < n1) {
+      const float g0 = grid_coord<ARITH>(P, __ldg(q00 + e0i * s0 * 3 + a0), a0);
+      const float g1 = grid_coord<ARITH>(P, __ldg(q00 + e1i * s1 * 3 + a1), a1);
+      plane_setup<ARITH>(g0, g1, P.W[pl], P.H[pl], wgt, base, mask);
+    }
+    s_w[e] = wgt;
+    s_om[e] = make_int2(base * C4, mask);
+    if (mask) live |= 1 << pl;
+  }
+  return live;
+}
+
+// block-wide OR of (live planes | 8 if some query broke the lattice): warp redux + one shared atomic. s_vote[2] is a
+// double buffer: the other slot is cleared here for the next block; the caller provides the barrier and reads
+// s_vote[n & 1] after it.
+__device__ __forceinline__ void grid_cast_vote(int* s_vote, int n, int live, bool ok, int tid) {
+  const int bits = __reduce_or_sync(0xffffffffu, live | (ok ? 0 : 8));
+  if ((tid & 31) == 0 && bits) atomicOr(&s_vote[n & 1], bits);
+  if (tid == 0) s_vote[(n + 1) & 1] = 0;
+}
+
 }  // namespace tp

@@ -1,7 +1,7 @@
 // Per-CTA timeline (globaltimer at entry / start of the second block / exit) of the lattice decode kernel on the
 // 640k-query occupancy lattice (200 x 200 x 16, C = 32, three 128 x 128 planes).
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -DTP_GRID_TRACE -I efficient_multimodal_perception_b200/csrc \
-//        -I include -o build/micro/grid_trace tools/micro/grid_trace.cu build/csrc/tp_{sample,api,voxelize,encode,lift,backward,mlp}.o
+//        -I include -o build/micro/grid_trace tools/micro/grid_trace.cu build/csrc/tp_{sample,sample_head,api,voxelize,encode,lift,backward,backward_grid,mlp}.o
 #include <cstdarg>
 #include <cstdio>
 #include <vector>

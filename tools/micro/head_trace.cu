@@ -1,7 +1,7 @@
 // Phase timeline (globaltimer) of the decode + head kernel on the 640k-query occupancy lattice: for every CTA the first
 // block that runs tile chains: A+B, C, first stage, the four tiles; plus CTA start / end.
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -DTP_HEAD_TRACE -I efficient_multimodal_perception_b200/csrc \
-//        -I include -o build/micro/head_trace tools/micro/head_trace.cu build/csrc/tp_{sample,sample_grid,api,voxelize,encode,lift,backward,mlp}.o
+//        -I include -o build/micro/head_trace tools/micro/head_trace.cu build/csrc/tp_{sample,sample_grid,api,voxelize,encode,lift,backward,backward_grid,mlp}.o
 #include <algorithm>
 #include <cstdio>
 #include <vector>

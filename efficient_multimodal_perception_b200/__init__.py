@@ -7,10 +7,13 @@ method names. There is no CPU or PyTorch fallback: a missing library raises Trip
 """
 from ._lib import LIB_PATH, TriplaneError, lib
 from . import ops, synth
-from .modules import (Mlp, PointTriplaneProjector, TriplaneHotPathMixin, point_to_cam, register_with_mmdet, roi,
-                      sample_and_decode, sample_points_triplane, voxelize_points)
+from .modules import (Mlp, PointTriplaneProjector, TriplaneHotPathMixin, cam_proj_feat, cam_rec_feat, interact,
+                      point_to_cam, radius_search, register_with_mmdet, roi, sam_subsets, sample_and_decode,
+                      sample_points_triplane, sample_points_triplane_segments, sample_roi_triplane, voxelize_points)
 
 __all__ = ["LIB_PATH", "TriplaneError", "lib", "ops", "synth", "Mlp", "PointTriplaneProjector",
-           "TriplaneHotPathMixin", "point_to_cam", "register_with_mmdet", "roi", "sample_and_decode", "sample_points_triplane", "voxelize_points"]
+           "TriplaneHotPathMixin", "cam_proj_feat", "cam_rec_feat", "interact", "point_to_cam", "radius_search",
+           "register_with_mmdet", "roi", "sam_subsets", "sample_and_decode", "sample_points_triplane",
+           "sample_points_triplane_segments", "sample_roi_triplane", "voxelize_points"]
 
 register_with_mmdet()

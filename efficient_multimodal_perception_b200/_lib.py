@@ -60,6 +60,23 @@ SIGNATURES = {
                                            C.POINTER(tp_sample_geom), _i32, _vp, _vp]),
     "tp_sample3_grid_nchw_f32": (C.c_int, [C.POINTER(tp_plane * 3), _i32, _vp, C.POINTER(_i32 * 3), _i32,
                                            C.POINTER(tp_sample_geom), _i32, _vp, _vp, _i64, _vp]),
+    "tp_sample3_lattice_nhwc_f32": (C.c_int, [C.POINTER(tp_plane * 3), _i32, C.POINTER(_i32 * 3), C.POINTER(C.c_float * 3),
+                                              C.POINTER(C.c_float * 3), _i32, C.POINTER(tp_sample_geom), _i32, _vp, _vp]),
+    "tp_sample3_seg_nhwc_f32": (C.c_int, [C.POINTER(tp_plane * 3), _i32, _vp, _i64, _vp, _vp, _i32, _i32,
+                                          C.POINTER(tp_sample_geom), _i32, _vp, _vp]),
+    "tp_sample3_seg_backward_nhwc_f32": (C.c_int, [C.POINTER(tp_plane * 3), _i32, _vp, _i64, _vp, _vp, _i32, _i32,
+                                                   C.POINTER(tp_sample_geom), _i32, _vp, _vp]),
+    "tp_pixel_winner_coors_i32": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp]),
+    "tp_pixel_winner_points_i32": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _vp, _i32, C.c_float, C.c_float, _vp, _vp]),
+    "tp_winner_gather_f32": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "tp_winner_gather_backward_f32": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
+    "tp_range_project_f32": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _i32, C.c_float, C.c_float, _i32, _i32, _i32, _vp, _vp,
+                                       _vp, _vp]),
+    "tp_range_gather_f32": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _i32, _i32, _vp, _vp]),
+    "tp_range_gather_backward_f32": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _i32, _i32, _vp, _vp]),
+    "tp_posembed_scatter_f32": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
+    "tp_posembed_scatter_backward_f32": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
+    "tp_radius_i32": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, C.c_float, _i32, _vp, _vp, _vp]),
     "tp_lift_cam_f32": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, C.c_float, C.c_float,
                                   _i32, _vp, _vp]),
     "tp_sample3_grid_backward_nhwc_f32": (C.c_int, [C.POINTER(tp_plane * 3), _i32, _vp, C.POINTER(_i32 * 3), _i32,

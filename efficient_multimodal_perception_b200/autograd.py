@@ -110,3 +110,88 @@ def lift_cam_autograd(points, offsets, img_features, cams, resize_dims, arith: s
     if points.requires_grad:
         raise TriplaneError("point_to_cam: gradients w.r.t. the points are not implemented")
     return _LiftCam.apply(img_features, points, offsets, cams, resize_dims, arith)
+
+
+class _Sample3Segments(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, queries, seg_offsets, seg_batch, lo, vs, half, arith, p0, p1, p2):
+        out = ops.sample3_segments([p0, p1, p2], queries, seg_offsets, seg_batch, lo, vs, half, arith=arith)
+        ctx.save_for_backward(queries, seg_offsets, seg_batch)
+        ctx.cfg = (lo, vs, half, arith, p0.shape[0], [tuple(p.shape[-2:]) for p in (p0, p1, p2)])
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        queries, seg_offsets, seg_batch = ctx.saved_tensors
+        lo, vs, half, arith, batch, shapes = ctx.cfg
+        g0, g1, g2 = ops.sample3_segments_backward(grad_out, queries, seg_offsets, seg_batch, batch, shapes, lo, vs, half,
+                                                   arith=arith)
+        need = ctx.needs_input_grad
+        return (None, None, None, None, None, None, None, g0 if need[7] else None, g1 if need[8] else None,
+                g2 if need[9] else None)
+
+
+def sample3_segments_autograd(triplane, queries, seg_offsets, seg_batch, lo, vs, half, arith: str = "cuda") -> torch.Tensor:
+    """Differentiable (w.r.t. the planes) ragged-subset decode: [T, C] point-major."""
+    if queries.requires_grad:
+        raise TriplaneError("sample_points_triplane: gradients w.r.t. the query points are not implemented")
+    planes = [triplane[:, 0], triplane[:, 1], triplane[:, 2]] if isinstance(triplane, torch.Tensor) else list(triplane)
+    return _Sample3Segments.apply(queries, seg_offsets, seg_batch, list(lo), list(vs), list(half), arith, *planes)
+
+
+class _WinnerGather(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, winner, imgs_per_feat, layout, row0):
+        out = ops.winner_gather(winner, feat, imgs_per_feat, layout=layout, row0=row0)
+        ctx.save_for_backward(winner, row0)
+        ctx.cfg = (tuple(feat.shape), imgs_per_feat, layout)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        winner, row0 = ctx.saved_tensors
+        shape, imgs_per_feat, layout = ctx.cfg
+        return ops.winner_gather_backward(winner, grad_out, shape, imgs_per_feat, layout=layout, row0=row0), None, None, None, None
+
+
+def winner_gather_autograd(feat, winner, imgs_per_feat, layout="bcn", row0=None):
+    return _WinnerGather.apply(feat, winner, imgs_per_feat, layout, row0)
+
+
+class _RangeGather(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img_features, fidx):
+        ctx.save_for_backward(fidx)
+        ctx.shape = tuple(img_features.shape)
+        return ops.range_gather(fidx, img_features)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (fidx,) = ctx.saved_tensors
+        return ops.range_gather_backward(fidx, grad_out, ctx.shape), None
+
+
+def range_gather_autograd(img_features, fidx):
+    return _RangeGather.apply(img_features, fidx)
+
+
+class _PosEmbedScatter(torch.autograd.Function):
+    """img_features + scatter(pos_embed): the forward updates a COPY when gradients are tracked (autograd forbids the
+    reference's in-place write into a tensor other ops have saved); without gradients ops.posembed_scatter_ is used."""
+
+    @staticmethod
+    def forward(ctx, img_features, pos_embed, winner):
+        ctx.save_for_backward(winner)
+        out = img_features.contiguous().clone()
+        return ops.posembed_scatter_(out, winner, pos_embed)
+
+    @staticmethod
+    def backward(ctx, grad_img):
+        (winner,) = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        gpe = ops.posembed_scatter_backward(grad_img, winner) if need[1] else None
+        return (grad_img if need[0] else None), gpe, None
+
+
+def posembed_scatter_autograd(img_features, pos_embed, winner):
+    return _PosEmbedScatter.apply(img_features, pos_embed, winner)

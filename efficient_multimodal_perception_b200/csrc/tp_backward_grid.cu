@@ -174,13 +174,7 @@ static void launch_grid_bwd(const GridBwdParams& BP, cudaStream_t s) {
   const int nb = BP.G.nblocks;
   const int cap = kBwdGridCtasPerSm * kSMs;
   auto kern = sample3_grid_backward_kernel<ARITH, BI>;
-  static bool opted_in[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !opted_in[dev]) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GridCfg<BI>::kSmemBytes);
-    if (dev >= 0 && dev < 64) opted_in[dev] = true;
-  }
+  opt_in_smem<sample3_grid_backward_kernel<ARITH, BI>>(GridCfg<BI>::kSmemBytes);  // a failure surfaces at the launch check
   kern<<<(unsigned)(nb < cap ? nb : cap), kGridThreads, GridCfg<BI>::kSmemBytes, s>>>(BP);
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include "triplane.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -25,6 +26,22 @@ int check_cuda(cudaError_t e, const char* what);
     cudaError_t _e = cudaGetLastError();               \
     if (_e != cudaSuccess) return ::tp::check_cuda(_e, name); \
   } while (0)
+
+// > 48 KB of dynamic shared memory needs a per-device opt-in. One atomic device bitmask per kernel
+// (the kernel is a template argument, so two kernels of the same signature do not share it);
+// racing threads at worst repeat the idempotent cudaFuncSetAttribute.
+template <auto Kern>
+inline cudaError_t opt_in_smem(int bytes) {
+  static std::atomic<unsigned long long> done{0};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const bool tracked = dev >= 0 && dev < 64;
+  if (tracked && ((done.load(std::memory_order_acquire) >> dev) & 1ull)) return cudaSuccess;
+  e = cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && tracked) done.fetch_or(1ull << dev, std::memory_order_release);
+  return e;
+}
 
 // ---- the reference's coordinate chain, op by op, never contracted -----------------------------
 // (p - lo) (/) vs : torch-CUDA multiplies by the fp32 reciprocal of the Python-float divisor,

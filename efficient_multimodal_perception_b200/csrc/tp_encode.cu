@@ -779,13 +779,9 @@ extern "C" int tp_encode_f32(const float* feats, int64_t feat_stride, int32_t C,
   }
   constexpr int kSmem = kTileFloats * 4 + kMaxCpt * 4;  // 17 KB
   const size_t smem = kSmem;
-  static bool attr_done = false;
-  if (!attr_done) {
-    TP_CUDA(cudaFuncSetAttribute(encode_reduce_kernel<TP_REDUCE_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    TP_CUDA(cudaFuncSetAttribute(encode_reduce_kernel<TP_REDUCE_MEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    TP_CUDA(cudaFuncSetAttribute(encode_reduce_kernel<TP_REDUCE_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    attr_done = true;
-  }
+  TP_CUDA(opt_in_smem<encode_reduce_kernel<TP_REDUCE_MAX>>(kSmem));
+  TP_CUDA(opt_in_smem<encode_reduce_kernel<TP_REDUCE_MEAN>>(kSmem));
+  TP_CUDA(opt_in_smem<encode_reduce_kernel<TP_REDUCE_SUM>>(kSmem));
   const int64_t ctas = (L.tiles_total + kGrab - 1) / kGrab;
   const int64_t cap = (int64_t)kSMs * kRedCtasPerSm;  // persistent: one resident wave
   const int grid = (int)(ctas < cap ? ctas : cap);

@@ -10,6 +10,7 @@
 // Feature maps are read channels-last [B, ncam, Hf, Wf, Cf] (tp_planes_nchw_to_nhwc_f32 with
 // batch = B * ncam converts the encoder's NCHW output): a tap is Cf contiguous floats, a warp reads
 // 512 contiguous bytes per instruction.
+#include "tp_cam.cuh"
 #include "tp_sample_dev.cuh"
 
 namespace tp {
@@ -36,27 +37,9 @@ struct LiftParams {
 template <int ARITH>
 __device__ __forceinline__ void lift_setup(const LiftParams& P, const float* __restrict__ cam, float px, float py,
                                            float pz, float4& w, int& off, int& mask) {
-  // einsum("cij,hj->chi"): sum_j M[i][j] * hom[j], fp32 fma chain in j order from 0
-  float c[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    float a = __fmaf_rn(__ldg(cam + 4 * i), px, 0.f);
-    a = __fmaf_rn(__ldg(cam + 4 * i + 1), py, a);
-    a = __fmaf_rn(__ldg(cam + 4 * i + 2), pz, a);
-    c[i] = __fmaf_rn(__ldg(cam + 4 * i + 3), 1.0f, a);
-  }
-  const float z = fmaxf(c[2], 1e-5f);  // torch.maximum(z, 1e-5) (NaN propagates below through the compares)
-  float x = __fdiv_rn(c[0], z), y = __fdiv_rn(c[1], z);
-  const float resize = __ldg(cam + 16), crop_x = __ldg(cam + 17), crop_y = __ldg(cam + 18);
-  const bool flip = __ldg(cam + 19) != 0.f;
-  x = __fsub_rn(__fmul_rn(x, resize), crop_x);
-  y = __fsub_rn(__fmul_rn(y, resize), crop_y);
-  if (flip) x = __fsub_rn(P.R1, x);
-  // "-= W/2, rotate by 0, += W/2" (:211-221): the rotation is the identity on finite values, the
-  // subtract/add pair is not (it rounds twice) and is replayed
-  x = __fadd_rn(__fsub_rn(x, P.half1), P.half1);
-  y = __fadd_rn(__fsub_rn(y, P.half0), P.half0);
-  const bool valid = (y < P.R0) & (x < P.R1) & (y >= 0.f) & (x >= 0.f) & !isnan(c[2]);
+  const CamPixel cp = cam_project(cam, px, py, pz, P.R0, P.R1, P.half0, P.half1);
+  const float x = cp.x, y = cp.y;
+  const bool valid = cp.valid;
   // swap to (row, col); normalise 2*row/H - 1, 2*col/W - 1 with H = R0, W = R1 (:229-233)
   float g0 = __fmul_rn(2.0f, y), g1 = __fmul_rn(2.0f, x);
   g0 = (ARITH == TP_ARITH_TORCH_CPU) ? __fdiv_rn(g0, P.R0) : __fmul_rn(g0, P.rcp0);

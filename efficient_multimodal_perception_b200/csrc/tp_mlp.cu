@@ -301,14 +301,8 @@ extern "C" int tp_mlp_head_tf32(const float* feats, int64_t Q, int32_t batch, in
   P.Q = (int)Q; P.ncls = num_classes;
   P.tiles_per_sample = (int)((Q + 127) / 128);
   P.tiles = P.tiles_per_sample * batch;
-  static bool opted_in[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !opted_in[dev]) {
-    TP_CUDA(cudaFuncSetAttribute(mlp_head_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMlpSmem));
-    TP_CUDA(cudaFuncSetAttribute(mlp_head_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMlpSmem));
-    if (dev >= 0 && dev < 64) opted_in[dev] = true;
-  }
+  TP_CUDA(opt_in_smem<mlp_head_kernel<true>>(kMlpSmem));
+  TP_CUDA(opt_in_smem<mlp_head_kernel<false>>(kMlpSmem));
   const int64_t cap = (int64_t)kSMs * 4;  // 128 of the 512 TMEM columns per CTA: 4 per SM
   const int grid = (int)(P.tiles < cap ? P.tiles : cap);
   const bool vec = (Q % 4 == 0) && (((uintptr_t)feats & 15) == 0);

@@ -12,8 +12,6 @@
 // are read once, as the algorithmic-bytes model says) and checks bit-for-bit that the block is
 // separable. A block that is not (jittered points, a permuted tensor, ...) falls back, inside the
 // same launch, to the per-query tile routine of tp_sample.cu.
-#include <cstdlib>
-
 #include "tp_sample_grid.cuh"
 
 namespace tp {
@@ -43,7 +41,7 @@ __device__ __noinline__ void grid_fallback(const GridParams& G, int b, int i0, i
 
 // Persistent CTAs: block n+1's queries are prefetched into L2 while block n is gathered and written,
 // so the only DRAM-latency-bound step of a block (reading its 12 B/query) is off the critical path.
-template <int ARITH, int C4T, int BI>
+template <int ARITH, int C4T, int BI, bool GEN>
 __global__ void __launch_bounds__(kGridThreads, kGridCtasPerSm)
 sample3_grid_kernel(const __grid_constant__ GridParams G) {
   using Cfg = GridCfg<BI>;
@@ -90,9 +88,9 @@ sample3_grid_kernel(const __grid_constant__ GridParams G) {
     const float* q00 = P.queries + ((int64_t)b * P.Q + ((int64_t)i0 * G.w + j0) * G.d + k0) * 3;  // block origin
 
     // ---- A: read the block's queries once; is x = x(i), y = y(j), z = z(k) bit for bit? --------
-    const bool ok = grid_block_is_lattice<BI>(G, q00, ni, nj, nk, wd, tid);
+    const bool ok = GEN ? true : grid_block_is_lattice<BI>(G, q00, ni, nj, nk, wd, tid);
     // ---- B: one bilinear footprint per table entry (index pair), from the representative queries -
-    const int live = grid_build_records<ARITH, BI>(G, q00, ni, nj, nk, wd, C4, s_w, s_om, tid);
+    const int live = grid_build_records<ARITH, BI, GEN>(G, q00, ni, nj, nk, wd, C4, s_w, s_om, tid, i0, j0, k0);
     grid_cast_vote(s_vote, nblk_done, live, ok, tid);
     __syncthreads();
     const int vote = s_vote[nblk_done & 1];
@@ -102,7 +100,7 @@ sample3_grid_kernel(const __grid_constant__ GridParams G) {
 
     // ---- prefetch the next block's queries (DRAM -> L2) behind this block's gathers and stores ---
     const int next = blk + gridDim.x;
-    if (next < nblocks) {
+    if (!GEN && next < nblocks) {
       const BlockPos np = block_pos<BI>(G, next);
       if (np.j0 + aj < G.w && np.k0 + ak < G.d) {
         const float* n00 = P.queries + ((int64_t)np.b * P.Q + ((int64_t)np.i0 * G.w + np.j0) * G.d + np.k0) * 3;
@@ -177,22 +175,12 @@ sample3_grid_kernel(const __grid_constant__ GridParams G) {
   GRID_G(2);
 }
 
-template <int ARITH, int C4T, int BI>
+template <int ARITH, int C4T, int BI, bool GEN>
 static void launch_grid(const GridParams& G, int batch, cudaStream_t s) {
-  // persistent CTAs (kGridCtasPerSm per SM); TP_GRID_CTAS (experiments) overrides the grid size
-  int64_t blocks = G.nblocks < kGridCtasPerSm * kSMs ? G.nblocks : kGridCtasPerSm * kSMs;
-  if (const char* e = getenv("TP_GRID_CTAS")) {
-    const int64_t v = atoll(e);
-    if (v > 0) blocks = v < G.nblocks ? v : G.nblocks;
-  }
-  auto kern = sample3_grid_kernel<ARITH, C4T, BI>;
-  static bool opted_in[64] = {};  // per device: > 48 KB of dynamic shared memory needs the opt-in once
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !opted_in[dev]) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GridCfg<BI>::kSmemBytes);
-    if (dev >= 0 && dev < 64) opted_in[dev] = true;
-  }
+  // persistent CTAs (kGridCtasPerSm per SM)
+  const int64_t blocks = G.nblocks < kGridCtasPerSm * kSMs ? G.nblocks : kGridCtasPerSm * kSMs;
+  auto kern = sample3_grid_kernel<ARITH, C4T, BI, GEN>;
+  opt_in_smem<sample3_grid_kernel<ARITH, C4T, BI, GEN>>(GridCfg<BI>::kSmemBytes);  // a failure surfaces at the launch check
   kern<<<(unsigned)blocks, kGridThreads, GridCfg<BI>::kSmemBytes, s>>>(G);
 }
 
@@ -200,20 +188,28 @@ static void launch_grid(const GridParams& G, int batch, cudaStream_t s) {
 
 using namespace tp;
 
-extern "C" int tp_sample3_grid_nhwc_f32(const tp_plane planes[3], int32_t C, const float* queries,
-                                        const int32_t dims[3], int32_t batch, const tp_sample_geom* sg,
-                                        int32_t arith, float* out, void* stream) {
+// queries == nullptr: generated lattice (lat_org / lat_step), no fallback to the per-query kernel
+static int grid_entry(const tp_plane planes[3], int32_t C, const float* queries, const float* lat_org,
+                      const float* lat_step, const int32_t dims[3], int32_t batch, const tp_sample_geom* sg,
+                      int32_t arith, float* out, void* stream) {
+  const bool gen = queries == nullptr;
   if (!dims) return fail(TP_E_NULL, "tp_sample3_grid_nhwc_f32: null dims");
   const int h = dims[0], w = dims[1], d = dims[2];
   if (h < 0 || w < 0 || d < 0) return fail(TP_E_SHAPE, "tp_sample3_grid_nhwc_f32: bad dims %d %d %d", h, w, d);
   const int64_t Q = (int64_t)h * w * d;
   // lattice path needs 16-byte aligned k-runs; anything else goes through the per-query kernel
-  if ((d & 3) || (reinterpret_cast<uintptr_t>(out) & 15) || arith == 2 || Q == 0 || Q * 3 >= ((int64_t)1 << 31))
+  if ((d & 3) || (reinterpret_cast<uintptr_t>(out) & 15) || arith == 2 || Q == 0 || Q * 3 >= ((int64_t)1 << 31)) {
+    if (gen) return Q == 0 ? 0 : fail(TP_E_SHAPE, "tp_sample3_lattice_nhwc_f32: needs d %% 4 == 0, a 16-byte aligned out and h*w*d*3 < 2^31 (got %d %d %d)", h, w, d);
     return tp_sample3_nhwc_f32(planes, C, queries, Q, batch, sg, arith, out, stream);
+  }
   if (C <= 0 || (C & 3)) return fail(TP_E_SHAPE, "tp_sample3_grid_nhwc_f32: C=%d must be a positive multiple of 4", C);
   if (batch <= 0) return fail(TP_E_SHAPE, "tp_sample3_grid_nhwc_f32: bad B=%d", batch);
-  if (!planes || !queries || !out || !sg) return fail(TP_E_NULL, "tp_sample3_grid_nhwc_f32: null argument");
+  if (!planes || !out || !sg || (gen && (!lat_org || !lat_step))) return fail(TP_E_NULL, "tp_sample3_grid_nhwc_f32: null argument");
   GridParams G;
+  for (int a = 0; a < 3; ++a) {
+    G.gen_org[a] = gen ? lat_org[a] : 0.f;
+    G.gen_step[a] = gen ? lat_step[a] : 0.f;
+  }
   SampleParams& P = G.S;
   for (int k = 0; k < 3; ++k) {
     if (!planes[k].data) return fail(TP_E_NULL, "tp_sample3_grid_nhwc_f32: plane %d is null", k);
@@ -245,20 +241,17 @@ extern "C" int tp_sample3_grid_nhwc_f32(const tp_plane planes[3], int32_t C, con
   // block shape BI x 8 x 16: the larger one shares each yz footprint between 8 lattice rows instead
   // of 4; the smaller one is for grids that would not give every resident CTA a block
   auto nblocks = [&](int bi) { return (int64_t)batch * ((h + bi - 1) / bi) * ((w + kBJ - 1) / kBJ) * G.nkb; };
-  int cfg = nblocks(8) >= kGridCtasPerSm * kSMs ? 0 : 1;
-  if (const char* e = getenv("TP_GRID_TILE")) {  // experiments only: 0 = 8x8x16, 1 = 4x8x16
-    const int v = atoi(e);
-    if (v >= 0 && v <= 1) cfg = v;
-  }
+  const int cfg = nblocks(8) >= kGridCtasPerSm * kSMs ? 0 : 1;
   const int bi = cfg == 0 ? 8 : 4;
   G.nib = (h + bi - 1) / bi;
   G.njb = (w + kBJ - 1) / kBJ;
   if (nblocks(bi) >= ((int64_t)1 << 30)) return fail(TP_E_SHAPE, "tp_sample3_grid_nhwc_f32: too many queries");
   G.nblocks = (int)nblocks(bi);
   cudaStream_t s = (cudaStream_t)stream;
-#define TP_GRID_B(A, C4T)                                             \
-  switch (cfg) { case 0: launch_grid<A, C4T, 8>(G, batch, s); break; \
-                 default: launch_grid<A, C4T, 4>(G, batch, s); break; }
+#define TP_GRID_G(A, C4T, BI) \
+  if (gen) launch_grid<A, C4T, BI, true>(G, batch, s); else launch_grid<A, C4T, BI, false>(G, batch, s);
+#define TP_GRID_B(A, C4T) \
+  switch (cfg) { case 0: TP_GRID_G(A, C4T, 8) break; default: TP_GRID_G(A, C4T, 4) break; }
 #define TP_GRID_C(A)                                                      \
   switch (C) { case 32: TP_GRID_B(A, 8) break; case 96: TP_GRID_B(A, 24) break; \
                case 128: TP_GRID_B(A, 32) break; default: TP_GRID_B(A, 0) break; }
@@ -269,8 +262,23 @@ extern "C" int tp_sample3_grid_nhwc_f32(const tp_plane planes[3], int32_t C, con
   }
 #undef TP_GRID_C
 #undef TP_GRID_B
+#undef TP_GRID_G
   TP_LAUNCH_CHECK("sample3_grid_kernel");
   return 0;
+}
+
+extern "C" int tp_sample3_grid_nhwc_f32(const tp_plane planes[3], int32_t C, const float* queries,
+                                        const int32_t dims[3], int32_t batch, const tp_sample_geom* sg,
+                                        int32_t arith, float* out, void* stream) {
+  if (!queries) return fail(TP_E_NULL, "tp_sample3_grid_nhwc_f32: null queries");
+  return grid_entry(planes, C, queries, nullptr, nullptr, dims, batch, sg, arith, out, stream);
+}
+
+extern "C" int tp_sample3_lattice_nhwc_f32(const tp_plane planes[3], int32_t C, const int32_t dims[3],
+                                           const float origin[3], const float step[3], int32_t batch,
+                                           const tp_sample_geom* sg, int32_t arith, float* out, void* stream) {
+  if (!origin || !step) return fail(TP_E_NULL, "tp_sample3_lattice_nhwc_f32: null lattice");
+  return grid_entry(planes, C, nullptr, origin, step, dims, batch, sg, arith, out, stream);
 }
 
 extern "C" int tp_sample3_grid_nchw_f32(const tp_plane planes_nchw[3], int32_t C, const float* queries,

@@ -11,7 +11,14 @@ struct GridParams {
   int nib, njb, nkb;  // blocks along h, w, d
   int nblocks;        // batch * nib * njb * nkb
   int vec_ok;
+  // generated lattice (tp_sample3_lattice_nhwc_f32): q_a(n) = (n + 0.5) * gen_step[a] + gen_org[a], S.queries == nullptr
+  float gen_org[3], gen_step[3];
 };
+
+// roi()'s voxel centres, op by op (triplane_occ.py:311-316: three separate fp32 tensor ops, never contracted)
+__device__ __forceinline__ float lattice_coord(const GridParams& G, int a, int n) {
+  return __fadd_rn(__fmul_rn(__fadd_rn((float)n, 0.5f), G.gen_step[a]), G.gen_org[a]);
+}
 
 #ifdef TP_GRID_TRACE  // tools/micro/grid_trace.cu: per-CTA timeline (not part of the library build)
 __device__ unsigned long long g_grid_cta[8 * 1024];
@@ -203,9 +210,12 @@ __device__ __forceinline__ bool grid_block_is_lattice(const GridParams& G, const
 // offset in float4 units, in-bounds mask. Returns this thread's "plane p has an in-bounds tap" bits.
 // (Measured: computing the 2 (BI + 8 + 16) distinct 1-D taps once and combining pairs saves ~half of this phase's
 // instructions but needs a barrier in between — same time on the 640k lattice, 2 % slower on 8 x roi.)
-template <int ARITH, int BI>
+// GEN: the representative coordinates are generated from the lattice indices (org = block origin {i0, j0, k0})
+// instead of being read from the query tensor.
+template <int ARITH, int BI, bool GEN = false>
 __device__ __forceinline__ int grid_build_records(const GridParams& G, const float* q00, int ni, int nj, int nk, int wd,
-                                                  int C4, float4* s_w, int2* s_om, int tid) {
+                                                  int C4, float4* s_w, int2* s_om, int tid, int gi0 = 0, int gj0 = 0,
+                                                  int gk0 = 0) {
   using Cfg = GridCfg<BI>;
   const SampleParams& P = G.S;
   int live = 0;
@@ -223,8 +233,16 @@ __device__ __forceinline__ int grid_build_records(const GridParams& G, const flo
     float4 wgt = make_float4(0.f, 0.f, 0.f, 0.f);
     int base = 0, mask = 0;
     if (e0i < n0 && e1i < n1) {
-      const float g0 = grid_coord<ARITH>(P, __ldg(q00 + e0i * s0 * 3 + a0), a0);
-      const float g1 = grid_coord<ARITH>(P, __ldg(q00 + e1i * s1 * 3 + a1), a1);
+      float c0, c1;
+      if (GEN) {  // axis 0 <-> i, 1 <-> j, 2 <-> k
+        c0 = lattice_coord(G, a0, (a0 == 0 ? gi0 : gj0) + e0i);
+        c1 = lattice_coord(G, a1, (a1 == 1 ? gj0 : gk0) + e1i);
+      } else {
+        c0 = __ldg(q00 + e0i * s0 * 3 + a0);
+        c1 = __ldg(q00 + e1i * s1 * 3 + a1);
+      }
+      const float g0 = grid_coord<ARITH>(P, c0, a0);
+      const float g1 = grid_coord<ARITH>(P, c1, a1);
       plane_setup<ARITH>(g0, g1, P.W[pl], P.H[pl], wgt, base, mask);
     }
     s_w[e] = wgt;

@@ -514,18 +514,12 @@ extern "C" int tp_sample3_grid_head_tf32(const tp_plane planes[3], const float* 
   static std::atomic<unsigned> launch_seq{0};
   HP.slot = (int)(launch_seq.fetch_add(1, std::memory_order_relaxed) % kHeadTicketSlots);
   HP.w1 = w1; HP.w2 = w2; HP.w3 = w3; HP.logits = logits; HP.ncls = num_classes;
-  static bool opted_in[64][2] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
   const int64_t cap = (int64_t)kHeadCtasPerSm * kSMs;
   const unsigned grid = (unsigned)(nb < cap ? nb : cap);
   cudaStream_t s = (cudaStream_t)stream;
   const int ai = arith == TP_ARITH_TORCH_CUDA ? 0 : 1;
-  if (dev < 0 || dev >= 64 || !opted_in[dev][ai]) {
-    if (ai == 0) TP_CUDA(cudaFuncSetAttribute(sample3_grid_head_kernel<TP_ARITH_TORCH_CUDA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem));
-    else TP_CUDA(cudaFuncSetAttribute(sample3_grid_head_kernel<TP_ARITH_TORCH_CPU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem));
-    if (dev >= 0 && dev < 64) opted_in[dev][ai] = true;
-  }
+  if (ai == 0) TP_CUDA(opt_in_smem<sample3_grid_head_kernel<TP_ARITH_TORCH_CUDA>>(kHeadSmem));
+  else TP_CUDA(opt_in_smem<sample3_grid_head_kernel<TP_ARITH_TORCH_CPU>>(kHeadSmem));
   if (ai == 0) sample3_grid_head_kernel<TP_ARITH_TORCH_CUDA><<<grid, kGridThreads, kHeadSmem, s>>>(HP);
   else sample3_grid_head_kernel<TP_ARITH_TORCH_CPU><<<grid, kGridThreads, kHeadSmem, s>>>(HP);
   TP_LAUNCH_CHECK("sample3_grid_head_kernel");

@@ -4,6 +4,7 @@ raise (never fall back) otherwise."""
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from typing import List, Optional, Sequence, Tuple, Union
 
 import torch
@@ -21,6 +22,32 @@ launch_count = 0
 
 def _stream(t: torch.Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _tensors(objs):
+    for o in objs:
+        if isinstance(o, torch.Tensor):
+            yield o
+        elif isinstance(o, (list, tuple)):
+            yield from _tensors(o)
+
+
+def _on_device(fn):
+    """Every wrapper hands raw pointers and the tensors' current stream to libtriplane, which launches on the
+    CURRENT device: make the tensors' device current for the call (model.to('cuda:1') without set_device,
+    several GPUs in one process) and refuse arguments spread over several devices."""
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        devs = {t.device for t in _tensors(list(args) + list(kwargs.values())) if t.is_cuda}
+        if len(devs) > 1:
+            raise TriplaneError(f"{fn.__name__}: tensor arguments live on several devices: {sorted(map(str, devs))}")
+        if not devs:
+            return fn(*args, **kwargs)  # the wrapper raises its own 'expected a CUDA tensor' error
+        with torch.cuda.device(next(iter(devs))):
+            return fn(*args, **kwargs)
+
+    return wrapped
 
 
 def _need_cuda(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
@@ -48,6 +75,7 @@ def pooled_sizes(grid_size, pool) -> Tuple[int, int, int]:
 # ------------------------------------------------------------------------------------------------
 # a1
 # ------------------------------------------------------------------------------------------------
+@_on_device
 def voxelize(points: torch.Tensor, offsets: torch.Tensor, pc_range, voxel_size, grid_size=(1, 1, 1),
              ncols: Optional[int] = None, arith: str = "cuda"):
     """points [N, D] (samples concatenated), offsets [B+1] int64 ->
@@ -77,6 +105,7 @@ def voxelize(points: torch.Tensor, offsets: torch.Tensor, pc_range, voxel_size, 
     return out_pts[:n_kept], out_idx[:n_kept], out_off
 
 
+@_on_device
 def voxel_index(points: torch.Tensor, pc_range, voxel_size, arith: str = "cuda"):
     """Uncompacted crop mask [N] (uint8) and int32 voxel index [N,3] for every raw point."""
     global launch_count
@@ -96,13 +125,27 @@ def voxel_index(points: torch.Tensor, pc_range, voxel_size, arith: str = "cuda")
 # a3
 # ------------------------------------------------------------------------------------------------
 class _EncodeWorkspace:
-    """Per (device, geometry, batch) scratch whose tile counters are left zero by every call."""
+    """Per (device, stream, geometry, batch) scratch whose tile counters are left zero by every successful call.
+    Keyed by stream: two encodes of one geometry on different streams must not share counters / CSR lists. An
+    entry is evicted when its call fails (the counters may be dirty), see encode()."""
     cache = {}
+
+    @classmethod
+    def clear(cls) -> None:
+        cls.cache.clear()
+
+    @classmethod
+    def evict(cls, k) -> None:
+        cls.cache.pop(k, None)
+
+    @classmethod
+    def key(cls, device, stream: int, key, batch: int):
+        return (device.index, stream, key, batch)
 
     @classmethod
     def get(cls, device, geom: L.tp_geom, key, batch: int, n: int, stream: int) -> Tuple[torch.Tensor, int]:
         lib = L.lib()
-        k = (device.index, key, batch)
+        k = cls.key(device, stream, key, batch)
         need = lib.tp_encode_workspace_bytes(C.byref(geom), batch, n)
         if need < 0:
             raise TriplaneError("tp_encode_workspace_bytes: bad geometry")
@@ -117,6 +160,7 @@ class _EncodeWorkspace:
         return ent[0], ent[2]
 
 
+@_on_device
 def encode(feats: torch.Tensor, offsets: torch.Tensor, pc_range, voxel_size, grid_size, split, *,
            grid_ind: Optional[torch.Tensor] = None, points: Optional[torch.Tensor] = None,
            reduce: str = "max", clamp_zero: bool = False, want_counts: bool = False, arith: str = "cuda",
@@ -161,15 +205,26 @@ def encode(feats: torch.Tensor, offsets: torch.Tensor, pc_range, voxel_size, gri
     if want_counts:
         ncell = batch * (X * Y * P[2] + Y * Z * P[0] + X * Z * P[1])
         counts = torch.zeros(ncell, dtype=torch.int32, device=dev)
-    L.check(L.lib().tp_encode_f32(feats.data_ptr(), feats.stride(0), Cch, _ptr(grid_ind), _ptr(points),
-                                  0 if points is None else points.shape[1], n, offsets.data_ptr(), batch,
-                                  C.byref(geom), _ARITH[arith], _REDUCE[reduce], int(bool(clamp_zero)),
-                                  _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(counts),
-                                  ws.data_ptr(), ws_bytes, stream), "tp_encode_f32")
+    try:
+        L.check(L.lib().tp_encode_f32(feats.data_ptr(), feats.stride(0), Cch, _ptr(grid_ind), _ptr(points),
+                                      0 if points is None else points.shape[1], n, offsets.data_ptr(), batch,
+                                      C.byref(geom), _ARITH[arith], _REDUCE[reduce], int(bool(clamp_zero)),
+                                      _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(counts),
+                                      ws.data_ptr(), ws_bytes, stream), "tp_encode_f32")
+    except BaseException:
+        # a failure between the passes can leave tile counters non-zero: never reuse this workspace
+        _EncodeWorkspace.evict(_EncodeWorkspace.key(dev, stream, key, batch))
+        raise
     launch_count += 4 if n else 1
     return (outs[0], outs[1], outs[2], counts) if want_counts else (outs[0], outs[1], outs[2])
 
 
+def clear_workspaces() -> None:
+    """Drop every cached encode workspace (frees the device memory once in-flight work has finished)."""
+    _EncodeWorkspace.clear()
+
+
+@_on_device
 def finalize_mean(planes: torch.Tensor, counts: torch.Tensor, channels: int) -> torch.Tensor:
     """In place: planes[cell, :] /= max(count[cell], 1) — after a point-sharded SUM all-reduce."""
     global launch_count
@@ -184,6 +239,7 @@ def finalize_mean(planes: torch.Tensor, counts: torch.Tensor, channels: int) -> 
     return planes
 
 
+@_on_device
 def finalize_max(planes: torch.Tensor, clamp_zero: bool = False) -> torch.Tensor:
     """In place: -inf -> 0 after the all-reduce(max) of reduce='max_partial' planes."""
     global launch_count
@@ -196,6 +252,7 @@ def finalize_max(planes: torch.Tensor, clamp_zero: bool = False) -> torch.Tensor
     return planes
 
 
+@_on_device
 def voxel_counts(grid_ind: torch.Tensor, offsets: torch.Tensor, grid_size) -> torch.Tensor:
     """Dense [B,X,Y,Z] int32 histogram of points per voxel (unq_cnt of projector.py:99, densified)."""
     global launch_count
@@ -224,6 +281,7 @@ def _plane_array(planes: Sequence[torch.Tensor]):
     return arr
 
 
+@_on_device
 def planes_to_channels_last(planes: Sequence[torch.Tensor]) -> List[torch.Tensor]:
     """NCHW planes (the reference layout; views of the stacked [B,3,C,H,W] are fine) -> contiguous
     channels-last [B,H,W,C] copies for the gather kernel."""
@@ -259,6 +317,7 @@ def _check_out(out, B, Cc, Q, device):
     return out
 
 
+@_on_device
 def sample3(planes: Union[torch.Tensor, Sequence[torch.Tensor]], queries: torch.Tensor, lo, vs, half, *,
             arith: str = "cuda", channels_last: bool = False, out: Optional[torch.Tensor] = None,
             grid_dims: Optional[Sequence[int]] = None) -> torch.Tensor:
@@ -363,6 +422,7 @@ def pack_cameras(img_metas, device) -> torch.Tensor:
     return torch.from_numpy(np.stack(rows)).to(device, non_blocking=True)
 
 
+@_on_device
 def features_to_channels_last(img_features: torch.Tensor) -> torch.Tensor:
     """[B, ncam, Cf, Hf, Wf] (camera encoder output) -> contiguous [B, ncam, Hf, Wf, Cf]."""
     global launch_count
@@ -378,6 +438,7 @@ def features_to_channels_last(img_features: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_on_device
 def lift_cam(points: torch.Tensor, offsets: torch.Tensor, img_features: torch.Tensor, cams: torch.Tensor,
              resize_dims, *, arith: str = "cuda", channels_last: bool = False) -> torch.Tensor:
     """Fused point_to_cam (point_triplane.py:164-241): points [N, >=3] (samples concatenated, offsets
@@ -408,6 +469,7 @@ def lift_cam(points: torch.Tensor, offsets: torch.Tensor, img_features: torch.Te
 # ------------------------------------------------------------------------------------------------
 # backward (SURVEY 8f #1)
 # ------------------------------------------------------------------------------------------------
+@_on_device
 def channels_last_to_nchw(x: torch.Tensor) -> torch.Tensor:
     """[N, H, W, C] -> contiguous [N, C, H, W] (the transpose kernel with the roles of C and H*W swapped)."""
     global launch_count
@@ -422,6 +484,7 @@ def channels_last_to_nchw(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_on_device
 def sample3_backward(grad_out: torch.Tensor, queries: torch.Tensor, plane_shapes, lo, vs, half, *,
                      arith: str = "cuda", grid_dims: Optional[Sequence[int]] = None) -> List[torch.Tensor]:
     """Gradient of sample3 w.r.t. the three planes. grad_out [B,C,Q], queries [B,Q,3], plane_shapes = three
@@ -454,6 +517,7 @@ def sample3_backward(grad_out: torch.Tensor, queries: torch.Tensor, plane_shapes
     return [channels_last_to_nchw(g) for g in g_nhwc]
 
 
+@_on_device
 def encode_backward(grads, feats: Optional[torch.Tensor], grid_ind: torch.Tensor, offsets: torch.Tensor, grid_size,
                     split, *, outs=None, counts: Optional[torch.Tensor] = None, reduce: str = "max",
                     clamp_zero: bool = False, channels: Optional[int] = None) -> torch.Tensor:
@@ -482,6 +546,7 @@ def encode_backward(grads, feats: Optional[torch.Tensor], grid_ind: torch.Tensor
     return gf
 
 
+@_on_device
 def lift_cam_backward(grad_out: torch.Tensor, points: torch.Tensor, offsets: torch.Tensor, feat_shape, cams,
                       resize_dims, *, arith: str = "cuda") -> torch.Tensor:
     """Gradient of lift_cam w.r.t. img_features: grad_out [N,Cf] -> [B,ncam,Cf,Hf,Wf]."""
@@ -502,6 +567,7 @@ def lift_cam_backward(grad_out: torch.Tensor, points: torch.Tensor, offsets: tor
 # ------------------------------------------------------------------------------------------------
 # occupancy head
 # ------------------------------------------------------------------------------------------------
+@_on_device
 def sample3_head(planes, queries: torch.Tensor, lo, vs, half, w1: torch.Tensor, w2: torch.Tensor, w3: torch.Tensor, *,
                  grid_dims: Sequence[int], arith: str = "cuda", channels_last: bool = False) -> torch.Tensor:
     """TriplaneOcc's decode + occupancy head in one kernel (triplane_occ.py:182-186 after :321-348): the [B,32,Q]
@@ -545,6 +611,7 @@ def sample3_head(planes, queries: torch.Tensor, lo, vs, half, w1: torch.Tensor, 
     return out
 
 
+@_on_device
 def mlp_head(feats: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor, w3: torch.Tensor) -> torch.Tensor:
     """The reference's Mlp head (dense_heads/mlp.py:57-70) on decode output: feats [B, C, Q] (or [B,C,X,Y,Z]),
     Conv3d weights w1 [2C,C,1,1,1], w2 [C,2C,1,1,1], w3 [ncls,C,1,1,1] (or already 2-D) -> logits [B, ncls, ...].
@@ -567,3 +634,302 @@ def mlp_head(feats: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor, w3: torch.
                                      out.data_ptr(), _stream(f)), "tp_mlp_head_tf32")
     launch_count += 1 if Q else 0
     return out.view(B, ncls, *shape[2:])
+
+
+# ------------------------------------------------------------------------------------------------
+# a4, ragged subsets and generated lattices
+# ------------------------------------------------------------------------------------------------
+def _nhwc_planes(planes, B: Optional[int], channels_last: bool, who: str):
+    """-> (list of contiguous [B,H,W,C] planes, tp_plane array)"""
+    if isinstance(planes, torch.Tensor):
+        if planes.dim() != 5 or planes.shape[1] != 3:
+            raise TriplaneError(f"{who}: stacked triplane must be [B,3,C,H,W], got {tuple(planes.shape)}")
+        planes = [planes[:, 0], planes[:, 1], planes[:, 2]]
+    if len(planes) != 3:
+        raise TriplaneError(f"{who}: expected three planes")
+    nhwc = list(planes) if channels_last else planes_to_channels_last(planes)
+    Cc = nhwc[0].shape[-1]
+    arr = (L.tp_plane * 3)()
+    for k, p in enumerate(nhwc):
+        _need_cuda(p, f"plane {k}")
+        if (B is not None and p.shape[0] != B) or p.shape[-1] != Cc or p.dim() != 4 or not p.is_contiguous():
+            raise TriplaneError(f"{who}: plane {k}: expected contiguous [B,H,W,C={Cc}], got {tuple(p.shape)}")
+        arr[k].data = p.data_ptr()
+        arr[k].batch_stride = p.stride(0)
+        arr[k].H, arr[k].W = p.shape[1], p.shape[2]
+    return nhwc, arr
+
+
+@_on_device
+def sample3_lattice(planes, dims: Sequence[int], origin, step, lo, vs, half, *, arith: str = "cuda",
+                    channels_last: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """sample3 on roi()'s voxel-centre lattice ((i, j, k) + 0.5) * step + origin (triplane_occ.py:311-316) without the
+    [B,h,w,d,3] tensor: the coordinates are generated in the kernel. Returns [B, C, h*w*d], bit-identical to
+    sample3(planes, roi_points, grid_dims=dims)."""
+    global launch_count
+    nhwc, arr = _nhwc_planes(planes, None, channels_last, "sample3_lattice")
+    B, Cc = nhwc[0].shape[0], nhwc[0].shape[-1]
+    h, w, d = (int(v) for v in dims)
+    Q = h * w * d
+    out = _check_out(out, B, Cc, Q, nhwc[0].device)
+    sg = L.make_sample_geom(lo, vs, half)
+    cd = (C.c_int32 * 3)(h, w, d)
+    org = (C.c_float * 3)(*[float(v) for v in origin[:3]])
+    stp = (C.c_float * 3)(*[float(v) for v in step[:3]])
+    L.check(L.lib().tp_sample3_lattice_nhwc_f32(C.byref(arr), Cc, C.byref(cd), C.byref(org), C.byref(stp), B, C.byref(sg),
+                                                _ARITH[arith], out.data_ptr(), _stream(nhwc[0])), "tp_sample3_lattice_nhwc_f32")
+    launch_count += 1 if Q else 0
+    return out
+
+
+@_on_device
+def sample3_segments(planes, queries: torch.Tensor, seg_offsets: torch.Tensor, seg_batch: Optional[torch.Tensor], lo, vs,
+                     half, *, arith: str = "cuda", channels_last: bool = False) -> torch.Tensor:
+    """Ragged subsets in one launch: queries [T,3] (segments concatenated), seg_offsets [S+1] int64, seg_batch [S] int32
+    (None: segment s reads sample s) -> point-major [T, C]."""
+    global launch_count
+    _need_cuda(queries, "queries")
+    _need_cuda(seg_offsets, "seg_offsets", torch.int64)
+    if seg_batch is not None:
+        _need_cuda(seg_batch, "seg_batch", torch.int32)
+        seg_batch = seg_batch.contiguous()
+    if queries.dim() != 2 or queries.shape[1] != 3:
+        raise TriplaneError(f"queries must be [T,3], got {tuple(queries.shape)}")
+    queries, seg_offsets = queries.contiguous(), seg_offsets.contiguous()
+    nseg = seg_offsets.numel() - 1
+    if nseg < 1 or (seg_batch is not None and seg_batch.numel() != nseg):
+        raise TriplaneError("sample3_segments: seg_offsets must be [S+1] with S >= 1 and seg_batch [S]")
+    nhwc, arr = _nhwc_planes(planes, None, channels_last, "sample3_segments")
+    B, Cc = nhwc[0].shape[0], nhwc[0].shape[-1]
+    T = queries.shape[0]
+    out = torch.empty((T, Cc), dtype=torch.float32, device=queries.device)
+    sg = L.make_sample_geom(lo, vs, half)
+    L.check(L.lib().tp_sample3_seg_nhwc_f32(C.byref(arr), Cc, queries.data_ptr(), T, seg_offsets.data_ptr(), _ptr(seg_batch),
+                                            nseg, B, C.byref(sg), _ARITH[arith], out.data_ptr(), _stream(queries)),
+            "tp_sample3_seg_nhwc_f32")
+    launch_count += 1 if T else 0
+    return out
+
+
+@_on_device
+def sample3_segments_backward(grad_out: torch.Tensor, queries: torch.Tensor, seg_offsets: torch.Tensor,
+                              seg_batch: Optional[torch.Tensor], batch: int, plane_shapes, lo, vs, half, *,
+                              arith: str = "cuda") -> List[torch.Tensor]:
+    """Gradient of sample3_segments w.r.t. the three planes: grad_out [T,C] -> three NCHW gradients [B,C,H,W]."""
+    global launch_count
+    _need_cuda(grad_out, "grad_out")
+    grad_out, queries = grad_out.contiguous(), queries.contiguous()
+    T, Cc = grad_out.shape
+    g_nhwc = [torch.zeros((batch, H, W, Cc), dtype=torch.float32, device=grad_out.device) for H, W in plane_shapes]
+    arr = (L.tp_plane * 3)()
+    for k, p in enumerate(g_nhwc):
+        arr[k].data = p.data_ptr()
+        arr[k].batch_stride = p.stride(0)
+        arr[k].H, arr[k].W = p.shape[1], p.shape[2]
+    sg = L.make_sample_geom(lo, vs, half)
+    nseg = seg_offsets.numel() - 1
+    L.check(L.lib().tp_sample3_seg_backward_nhwc_f32(C.byref(arr), Cc, queries.data_ptr(), T, seg_offsets.data_ptr(),
+                                                     _ptr(seg_batch), nseg, batch, C.byref(sg), _ARITH[arith],
+                                                     grad_out.data_ptr(), _stream(grad_out)), "tp_sample3_seg_backward_nhwc_f32")
+    launch_count += 1 if T else 0
+    return [channels_last_to_nchw(g) for g in g_nhwc]
+
+
+# ------------------------------------------------------------------------------------------------
+# 8f #4: nearest-pixel gathers / scatters around the decode
+# ------------------------------------------------------------------------------------------------
+@_on_device
+def pixel_winner_from_coors(coors: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """coors [..., npix, 2] fp32 (row, col; range_cam_coors of JointEncoder.interact, leading dims = images) ->
+    winner [n_images, H, W] int32: the highest source pixel whose long() coordinates land there (-1: none)."""
+    global launch_count
+    _need_cuda(coors, "coors")
+    if coors.dim() < 2 or coors.shape[-1] != 2:
+        raise TriplaneError(f"coors must be [..., npix, 2], got {tuple(coors.shape)}")
+    coors = coors.contiguous()
+    npix = coors.shape[-2]
+    M = coors.numel() // (2 * npix) if npix else 0
+    winner = torch.empty((M, H, W), dtype=torch.int32, device=coors.device)
+    L.check(L.lib().tp_pixel_winner_coors_i32(coors.data_ptr(), M, npix, H, W, winner.data_ptr(), _stream(coors)),
+            "tp_pixel_winner_coors_i32")
+    launch_count += 1
+    return winner
+
+
+@_on_device
+def pixel_winner_from_points(points: torch.Tensor, offsets: torch.Tensor, cams: torch.Tensor, resize_dims) -> torch.Tensor:
+    """points [N, >=3] (samples concatenated, offsets [B+1]), cams [B,ncam,20] -> winner [B*ncam, R0, R1] int32 holding
+    the in-sample index of the last point projected onto each pixel (point_triplane.py:263-307)."""
+    global launch_count
+    _need_cuda(points, "points")
+    _need_cuda(offsets, "offsets", torch.int64)
+    _need_cuda(cams, "cams")
+    points, cams = points.contiguous(), cams.contiguous()
+    B, ncam = cams.shape[0], cams.shape[1]
+    H, W = int(resize_dims[0]), int(resize_dims[1])
+    winner = torch.empty((B * ncam, H, W), dtype=torch.int32, device=points.device)
+    L.check(L.lib().tp_pixel_winner_points_i32(points.data_ptr(), points.shape[1], points.shape[0], offsets.data_ptr(), B,
+                                               cams.data_ptr(), ncam, float(resize_dims[0]), float(resize_dims[1]),
+                                               winner.data_ptr(), _stream(points)), "tp_pixel_winner_points_i32")
+    launch_count += 1
+    return winner
+
+
+def _feat_addressing(feat: torch.Tensor, layout: str):
+    """-> (C, batch stride, channel stride, source stride) of a contiguous feature tensor."""
+    if layout == "bcn":  # [Bf, C, N] channel-major decode output
+        if feat.dim() != 3:
+            raise TriplaneError(f"feat must be [B,C,N], got {tuple(feat.shape)}")
+        return feat.shape[1], feat.shape[1] * feat.shape[2], feat.shape[2], 1
+    if layout == "nc":   # [N, C] point-major rows, per-sample first rows given separately
+        if feat.dim() != 2:
+            raise TriplaneError(f"feat must be [N,C], got {tuple(feat.shape)}")
+        return feat.shape[1], 0, 1, feat.shape[1]
+    raise TriplaneError(f"unknown feature layout {layout!r}")
+
+
+@_on_device
+def winner_gather(winner: torch.Tensor, feat: torch.Tensor, imgs_per_feat: int, *, layout: str = "bcn",
+                  row0: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out [M, C, H, W] = feat[m // imgs_per_feat][:, winner[m]] (zeros where winner < 0). layout 'bcn': feat
+    [Bf, C, N]; 'nc': feat [N, C] with row0 [Bf+1] int64 = first row of each sample."""
+    global launch_count
+    _need_cuda(winner, "winner", torch.int32)
+    _need_cuda(feat, "feat")
+    winner, feat = winner.contiguous(), feat.contiguous()
+    M, H, W = winner.shape
+    Cc, bs, cs, ns = _feat_addressing(feat, layout)
+    if row0 is not None:
+        _need_cuda(row0, "row0", torch.int64)
+    out = torch.empty((M, Cc, H, W), dtype=torch.float32, device=feat.device)
+    L.check(L.lib().tp_winner_gather_f32(winner.data_ptr(), M, H * W, Cc, imgs_per_feat, feat.data_ptr(), bs, cs, ns,
+                                         _ptr(row0), out.data_ptr(), _stream(feat)), "tp_winner_gather_f32")
+    launch_count += 1 if M else 0
+    return out
+
+
+@_on_device
+def winner_gather_backward(winner: torch.Tensor, grad_out: torch.Tensor, feat_shape, imgs_per_feat: int, *,
+                           layout: str = "bcn", row0: Optional[torch.Tensor] = None) -> torch.Tensor:
+    global launch_count
+    grad_out, winner = grad_out.contiguous(), winner.contiguous()
+    M, H, W = winner.shape
+    gfeat = torch.zeros(tuple(feat_shape), dtype=torch.float32, device=grad_out.device)
+    Cc, bs, cs, ns = _feat_addressing(gfeat, layout)
+    L.check(L.lib().tp_winner_gather_backward_f32(winner.data_ptr(), M, H * W, Cc, imgs_per_feat, grad_out.data_ptr(),
+                                                  gfeat.data_ptr(), bs, cs, ns, _ptr(row0), _stream(grad_out)),
+            "tp_winner_gather_backward_f32")
+    launch_count += 1 if M else 0
+    return gfeat
+
+
+@_on_device
+def range_project(range_points: torch.Tensor, range_image: torch.Tensor, cams: torch.Tensor, resize_dims, feat_hw, *,
+                  arith: str = "cuda"):
+    """JointEncoder.interact's projection (joint_encoder.py:125-205): range_points [B,Hr,Wr,3], range_image
+    [B,1,Hr,Wr] (masked), cams [B,ncam,20] -> (range_cam_coors [B,ncam,Hr,Wr,2], fidx [B,ncam,Hr*Wr] int32, winner
+    [B*ncam, Hf*Wf] int32)."""
+    global launch_count
+    _need_cuda(range_points, "range_points")
+    _need_cuda(range_image, "range_image")
+    _need_cuda(cams, "cams")
+    B, Hr, Wr, _ = range_points.shape
+    range_points, range_image, cams = range_points.contiguous(), range_image.contiguous(), cams.contiguous()
+    if range_image.numel() != B * Hr * Wr:
+        raise TriplaneError(f"range_image {tuple(range_image.shape)} does not match range_points {tuple(range_points.shape)}")
+    ncam = cams.shape[1]
+    Hf, Wf = int(feat_hw[0]), int(feat_hw[1])
+    npix = Hr * Wr
+    dev = range_points.device
+    coors = torch.empty((B, ncam, Hr, Wr, 2), dtype=torch.float32, device=dev)
+    fidx = torch.empty((B, ncam, npix), dtype=torch.int32, device=dev)
+    winner = torch.empty((B * ncam, Hf * Wf), dtype=torch.int32, device=dev)
+    L.check(L.lib().tp_range_project_f32(range_points.data_ptr(), range_image.data_ptr(), npix, B, cams.data_ptr(), ncam,
+                                         float(resize_dims[0]), float(resize_dims[1]), Hf, Wf, _ARITH[arith],
+                                         coors.data_ptr(), fidx.data_ptr(), winner.data_ptr(), _stream(range_points)),
+            "tp_range_project_f32")
+    launch_count += 1
+    return coors, fidx, winner
+
+
+@_on_device
+def range_gather(fidx: torch.Tensor, img_features: torch.Tensor) -> torch.Tensor:
+    """cam_range_features [B, C, npix] = sum over cameras of img_features[b, cam, :, fidx] (joint_encoder.py:208)."""
+    global launch_count
+    _need_cuda(fidx, "fidx", torch.int32)
+    _need_cuda(img_features, "img_features")
+    B, ncam, Cc, Hf, Wf = img_features.shape
+    img_features = img_features.contiguous()
+    npix = fidx.shape[-1]
+    out = torch.empty((B, Cc, npix), dtype=torch.float32, device=img_features.device)
+    L.check(L.lib().tp_range_gather_f32(fidx.contiguous().data_ptr(), npix, B, ncam, img_features.data_ptr(), Cc, Hf * Wf,
+                                        out.data_ptr(), _stream(img_features)), "tp_range_gather_f32")
+    launch_count += 1 if npix else 0
+    return out
+
+
+@_on_device
+def range_gather_backward(fidx: torch.Tensor, grad_out: torch.Tensor, img_shape) -> torch.Tensor:
+    global launch_count
+    B, ncam, Cc, Hf, Wf = img_shape
+    grad_out = grad_out.contiguous()
+    g = torch.zeros(tuple(img_shape), dtype=torch.float32, device=grad_out.device)
+    npix = fidx.shape[-1]
+    L.check(L.lib().tp_range_gather_backward_f32(fidx.contiguous().data_ptr(), npix, B, ncam, grad_out.data_ptr(), Cc, Hf * Wf,
+                                                 g.data_ptr(), _stream(grad_out)), "tp_range_gather_backward_f32")
+    launch_count += 1 if npix else 0
+    return g
+
+
+@_on_device
+def posembed_scatter_(img_features: torch.Tensor, winner: torch.Tensor, pos_embed: torch.Tensor) -> torch.Tensor:
+    """In place: img_features [B,ncam,C,Hf,Wf][m, :, p] += pos_embed [M, Hf*Wf, C][m, p, :] where winner [M, Hf*Wf] >= 0."""
+    global launch_count
+    _need_cuda(img_features, "img_features")
+    _need_cuda(pos_embed, "pos_embed")
+    _need_cuda(winner, "winner", torch.int32)
+    if not img_features.is_contiguous():
+        raise TriplaneError("posembed_scatter_: img_features must be contiguous (it is updated in place)")
+    B, ncam, Cc, Hf, Wf = img_features.shape
+    pos_embed = pos_embed.contiguous()
+    L.check(L.lib().tp_posembed_scatter_f32(winner.contiguous().data_ptr(), B * ncam, Cc, Hf * Wf, img_features.data_ptr(),
+                                            pos_embed.data_ptr(), _stream(img_features)), "tp_posembed_scatter_f32")
+    launch_count += 1
+    return img_features
+
+
+@_on_device
+def posembed_scatter_backward(grad_img: torch.Tensor, winner: torch.Tensor) -> torch.Tensor:
+    global launch_count
+    B, ncam, Cc, Hf, Wf = grad_img.shape
+    grad_img = grad_img.contiguous()
+    g = torch.empty((B * ncam, Hf * Wf, Cc), dtype=torch.float32, device=grad_img.device)
+    L.check(L.lib().tp_posembed_scatter_backward_f32(winner.contiguous().data_ptr(), B * ncam, Cc, Hf * Wf, grad_img.data_ptr(),
+                                                     g.data_ptr(), _stream(grad_img)), "tp_posembed_scatter_backward_f32")
+    launch_count += 1
+    return g
+
+
+@_on_device
+def radius(x: torch.Tensor, x_offsets: torch.Tensor, y: torch.Tensor, y_offsets: torch.Tensor, r: float,
+           max_num_neighbors: int = 32):
+    """torch_cluster.radius semantics (interpnet.py:65): for every query y, the first max_num_neighbors sources x of the
+    same sample (index order) with squared distance < r^2. Returns (col [Ny, max] int32 with -1 padding, count [Ny])."""
+    global launch_count
+    _need_cuda(x, "x")
+    _need_cuda(y, "y")
+    _need_cuda(x_offsets, "x_offsets", torch.int64)
+    _need_cuda(y_offsets, "y_offsets", torch.int64)
+    x, y = x.contiguous(), y.contiguous()
+    if x.dim() != 2 or x.shape[1] != 3 or y.dim() != 2 or y.shape[1] != 3:
+        raise TriplaneError("radius: x and y must be [N,3]")
+    ny = y.shape[0]
+    B = y_offsets.numel() - 1
+    if x_offsets.numel() != B + 1:
+        raise TriplaneError("radius: x_offsets and y_offsets must describe the same number of samples")
+    col = torch.empty((ny, max_num_neighbors), dtype=torch.int32, device=y.device)
+    cnt = torch.empty((ny,), dtype=torch.int32, device=y.device)
+    L.check(L.lib().tp_radius_i32(x.data_ptr(), x_offsets.data_ptr(), y.data_ptr(), y_offsets.data_ptr(), ny, B, float(r),
+                                  int(max_num_neighbors), col.data_ptr(), cnt.data_ptr(), _stream(y)), "tp_radius_i32")
+    launch_count += 1 if ny else 0
+    return col, cnt

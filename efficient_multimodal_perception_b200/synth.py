@@ -141,12 +141,14 @@ def range_image_points(batch: int = 8, seed: int = 1003) -> torch.Tensor:
 class CameraRig:
     lidar2image: torch.Tensor  # [6, 4, 4]
     imgs_aug: list            # per camera dict(resize, crop, flip)
-    img_shape: Tuple[int, int]  # (H, W) after augmentation: (256, 512)
+    img_shape: Tuple[int, int]  # PIL size (W, H) after augmentation = (512, 256), as transforms_3d.py:169 stores it
 
 
 def camera_rig(seed: int = 1004) -> CameraRig:
     """Six pinhole cameras at 60-degree yaw steps; 1600x900 images resized by 0.525 and cropped to
-    256x512 with (164, 216) (transforms_3d.py:69-77), no flip."""
+    256x512 with (164, 216) (transforms_3d.py:69-77), no flip. img_shape is PIL's (W, H) = (512, 256)
+    (`data["img_shape"] = new_imgs[0].size`, transforms_3d.py:169), so the reference's
+    `resize_dims = img_shape[::-1]` is (H, W) = (256, 512)."""
     g = _gen(seed)
     fx = fy = 1266.0
     cx, cy = 816.0, 491.0
@@ -165,7 +167,7 @@ def camera_rig(seed: int = 1004) -> CameraRig:
         T[:3, 3] = t
         mats.append(K @ T)
     augs = [dict(resize=0.525, crop=(164, 216), flip=False) for _ in range(6)]
-    return CameraRig(torch.stack(mats), augs, (256, 512))
+    return CameraRig(torch.stack(mats), augs, (512, 256))
 
 
 def batch_offsets(sizes: Sequence[int]) -> torch.Tensor:

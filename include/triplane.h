@@ -199,6 +199,31 @@ TP_API int tp_sample3_grid_nchw_f32(const tp_plane planes_nchw[3], int32_t C,
                              float* out, float* nhwc_workspace, int64_t nhwc_workspace_floats,
                              void* stream);
 
+/* The same decode for the reference's regular query grids WITHOUT a query tensor: roi() (triplane_occ.py:291-318,
+ * point_triplane_occ.py:378-405) builds ref_3d[i,j,k] = ((i, j, k) + 0.5) * voxel_size + occ_range[0:3] once and
+ * `.repeat`s it per batch every step (triplane_occ.py:153,249). Here the coordinates are generated in the kernel by the
+ * same three fp32 operations (add 0.5, multiply, add; never contracted), so the 12 bytes per query are not read:
+ * bit-identical to tp_sample3_grid_nhwc_f32 on the materialised tensor. dims = {h, w, d}, d % 4 == 0, out 16-byte aligned
+ * (else TP_E_SHAPE: materialise the points and use the entry point above). */
+TP_API int tp_sample3_lattice_nhwc_f32(const tp_plane planes_nhwc[3], int32_t C, const int32_t dims[3],
+                                const float origin[3], const float step[3], int32_t batch,
+                                const tp_sample_geom* sg, int32_t arith, float* out, void* stream);
+
+/* Ragged point subsets in ONE launch: the per-(sample, camera) loops around sample_points_triplane in the contrastive
+ * branches (triplane.py:438-458: B x 6 SAM-labelled subsets; point_triplane.py:365-372, 389-403). queries [T, 3] = the
+ * segments concatenated; seg_offsets [S+1] int64 (device); seg_batch [S] int32 (device; NULL: segment s reads sample
+ * s) names the sample whose planes a segment reads (out of range: the segment yields zeros). out [T, C] is POINT-major:
+ * every caller turns the reference's [1,C,1,N] result into [N, C] rows (`features.permute(1, 0)`, triplane.py:453-455).
+ * Values are bit-identical to tp_sample3_nhwc_f32. The backward scatters grad_out [T, C] into ZEROED channels-last
+ * gradient planes, like tp_sample3_backward_nhwc_f32. */
+TP_API int tp_sample3_seg_nhwc_f32(const tp_plane planes_nhwc[3], int32_t C, const float* queries, int64_t total,
+                            const int64_t* seg_offsets, const int32_t* seg_batch, int32_t num_segments,
+                            int32_t batch, const tp_sample_geom* sg, int32_t arith, float* out, void* stream);
+TP_API int tp_sample3_seg_backward_nhwc_f32(const tp_plane gplanes_nhwc[3], int32_t C, const float* queries,
+                                     int64_t total, const int64_t* seg_offsets, const int32_t* seg_batch,
+                                     int32_t num_segments, int32_t batch, const tp_sample_geom* sg, int32_t arith,
+                                     const float* grad_out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a2  point_to_cam — point_triplane.py:164-241 (twin point_triplane_occ.py:163-239)
  *     einsum(lidar2image, hom_points) -> / max(z, 1e-5) -> * resize - crop (-> flip) -> the -W/2, rotate
@@ -271,6 +296,71 @@ TP_API int tp_mlp_head_tf32(const float* feats, int64_t Q, int32_t batch, int32_
 TP_API int tp_sample3_grid_head_tf32(const tp_plane planes_nhwc[3], const float* queries, const int32_t dims[3],
                               int32_t batch, const tp_sample_geom* sg, int32_t arith, const float* w1,
                               const float* w2, const float* w3, int32_t num_classes, float* logits, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * 8f#4  gathers / scatters either side of the decode (nearest-pixel, i.e. integer index work)
+ *
+ * Feature -> camera-pixel scatter: TriplaneMAE.forward triplane.py:381-390 and PointTriplane.cam_rec_feat
+ * point_triplane.py:243-309: `img[:, rows, cols] = feat[:, valid]` with duplicate targets. torch-CUDA leaves the order
+ * undefined; torch-CPU keeps the LAST source in list order. This library defines the order as torch-CPU's: the source
+ * with the highest index wins. Two steps: a winner image (int32, -1 = empty; written by the call, atomicMax), then a
+ * write-once gather of the dense output.
+ *   tp_pixel_winner_coors_i32: coors [M, npix, 2] fp32 (row, col) as range_cam_coors of JointEncoder.interact; a source
+ *     is used iff long(row) > 0 (triplane.py:386 tests AFTER .long(): row 0 is dropped there too) and inside H x W.
+ *   tp_pixel_winner_points_i32: points [N, stride] (samples concatenated, offsets [B+1]), cams as tp_lift_cam_f32;
+ *     projects every point into every camera with the chain of point_triplane.py:263-301, pixel = (long(y), long(x));
+ *     winner [B, ncam, R0, R1] holds the point index inside its sample.
+ *   tp_winner_gather_f32: out [M, C, HW] = feat[m / imgs_per_feat][c][winner[m, pix]] (0 where winner < 0). feat is
+ *     addressed as feat + fb * feat_bstride + (feat_row0 ? feat_row0[fb] * feat_nstride : 0) + c * feat_cstride +
+ *     n * feat_nstride: channel-major decode output [B, C, N] or point-major rows [N, C].
+ *   tp_winner_gather_backward_f32: grad_feat (ZEROED by the caller, same addressing) += grad_out at the winners.
+ * ------------------------------------------------------------------------------------------- */
+TP_API int tp_pixel_winner_coors_i32(const float* coors, int64_t n_images, int64_t npix, int32_t H, int32_t W,
+                              int32_t* winner, void* stream);
+TP_API int tp_pixel_winner_points_i32(const float* points, int32_t point_stride, int64_t n_total,
+                               const int64_t* offsets, int32_t batch, const float* cams, int32_t ncam,
+                               float resize_dim0, float resize_dim1, int32_t* winner, void* stream);
+TP_API int tp_winner_gather_f32(const int32_t* winner, int64_t n_images, int64_t HW, int32_t C, int32_t imgs_per_feat,
+                         const float* feat, int64_t feat_bstride, int64_t feat_cstride, int64_t feat_nstride,
+                         const int64_t* feat_row0, float* out, void* stream);
+TP_API int tp_winner_gather_backward_f32(const int32_t* winner, int64_t n_images, int64_t HW, int32_t C,
+                                  int32_t imgs_per_feat, const float* grad_out, float* grad_feat,
+                                  int64_t feat_bstride, int64_t feat_cstride, int64_t feat_nstride,
+                                  const int64_t* feat_row0, void* stream);
+
+/* JointEncoder.interact — joint_encoder.py:97-215, everything but the position_encoder MLP:
+ *   tp_range_project_f32: range_points [B, npix, 3], range_image [B, npix] (masked input; > 0 = unmasked), cams
+ *     [B, ncam, 20] -> coors [B, ncam, npix, 2] = range_cam_coors (row, col; -1 where the pixel holds no point
+ *     (x = y = z = 0) or the camera does not see it, :180-187), fidx [B, ncam, npix] = nearest feature-map pixel
+ *     long(row * Hf / R0) * Wf + long(col * Wf / R1) of the unmasked visible points (-1 otherwise, :190-205), winner
+ *     [B, ncam, Hf*Wf] = highest range pixel landing on each feature pixel (for the position-embedding index-put).
+ *   tp_range_gather_f32: out [B, C, npix] = sum over cameras, ascending from zero, of img_features[b, cam, :, fidx]
+ *     (img_features [B, ncam, C, Hf*Wf], the reference's NCHW maps; :208). Backward: grad_img (ZEROED) += grad_out.
+ *   tp_posembed_scatter_f32: img_features[m, :, p] += pos_embed[m, p, :] where winner[m, p] >= 0, in place
+ *     (m = b * ncam + cam; pos_embed [M, Hf*Wf, C] = position_encoder of the winners' points; :211-213, duplicates
+ *     resolved as above). Backward: grad_pos_embed[m, p, :] = winner >= 0 ? grad_img[m, :, p] : 0.
+ * ------------------------------------------------------------------------------------------- */
+TP_API int tp_range_project_f32(const float* range_points, const float* range_image, int64_t npix, int32_t batch,
+                         const float* cams, int32_t ncam, float resize_dim0, float resize_dim1, int32_t Hf,
+                         int32_t Wf, int32_t arith, float* coors, int32_t* fidx, int32_t* winner, void* stream);
+TP_API int tp_range_gather_f32(const int32_t* fidx, int64_t npix, int32_t batch, int32_t ncam,
+                        const float* img_features, int32_t C, int32_t HWf, float* out, void* stream);
+TP_API int tp_range_gather_backward_f32(const int32_t* fidx, int64_t npix, int32_t batch, int32_t ncam,
+                                 const float* grad_out, int32_t C, int32_t HWf, float* grad_img, void* stream);
+TP_API int tp_posembed_scatter_f32(const int32_t* winner, int64_t n_images, int32_t C, int32_t HWf,
+                            float* img_features, const float* pos_embed, void* stream);
+TP_API int tp_posembed_scatter_backward_f32(const int32_t* winner, int64_t n_images, int32_t C, int32_t HWf,
+                                     const float* grad_img, float* grad_pos_embed, void* stream);
+
+/* InterpNet's neighbourhood search — interpnet.py:44,65: torch_geometric.nn.radius(x = sources, y = queries, r,
+ * batch_x, batch_y) -> torch_cluster.radius with max_num_neighbors = 32 (un-vendored third-party op, restated from
+ * its CUDA kernel): for every query the FIRST max_num_neighbors sources of the same sample, in index order, with
+ * squared distance < r^2. x [Nx, 3] / y [Ny, 3] samples concatenated, x_offsets / y_offsets [B+1] int64 (device).
+ * col [Ny, max_num_neighbors] int32 global source indices, -1 padded; count [Ny]. (row, col) pairs of the reference =
+ * (q, col[q, k]) for k < count[q], queries ascending. */
+TP_API int tp_radius_i32(const float* x, const int64_t* x_offsets, const float* y, const int64_t* y_offsets,
+                  int64_t ny, int32_t batch, float r, int32_t max_num_neighbors, int32_t* col, int32_t* count,
+                  void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Host-buffer entry points (what a non-PyTorch caller binds; bench.py's `e2e` leg).

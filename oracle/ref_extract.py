@@ -51,6 +51,48 @@ def load_method(relpath: str, class_name: str, method_name: str):
     raise LookupError(f"{class_name}.{method_name} not found in {path}")
 
 
+def load_statements(relpath: str, class_name: str, method_name: str, contains: str, before: int = 0):
+    """Compile a run of statements from INSIDE a reference method as a function(namespace) -> namespace: the first
+    statement (searched depth-first) whose source contains `contains`, plus the `before` sibling statements in front of
+    it. For code the reference writes inline in forward() (e.g. the camera-pixel scatter, triplane.py:379-390)."""
+    path = os.path.join(REFERENCE_ROOT, relpath)
+    with open(path, "r") as fh:
+        src = fh.read()
+    tree = ast.parse(src, filename=path)
+
+    def find(body):
+        for k, st in enumerate(body):
+            seg = ast.get_source_segment(src, st) or ""
+            if contains in seg:
+                for field in ("body", "orelse"):
+                    sub = getattr(st, field, None)
+                    if isinstance(sub, list) and sub and isinstance(st, (ast.If, ast.With)):
+                        hit = find(sub)
+                        if hit is not None:
+                            return hit
+                return body[max(0, k - before):k + 1]
+        return None
+
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name == class_name:
+            for item in node.body:
+                if isinstance(item, ast.FunctionDef) and item.name == method_name:
+                    stmts = find(item.body)
+                    if stmts is None:
+                        break
+                    code = compile(ast.Module(body=list(stmts), type_ignores=[]), path, "exec")
+
+                    def run(ns):
+                        ns = dict(ns)
+                        ns.update({"torch": torch, "F": F, "np": np, "math": math})
+                        exec(code, ns)
+                        return ns
+
+                    run.lines = (stmts[0].lineno, stmts[-1].end_lineno)
+                    return run
+    raise LookupError(f"no statement containing {contains!r} in {class_name}.{method_name} of {path}")
+
+
 class _Registry:
     def register_module(self, *a, **k):
         return lambda cls: cls

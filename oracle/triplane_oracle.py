@@ -324,3 +324,149 @@ def sample3_np(planes: Sequence[np.ndarray], points: np.ndarray, lo, vs, half, d
     g = [((p[:, a] - dtype(lo[a])) / dtype(vs[a])) / dtype(half[a]) - 1 for a in range(3)]
     return (grid_sample_np(planes[0], g[0], g[1], dtype) + grid_sample_np(planes[1], g[1], g[2], dtype)
             + grid_sample_np(planes[2], g[0], g[2], dtype))
+
+
+# ------------------------------------------------------------------------------------------------
+# SURVEY 8f #4 — gathers / scatters either side of the decode
+# ------------------------------------------------------------------------------------------------
+def _augmented_pixels(cam_points_cam: torch.Tensor, resize_dims, resize, crop, flip):
+    """The per-camera augmentation chain shared by point_to_cam (point_triplane.py:203-227), cam_rec_feat
+    (point_triplane.py:277-301) and JointEncoder.interact (joint_encoder.py:160-185): returns (this_coor, valid_mask)."""
+    this_coor = cam_points_cam
+    H, W = resize_dims
+    this_coor[:, :2] = this_coor[:, :2] * resize
+    this_coor[:, 0] -= crop[0]
+    this_coor[:, 1] -= crop[1]
+    if flip:
+        this_coor[:, 0] = resize_dims[1] - this_coor[:, 0]
+    this_coor[:, 0] -= W / 2.0
+    this_coor[:, 1] -= H / 2.0
+    h = 0.0
+    rot_matrix = this_coor.new_tensor([[math.cos(h), math.sin(h)], [-math.sin(h), math.cos(h)]])
+    this_coor[:, :2] = torch.matmul(rot_matrix, this_coor[:, :2].T).T
+    this_coor[:, 0] += W / 2.0
+    this_coor[:, 1] += H / 2.0
+    valid_mask = ((this_coor[:, 1] < resize_dims[0]) & (this_coor[:, 0] < resize_dims[1])
+                  & (this_coor[:, 1] >= 0) & (this_coor[:, 0] >= 0))
+    return this_coor, valid_mask
+
+
+def cam_proj_feat(range_proj_feat: torch.Tensor, range_cam_coors: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """TriplaneMAE.forward, triplane.py:379-390 (inline code): scatter range-image features into camera images.
+    torch-CPU index_put keeps the LAST duplicate in list order; that order is the parity definition."""
+    B, N = range_cam_coors.shape[:2]
+    range_cam_coors = range_cam_coors.long()
+    out = torch.zeros(B, N, range_proj_feat.shape[1], H, W, device=range_proj_feat.device)
+    for b in range(B):
+        for cam_it in range(N):
+            cam_coors = range_cam_coors[b, cam_it]
+            cam_coors_valid = cam_coors[..., 0] > 0
+            proj_feat = range_proj_feat[b]
+            cam_coors = cam_coors[cam_coors_valid, :]
+            proj_feat = proj_feat[:, cam_coors_valid]
+            out[b, cam_it][:, cam_coors[:, 0], cam_coors[:, 1]] = proj_feat
+    return out
+
+
+def cam_rec_feat(points: torch.Tensor, points_feat: torch.Tensor, img_metas) -> torch.Tensor:
+    """PointTriplane.cam_rec_feat, point_triplane.py:243-309: points [N,3], points_feat [C,N], img_metas one dict."""
+    resize_dims = img_metas["img_shape"][::-1]
+    lidar2img = points.new_tensor(np.asarray(img_metas["lidar2image"]))
+    img_augs = img_metas["imgs_aug"]
+    num_cam = lidar2img.shape[0]
+    out = torch.zeros((num_cam, points_feat.shape[0], resize_dims[0], resize_dims[1]), device=points_feat.device)
+    hom_points = torch.cat((points, torch.ones_like(points[..., :1])), -1)
+    cam_points = torch.einsum("cij, hj->chi", lidar2img, hom_points)
+    cam_points = cam_points[..., 0:2] / torch.maximum(cam_points[..., 2:3], torch.ones_like(cam_points[..., 2:3]) * 1e-5)
+    for cam_it in range(num_cam):
+        aug = img_augs[cam_it]
+        this_coor, valid_mask = _augmented_pixels(cam_points[cam_it], resize_dims, aug["resize"], aug["crop"], aug["flip"])
+        valid_coor = this_coor[valid_mask, :].type(torch.long)
+        valid_coor[:, [0, 1]] = valid_coor[:, [1, 0]]
+        out[cam_it][:, valid_coor[:, 0], valid_coor[:, 1]] = points_feat[:, valid_mask]
+    return out
+
+
+def interact(img_features: torch.Tensor, range_image: torch.Tensor, img_metas, range_points: torch.Tensor, position_encoder):
+    """JointEncoder.interact, joint_encoder.py:97-215. img_features is updated in place, as in the reference."""
+    resize_dims = img_metas[0]["img_shape"][::-1]
+    lidar2imgs = range_points.new_tensor(np.asarray([m["lidar2image"] for m in img_metas]))
+    img_augs = [m["imgs_aug"] for m in img_metas]
+    hom_points = torch.cat((range_points, torch.ones_like(range_points[..., :1])), -1)
+    cam_points = torch.einsum("bcij, bhwj->bchwi", lidar2imgs, hom_points)
+    cam_points = cam_points[..., 0:2] / torch.maximum(cam_points[..., 2:3], torch.ones_like(cam_points[..., 2:3]) * 1e-5)
+    num_cam = lidar2imgs.shape[1]
+    batch_range_mask = range_image > 0
+    batch_size = range_points.shape[0]
+    batch_no_point_mask = torch.ones_like(range_image).squeeze(1)
+    batch_no_point_mask[(range_points == 0).sum(dim=3) == 3] = 0
+    batch_no_point_mask = batch_no_point_mask.type(torch.bool)
+    cam_range_features = torch.zeros(batch_size, img_features.shape[2], range_image.shape[2], range_image.shape[3],
+                                     device=range_image.device)
+    range_cam_coors = torch.zeros(batch_size, num_cam, range_image.shape[2], range_image.shape[3], 2,
+                                  device=range_image.device) - 1
+    for i in range(batch_size):
+        this_coors = cam_points[i]
+        range_mask = batch_range_mask[i].squeeze(0)
+        no_point_mask = batch_no_point_mask[i]
+        no_point_range_mask = range_mask[no_point_mask]
+        for cam_it in range(num_cam):
+            aug = img_augs[i][cam_it]
+            this_coor, valid_mask = _augmented_pixels(this_coors[cam_it][no_point_mask, :], resize_dims, aug["resize"],
+                                                      aug["crop"], aug["flip"])
+            valid_coor = this_coor[valid_mask, :]
+            valid_coor[:, [0, 1]] = valid_coor[:, [1, 0]]
+            range_valid_mask = no_point_mask.clone()
+            range_valid_mask[no_point_mask] = valid_mask
+            range_cam_coors[i, cam_it][range_valid_mask] = valid_coor
+            valid_mask = valid_mask & no_point_range_mask
+            valid_points = range_points[i, no_point_mask, :][valid_mask, :]
+            valid_coor = this_coor[valid_mask, :]
+            valid_coor[:, [0, 1]] = valid_coor[:, [1, 0]]
+            range_valid_mask = no_point_mask.clone()
+            range_valid_mask[no_point_mask] = valid_mask
+            valid_coor[:, 0] = valid_coor[:, 0] * img_features.shape[-2] / resize_dims[0]
+            valid_coor[:, 1] = valid_coor[:, 1] * img_features.shape[-1] / resize_dims[1]
+            valid_coor = valid_coor.type(torch.long)
+            cam_range_features[i, :, range_valid_mask] += img_features[i, cam_it][:, valid_coor[:, 0], valid_coor[:, 1]]
+            pos_embed = position_encoder(valid_points)
+            img_features[i, cam_it][:, valid_coor[:, 0], valid_coor[:, 1]] += pos_embed.permute(1, 0)
+    return torch.cat((range_image, cam_range_features), dim=1), img_features, range_cam_coors
+
+
+def radius(x: torch.Tensor, y: torch.Tensor, r: float, batch_x: torch.Tensor, batch_y: torch.Tensor,
+           max_num_neighbors: int = 32):
+    """torch_geometric.nn.radius -> torch_cluster.radius (interpnet.py:5,44,65). NOT in /root/reference and not
+    installable here: restated from torch_cluster's CUDA kernel (one thread per query walks the sources of the same
+    sample in index order, keeps those with squared distance < r*r, stops after max_num_neighbors) — 'parity
+    unpinned'. Returns (row = query index, col = source index), queries ascending."""
+    rows, cols = [], []
+    for q in range(y.shape[0]):
+        src = torch.nonzero(batch_x == batch_y[q]).flatten()
+        d = x[src] - y[q]
+        d2 = d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2]
+        hit = src[d2 < r * r][:max_num_neighbors]
+        rows.append(torch.full_like(hit, q))
+        cols.append(hit)
+    return torch.cat(rows), torch.cat(cols)
+
+
+def contrastive_features(sample_fn, triplane, points: Sequence[torch.Tensor], pc_range, num_cam: int = 6):
+    """The sampling loop of the contrastive branch, triplane.py:438-455: per sample crop, per camera the points with a
+    positive SAM label; `sample_fn(triplane[i][None], coords[None, None]).squeeze().permute(1, 0)`. Returns the list
+    of ([N_s, C] features, labels) in loop order, skipping subsets with <= 1 point as the reference does."""
+    out = []
+    for i, pts in enumerate(points):
+        crop_mask = ((pts[..., 0] > pc_range[0]) & (pts[..., 0] < pc_range[3]) & (pts[..., 1] > pc_range[1]) &
+                     (pts[..., 1] < pc_range[4]) & (pts[..., 2] > pc_range[2]) & (pts[..., 2] < pc_range[5]))
+        pts = pts[crop_mask]
+        for cam in range(num_cam):
+            coords = pts[:, 0:3]
+            labels = pts[:, 5 + cam]
+            valid_mask = labels > 0
+            coords = coords[valid_mask]
+            labels = labels[valid_mask].type(torch.int)
+            if labels.shape[0] > 1:
+                features = sample_fn(triplane[i][None, ...], coords[None, None, ...]).squeeze()
+                out.append((features.permute(1, 0), labels))
+    return out

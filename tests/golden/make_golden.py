@@ -14,6 +14,10 @@ efficient_multimodal_perception_b200.synth) and the reference's outputs. Source 
   lift         PointTriplane.point_to_cam            point_triplane.py:164-241
   projector_*  PointTriplaneProjector.forward        point_triplane_projector.py:66-117, with
                torch_scatter / spconv replaced by the oracle's restatements (oracle/ref_extract.py)
+  interact     JointEncoder.interact                 mmdet3d/models/backbones/joint_encoder.py:97-215
+  cam_proj_feat  the inline camera-pixel scatter     triplane.py:380-390 (statements cut out of TriplaneMAE.forward)
+  cam_rec_feat PointTriplane.cam_rec_feat            point_triplane.py:243-309
+  contrastive  the contrastive sampling loop         triplane.py:438-455 around TriplaneMAE.sample_points_triplane
 """
 from __future__ import annotations
 
@@ -190,10 +194,89 @@ def gen_projector():
              tpv_xy=out[0], tpv_yz=out[1], tpv_xz=out[2], **arrays)
 
 
+def small_rig(seed, flips=(False,) * 6):
+    """synth.camera_rig scaled to 64x128 (H x W) images (resize 0.525/4, crop (41, 54)) so dense image fixtures stay
+    small; img_shape is PIL's (W, H)."""
+    rig = synth.camera_rig(seed)
+    augs = [dict(resize=0.525 / 4, crop=(41, 54), flip=bool(f)) for f in flips]
+    return dict(img_shape=(128, 64), lidar2image=rig.lidar2image.numpy(), imgs_aug=augs)
+
+
+def meta_arrays(metas, prefix="meta"):
+    out = {}
+    for i, m in enumerate(metas):
+        out[f"{prefix}{i}.lidar2image"] = np.asarray(m["lidar2image"], dtype=np.float64)
+        out[f"{prefix}{i}.resize"] = [a["resize"] for a in m["imgs_aug"]]
+        out[f"{prefix}{i}.crop"] = [a["crop"] for a in m["imgs_aug"]]
+        out[f"{prefix}{i}.flip"] = [a["flip"] for a in m["imgs_aug"]]
+        out[f"{prefix}{i}.img_shape"] = m["img_shape"]
+    return out
+
+
+def gen_interact():
+    """JointEncoder.interact (joint_encoder.py:97-215) executed as-is, then the inline camera-pixel scatter of
+    TriplaneMAE.forward (triplane.py:380-390) executed on ITS range_cam_coors."""
+    fn = R.load_method("mmdet3d/models/backbones/joint_encoder.py", "JointEncoder", "interact")
+    B, C, Hf, Wf = 2, 8, 8, 16
+    metas = [small_rig(51), small_rig(52, flips=(False, True, False, False, True, False))]
+    rp = synth.range_image_points(B, seed=53)[:, ::2, ::4].contiguous()       # [2,16,256,3], ~30 % empty pixels
+    g = torch.Generator().manual_seed(54)
+    rng_img = rp.norm(dim=-1)[:, None].clone()                                # range image; 0 where no point
+    rng_img[torch.rand(rng_img.shape, generator=g) < 0.4] = 0.0               # MAE-masked pixels
+    img = torch.randn(B, 6, C, Hf, Wf, generator=g)
+    torch.manual_seed(55)
+    pe = torch.nn.Sequential(torch.nn.Linear(3, 32), torch.nn.ReLU(), torch.nn.Linear(32, C))
+    self = SimpleNamespace(position_encoder=pe)
+    with torch.no_grad():
+        cat, img_out, coors = fn(self, img.clone(), rng_img, metas, rp)
+    arrays = {f"pe.{k}": v for k, v in pe.state_dict().items()}
+    arrays.update(meta_arrays(metas))
+    save("interact", range_points=rp, range_image=rng_img, img_features=img, out_cat=cat, out_img=img_out,
+         range_cam_coors=coors, **arrays)
+    # triplane.py:380-390 on the reference's own coordinates
+    run = R.load_statements(DET + "triplane.py", "TriplaneMAE", "forward",
+                            "cam_proj_feat[b, cam_it][:, cam_coors[:, 0], cam_coors[:, 1]] = proj_feat", before=2)
+    assert run.lines == (380, 390), run.lines
+    feat = torch.randn(B, 4, rp.shape[1], rp.shape[2], generator=g)
+    H, W = metas[0]["img_shape"][::-1]
+    ns = run(dict(range_cam_coors=coors.clone(), B=B, N=6, range_proj_feat=feat, H=H, W=W, img=feat))
+    save("cam_proj_feat", range_proj_feat=feat, range_cam_coors=coors, H=H, W=W, out=ns["cam_proj_feat"])
+
+
+def gen_cam_rec():
+    fn = R.load_method(DET + "point_triplane.py", "PointTriplane", "cam_rec_feat")
+    meta = small_rig(61, flips=(False, False, True, False, False, False))
+    pts = synth.lidar_sweep(3000, seed=62)[:, :3].contiguous()
+    feat = torch.randn(4, pts.shape[0], generator=torch.Generator().manual_seed(63))
+    out = fn(None, pts.clone(), feat, meta)
+    save("cam_rec_feat", points=pts, points_feat=feat, out=out, **meta_arrays([meta]))
+
+
+def gen_contrastive():
+    """The contrastive sampling loop (triplane.py:438-455) with the reference's own sample_points_triplane."""
+    from oracle import triplane_oracle as O
+    fn = R.load_method(DET + "triplane.py", "TriplaneMAE", "sample_points_triplane")
+    G = synth.GEOM_A
+    self = SimpleNamespace(pc_range=G["pc_range"], voxel_size=G["voxel_size"])
+    tri = synth.triplane_stacked(3, 8, 32, seed=71)
+    pts = [synth.lidar_sweep(900, seed=72), synth.lidar_sweep(700, seed=73), synth.lidar_sweep(40, seed=74)]
+    pts[2][:, 5:] = 0          # a sample whose subsets are all empty
+    pts[2][:1, 5] = 3.0        # ... except one single-point subset (skipped: labels.shape[0] > 1 fails)
+    res = O.contrastive_features(lambda t, c: fn(self, t, c), tri, pts, G["pc_range"])
+    arrays = {}
+    for k, (f, lab) in enumerate(res):
+        arrays[f"feat{k}"], arrays[f"label{k}"] = f, lab
+    save("contrastive", triplane=tri, points0=pts[0], points1=pts[1], points2=pts[2], pc_range=G["pc_range"],
+         voxel_size=G["voxel_size"], nsubsets=len(res), **arrays)
+
+
 if __name__ == "__main__":
     if not R.available():
         sys.exit("needs /root/reference (build container only)")
     torch.set_num_threads(1)
-    for fn in (gen_voxelize, gen_sample, gen_lift, gen_projector):
+    only = set(sys.argv[1:])
+    for fn in (gen_voxelize, gen_sample, gen_lift, gen_projector, gen_interact, gen_cam_rec, gen_contrastive):
+        if only and fn.__name__ not in only:
+            continue
         print(fn.__name__)
         fn()

@@ -2,22 +2,25 @@
 """Benchmark of the triplane hot path (BASELINE.json metric: triplane encode points/s + query-sample
 queries/s on B200, % of HBM peak).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--queries ...]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload W] [--queries ...]
 
-Headline (`value`): occupancy decode of configs/triplane_occ.py at BASELINE.json's size — 640 000
-voxel queries sampled from three fp32 128x128 triplanes with C=32 (`configs[1]`) — in queries/s,
-inputs resident in HBM. A step = one pass of the decode path over one batch: the NCHW->NHWC
-conversion of the three planes (one launch) + the fused 3-plane gather kernel (one launch). Steps rotate over `nsets` disjoint
-buffer sets whose total footprint exceeds 3x the 126 MB L2, and are replayed from CUDA graphs so the
-Python launch cost is not what is measured. The same JSON line also carries the encode leg
-(`encode`: points/s for one synthetic nuScenes sweep at the config-exact geometry; `variants_kernel_only`:
-the other query sets of SURVEY 8(d) S2, including 640k uniform-random in-range queries = worst-case locality), `roofline`
-(dominant kernel, algorithmic bytes / CUDA-event time, vs MEASURED_PEAKS.json), `cpu_baseline`
-(the oracle on the box's host cores), `e2e` (host buffers through the C ABI) and `clocks`.
+Workloads = BASELINE.json's configs, each a parity-asserting leg with its own `roofline`, `cpu_baseline`
+(the reference's op chain = the oracle, on all host cores, core count stated) and `e2e` (host buffers):
 
-Under torchrun (N > 1) every rank runs the same per-GPU workload on its own shard of queries /
-samples (weak scaling, no data-path collective: decode queries and encode samples are independent);
-time is the max over ranks, value the sum of work over ranks / that time.
+  decode         configs[1]  triplane_occ occupancy decode, 640 000 voxel queries, C=32 (HEADLINE: `value`)
+  encode         configs[0]  point_triplane forward scatter: 1 sweep (34 720 pts), config-exact 128x128x80 grid
+  encode_b       configs[0]  the same at BASELINE's "200x200x16" grid (not a reference config)
+  surf_sam       configs[2]  bs=8: [8,32,1024,3] range points + per-(sample, camera) SAM subsets (one segment launch)
+  range_cam      configs[3]  bs=8: voxelize -> 6-camera lift -> PointTriplaneProjector forward, + interact / pixel scatter
+  point_sharded  configs[4]  10-sweep (~350k pts) samples x bs=64 sharded over the GPUs (+ one sample point-sharded, N > 1)
+
+With no --workload every workload runs (bounded) and rank 0 prints ONE JSON line: the headline decode line with the
+others nested under "workloads". `--workload X` prints X's own line. A step = one pass of the hot path over one
+batch. Decode steps rotate over buffer sets whose footprint exceeds 3x the 126 MB L2 and are replayed from CUDA
+graphs; every other workload moves > 3x L2 per step (stated in `config.l2`).
+
+Under torchrun (N > 1) every rank runs its shard (weak scaling unless stated; no data-path collective except
+point_sharded's single-sample legs); time is the max over ranks, value the sum of work over ranks / that time.
 """
 from __future__ import annotations
 
@@ -40,6 +43,7 @@ FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if 
 
 OCC_LO, OCC_VS, OCC_HALF = [-25.0, -25.0, -5.0], (0.4, 0.4, 0.1), [64.0] * 3
 C_DEC, PLANE = 32, 128
+WORKLOADS = ["decode", "encode", "encode_b", "surf_sam", "range_cam", "point_sharded"]
 
 
 def measured_hbm_peak():
@@ -48,6 +52,10 @@ def measured_hbm_peak():
             return float(json.load(fh)["hbm_gbs"]), "measured"
     except Exception:
         return FALLBACK_HBM_GBS, "fallback"
+
+
+def host_cores():
+    return {"os_cpu_count": os.cpu_count(), "affinity": len(os.sched_getaffinity(0)), "torch_threads": torch.get_num_threads()}
 
 
 def decode_queries(kind: str):
@@ -65,17 +73,20 @@ def decode_queries(kind: str):
 QUERY_DIMS = {"lattice640k": (200, 200, 16), "roi": (99, 99, 16), "uniform640k": None}
 
 
-def ncu_traffic(kernel: str, key: str):
-    """dram bytes per launch from the committed ncu capture (profiles/), or None."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
-            return json.load(fh)[kernel][key]
-    except Exception:
-        return None
+def profile_traffic(kernel: str, key: str):
+    """dram bytes per launch of the named kernel from the committed ncu capture under profiles/ (NOT measured in this
+    run: ncu cannot run inside the timed program), or None."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as fh:
+                return json.load(fh)[kernel][key]
+        except Exception:
+            continue
+    return None
 
 
 def decode_bytes(Q: int, C_: int = C_DEC) -> int:
-    """SURVEY §8(d): Q*(12 + 4C) + 4C*sum(HW) per sample."""
+    """SURVEY 8(d): Q*(12 + 4C) + 4C*sum(HW) per sample."""
     return Q * (12 + 4 * C_) + 4 * C_ * 3 * PLANE * PLANE
 
 
@@ -121,8 +132,162 @@ class ClockSampler(threading.Thread):
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+class Ctx:
+    """Per-process benchmark context: device, ranks, barrier, clock sampler, measured peak."""
+
+    def __init__(self, args):
+        import torch.distributed as dist
+        self.args, self.dist = args, dist
+        self.rank = int(os.environ.get("RANK", 0))
+        self.world = int(os.environ.get("WORLD_SIZE", 1))
+        self.local = int(os.environ.get("LOCAL_RANK", 0))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU path (use --impl reference)")
+        torch.cuda.set_device(self.local)
+        self.numa = bind_to_gpu(self.local, self.world) if self.world > 1 else None
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.barrier = lambda: dist.barrier()  # noqa: E731
+        else:
+            self.barrier = lambda: None  # noqa: E731
+        import efficient_multimodal_perception_b200 as emp
+        emp.lib()
+        self.peak, self.peak_src = measured_hbm_peak()
+        self.sampler = ClockSampler(self.local, getattr(torch.cuda.get_device_properties(self.dev), "uuid", None))
+        self.sampler.start()
+
+    def max_over_ranks(self, *vals):
+        t = torch.tensor(list(vals), device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+    def roofline(self, nbytes, ms, **extra):
+        ach = nbytes / (ms * 1e-3) / 1e9
+        return dict({"bound": "hbm", "achieved": ach, "peak": self.peak, "unit": "GB/s", "frac": ach / self.peak,
+                     "algorithmic_bytes": int(nbytes), "peak_source": self.peak_src}, **extra)
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def time_region(fn, barrier):
+    """CUDA-event time (ms) of fn() on the current stream, barrier + synchronize on both sides."""
+    barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    fn()
+    b.record()
+    torch.cuda.synchronize()
+    barrier()
+    return a.elapsed_time(b)
+
+
+def time_steps(step, steps, warmup, ctx):
+    """ms per step: `warmup` untimed steps, then `steps` timed ones between events."""
+    for _ in range(warmup):
+        step()
+
+    def run():
+        for _ in range(steps):
+            step()
+
+    ctx.sampler.active.set()
+    ms = time_region(run, ctx.barrier) / steps
+    ctx.sampler.active.clear()
+    return ms
+
+
+def kernel_time_ms(launch, reps: int, group: int):
+    """Average duration of ONE launch of a kernel: `group` back-to-back launches (one per rotating buffer set)
+    are captured in a CUDA graph, CUDA events bracket each replay, duration = elapsed / group. Events around a
+    single ~20 us launch would add the event/launch latency (~4 us) to every sample."""
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for i in range(group):
+            launch(i)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(group):
+            launch(i)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(max(3, reps // group)):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        g.replay()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) / group for a, b in evs)
+    return sum(ts) / len(ts), ts[len(ts) // 2], ts[0]
+
+
+def cpu_time(fn, budget_s=10.0, max_passes=10):
+    """median seconds of fn() on the host: one warm-up, then passes until the budget is spent (>= 2)."""
+    fn()
+    ts, t_start = [], time.perf_counter()
+    while len(ts) < max_passes and (time.perf_counter() - t_start < budget_s or len(ts) < 2):
+        t0 = time.perf_counter()
+        fn()
+        ts.append(time.perf_counter() - t0)
+    return statistics.median(ts), len(ts)
+
+
+def e2e_time(call, steps, ctx):
+    """Wall-clock ms per call of a synchronous host-buffer call (it ends with its own stream synchronize)."""
+    for _ in range(3):
+        call()
+    ctx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        call()
+    dt = time.perf_counter() - t0
+    ctx.barrier()
+    return ctx.max_over_ranks(dt / steps * 1e3)[0]
+
+
+def bind_to_gpu(local: int, world: int):
+    """Pin this rank's threads (and therefore its pinned host buffers, first-touch) near its GPU: the e2e legs move
+    ~100 MB per step over PCIe per rank. Uses the GPU's NUMA node when sysfs reports one; virtualised hosts report
+    -1, then the CPUs this process may use are split evenly between the local ranks. Best effort: returns a
+    description or None."""
+    try:
+        avail = sorted(os.sched_getaffinity(0))
+        node = -1
+        try:
+            p = torch.cuda.get_device_properties(local)
+            path = f"/sys/bus/pci/devices/{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0/numa_node"
+            node = int(open(path).read().strip())
+        except Exception:
+            node = -1
+        if node >= 0:
+            cpus = set()
+            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            cpus &= set(avail)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                return {"numa_node": node, "cpus": len(cpus)}
+        nloc = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        per = max(1, len(avail) // max(1, nloc))
+        mine = avail[(local % nloc) * per:(local % nloc + 1) * per] or avail
+        os.sched_setaffinity(0, set(mine))
+        return {"numa_node": None, "cpus": len(mine), "how": "even split of the visible CPUs between local ranks"}
+    except Exception:
+        return None
+
+
 # --------------------------------------------------------------------------------------------------
-# b200 arm
+# decode (configs[1], headline)
 # --------------------------------------------------------------------------------------------------
 class DecodeSets:
     """nsets disjoint (planes, queries, out) buffer sets + CUDA graphs of the 2-launch step."""
@@ -169,47 +334,6 @@ class DecodeSets:
             self.graph_all.replay()
         for s in range(rem):
             self.graph_one[s].replay()
-
-
-def time_region(fn, barrier):
-    """CUDA-event time (ms) of fn() on the current stream, barrier + synchronize on both sides."""
-    barrier()
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    fn()
-    b.record()
-    torch.cuda.synchronize()
-    barrier()
-    return a.elapsed_time(b)
-
-
-def kernel_time_ms(launch, reps: int, group: int):
-    """Average duration of ONE launch of a kernel: `group` back-to-back launches (one per rotating buffer set)
-    are captured in a CUDA graph, CUDA events bracket each replay, duration = elapsed / group. Events around a
-    single ~20 us launch would add the event/launch latency (~4 us) to every sample."""
-    side = torch.cuda.Stream()
-    with torch.cuda.stream(side):
-        for i in range(group):
-            launch(i)
-    torch.cuda.synchronize()
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
-        for i in range(group):
-            launch(i)
-    for _ in range(3):
-        g.replay()
-    torch.cuda.synchronize()
-    evs = []
-    for _ in range(max(3, reps // group)):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        g.replay()
-        b.record()
-        evs.append((a, b))
-    torch.cuda.synchronize()
-    ts = sorted(a.elapsed_time(b) / group for a, b in evs)
-    return sum(ts) / len(ts), ts[len(ts) // 2], ts[0]
 
 
 def bench_decode_device(args, dev, barrier, sampler):
@@ -259,29 +383,21 @@ def bench_decode_device(args, dev, barrier, sampler):
         variants[kind] = {"Q": qv.shape[1], "kernel_ms_avg": va, "kernel_ms_median": vm, "queries_per_s": qv.shape[1] / (va * 1e-3),
                           "algorithmic_bytes": vb, "achieved_gbs": vb / (va * 1e-3) / 1e9}
         del qs, outs
-    # range-image points of configs/triplane_surf_sam.py, bs=8: [8,32,1024,3] (30 % empty pixels at
-    # the origin), per-query kernel, one stacked triplane per sample
-    from efficient_multimodal_perception_b200 import synth
-    Br = 8
-    rq = synth.range_image_points(Br, seed=1003).reshape(Br, -1, 3).contiguous()
-    rbytes = Br * decode_bytes(rq.shape[1])
-    rsets = max(4, -(-3 * L2_BYTES // rbytes))
-    r_tri = [ops.planes_to_channels_last([t[:, 0], t[:, 1], t[:, 2]])
-             for t in (synth.triplane_stacked(Br, C_DEC, PLANE, seed=1003 + s).to(dev) for s in range(rsets))]
-    r_q = [rq.to(dev).clone() for _ in range(rsets)]
-    r_out = [torch.empty(Br, C_DEC, rq.shape[1], device=dev) for _ in range(rsets)]
+    # the same 640k lattice with the coordinates generated in the kernel (tp_sample3_lattice_nhwc_f32: no query tensor)
+    if args.queries == "lattice640k":
+        def launch_g(i):
+            _, _, out = sets.sets[i % nsets]
+            ops.sample3_lattice(nhwc[i % nsets], dims, [-50.0, -50.0, -5.0], (0.5, 0.5, 0.5), OCC_LO, OCC_VS, OCC_HALF,
+                                channels_last=True, out=out)
 
-    def launch_r(i):
-        ops.sample3(r_tri[i % rsets], r_q[i % rsets], OCC_LO, OCC_VS, OCC_HALF, channels_last=True, out=r_out[i % rsets])
-
-    for i in range(rsets):
-        launch_r(i)
-    torch.cuda.synchronize()
-    ra, rm, _ = kernel_time_ms(launch_r, min(reps, 200), rsets)
-    variants["range_points_bs8"] = {"Q": Br * rq.shape[1], "kernel_ms_avg": ra, "kernel_ms_median": rm,
-                                    "queries_per_s": Br * rq.shape[1] / (ra * 1e-3), "algorithmic_bytes": rbytes,
-                                    "achieved_gbs": rbytes / (ra * 1e-3) / 1e9}
-    del r_tri, r_q, r_out
+        for i in range(8):
+            launch_g(i)
+        torch.cuda.synchronize()
+        ga, gm, _ = kernel_time_ms(launch_g, min(reps, 200), nsets)
+        gb = decode_bytes(Q) - 12 * Q
+        variants["lattice640k_generated"] = {"Q": Q, "kernel_ms_avg": ga, "kernel_ms_median": gm, "queries_per_s": Q / (ga * 1e-3),
+                                             "algorithmic_bytes": gb, "achieved_gbs": gb / (ga * 1e-3) / 1e9,
+                                             "note": "roi()-style lattice generated in-kernel: no 12 B/query read"}
     sampler.active.clear()
     return dict(Q=Q, nsets=nsets, ms_total=ms, kernel_ms_avg=k_avg, kernel_ms_med=k_med, kernel_ms_min=k_min,
                 launches=args.steps * 2, sets=sets, variants=variants)
@@ -303,6 +419,10 @@ def torch_cuda_decode(q_dev, tri_dev, reps=5):
         xz = F.grid_sample(tri_dev[:, 2], v[..., [0, 2]], mode="bilinear", padding_mode="zeros", align_corners=False)
         return xy + yz + xz
 
+    return gpu_chain_ms(chain, reps)
+
+
+def gpu_chain_ms(chain, reps=5):
     for _ in range(2):
         chain()
     torch.cuda.synchronize()
@@ -315,7 +435,7 @@ def torch_cuda_decode(q_dev, tri_dev, reps=5):
     return a.elapsed_time(b) / reps
 
 
-def bench_decode_e2e(args, Q_host, barrier):
+def bench_decode_e2e(args, Q_host, ctx):
     """Host buffers through the C ABI (tp_sample3_host_f32): H2D of planes + queries, conversion,
     gather, D2H of the full [C,Q] result, synchronised, every step."""
     from efficient_multimodal_perception_b200 import _lib as L
@@ -329,7 +449,6 @@ def bench_decode_e2e(args, Q_host, barrier):
     hw = (C.c_int32 * 6)(*[PLANE] * 6)
     bs = (C.c_int64 * 3)(*[tri.stride(0)] * 3)
     sg = L.make_sample_geom(OCC_LO, OCC_VS, OCC_HALF)
-
     dims = QUERY_DIMS[args.queries]
     cdims = (C.c_int32 * 3)(*dims) if dims else None
 
@@ -343,87 +462,41 @@ def bench_decode_e2e(args, Q_host, barrier):
                                             C.byref(sg), L.TP_ARITH_TORCH_CUDA, out.data_ptr()), "tp_sample3_host_f32")
 
     steps = max(5, min(args.steps, 100))
-    for _ in range(3):
-        call()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        call()
-    dt = time.perf_counter() - t0
-    barrier()
-    h2d = tri.numel() * 4 + q.numel() * 4
-    d2h = out.numel() * 4
-    return dict(qps=Q * steps / dt, steps=steps, h2d=h2d, d2h=d2h, ms=dt / steps * 1e3, out=out)
+    ms = e2e_time(call, steps, ctx)
+    return dict(steps=steps, h2d=tri.numel() * 4 + q.numel() * 4, d2h=out.numel() * 4, ms=ms, out=out)
 
 
-def bench_encode_device(args, dev, barrier, sampler):
-    """Encode leg: configs/point_triplane.py geometry (128x128x80, pool 5/5/4, C=128), one synthetic
-    sweep (34 720 raw points), crop + index fused into the encode (raw points in)."""
+def bench_decode_head_e2e(args, ctx):
+    """Decode + occupancy head end to end with host buffers: planes + queries go up, ONE fused kernel produces the
+    logits (tp_sample3_grid_head_tf32), only the [5, Q] logits come back (12.8 MB instead of the 82 MB feature tensor).
+    Through the Python API: pinned host tensors, non_blocking copies, synchronised every step."""
     from efficient_multimodal_perception_b200 import ops, synth
-    G = synth.GEOM_A
-    n, Cc = 34720, G["channels"]
-    pts = synth.lidar_sweep(n, seed=1001)
-    xyz = pts[:, :3].contiguous().to(dev)
-    feats = synth.point_features(n, Cc, seed=1001).to(dev)
-    off = synth.batch_offsets([n]).to(dev)
-    inside = int(((pts[:, 0].abs() < 25) & (pts[:, 1].abs() < 25) & (pts[:, 2] > -5) & (pts[:, 2] < 3)).sum())
-    cells = 128 * 128 * 20 + 2 * 128 * 80 * 25
+    dev = ctx.dev
+    dims = QUERY_DIMS["lattice640k"]
+    q_h = synth.occ_gt_lattice().reshape(1, -1, 3).contiguous().pin_memory()
+    tri_h = synth.triplane_stacked(1, C_DEC, PLANE, seed=1002).pin_memory()
+    g = torch.Generator().manual_seed(7)
+    w = [(torch.randn(2 * C_DEC, C_DEC, generator=g) / C_DEC ** 0.5).to(dev), (torch.randn(C_DEC, 2 * C_DEC, generator=g) / (2 * C_DEC) ** 0.5).to(dev),
+         (torch.randn(5, C_DEC, generator=g) / C_DEC ** 0.5).to(dev)]
+    out_h = torch.empty(1, 5, q_h.shape[1]).pin_memory()
 
-    def step():
-        return ops.encode(feats, off, G["pc_range"], G["voxel_size"], G["grid_size"], G["split"], points=xyz)
+    def call():
+        tri = tri_h.to(dev, non_blocking=True)
+        q = q_h.to(dev, non_blocking=True)
+        logits = ops.sample3_head(tri, q, OCC_LO, OCC_VS, OCC_HALF, w[0], w[1], w[2], grid_dims=dims)
+        out_h.copy_(logits, non_blocking=True)
+        torch.cuda.synchronize()
 
-    for _ in range(max(3, min(args.warmup, 10))):
-        outs = step()
-    steps = max(10, min(args.steps, 200))
-    sampler.active.set()
-    def run():
-        for _ in range(steps):
-            step()  # outputs are dropped each step: the caching allocator hands the same blocks back
-
-    ms = time_region(run, barrier)
-    sampler.active.clear()
-    bytes_alg = n * 12 + inside * 4 * Cc + 4 * Cc * cells  # SURVEY §8(d)
-    return dict(n=n, inside=inside, cells=cells, steps=steps, ms_per_step=ms / steps, bytes=bytes_alg,
-                launches=4 * steps)
+    steps = max(5, min(args.steps, 100))
+    ms = e2e_time(call, steps, ctx)
+    return dict(ms=ms, steps=steps, h2d=tri_h.numel() * 4 + q_h.numel() * 4, d2h=out_h.numel() * 4, Q=q_h.shape[1])
 
 
-def bench_encode_dense(args, dev, barrier, sampler):
-    """BASELINE.json configs[4] shape per GPU: samples of 10 accumulated sweeps (~350k points each), sample-sharded
-    (bs=64 over 8 GPUs = 8 per GPU; 4 per GPU here to bound the footprint), one batched encode call."""
-    from efficient_multimodal_perception_b200 import ops, synth
-    G = synth.GEOM_A
-    B, Cc = 4, G["channels"]
-    pts = [synth.multi_sweep(10, 35000, seed=1005 + b) for b in range(B)]
-    sizes = [p.shape[0] for p in pts]
-    xyz = torch.cat([p[:, :3] for p in pts]).contiguous().to(dev)
-    feats = synth.point_features(sum(sizes), Cc, seed=1005).to(dev)
-    off = synth.batch_offsets(sizes).to(dev)
-    inside = int(sum(int(((p[:, 0].abs() < 25) & (p[:, 1].abs() < 25) & (p[:, 2] > -5) & (p[:, 2] < 3)).sum()) for p in pts))
-    cells = B * (128 * 128 * 20 + 2 * 128 * 80 * 25)
-
-    def step():
-        return ops.encode(feats, off, G["pc_range"], G["voxel_size"], G["grid_size"], G["split"], points=xyz)
-
-    for _ in range(3):
-        step()
-    steps = max(5, min(args.steps, 20))
-    sampler.active.set()
-
-    def run():
-        for _ in range(steps):
-            step()
-
-    ms = time_region(run, barrier)
-    sampler.active.clear()
-    n = sum(sizes)
-    return dict(n=n, B=B, inside=inside, steps=steps, ms_per_step=ms / steps,
-                bytes=n * 12 + inside * 4 * Cc + 4 * Cc * cells, launches=4 * steps)
-
-
-def bench_lift(args, dev, barrier, sampler):
+def bench_lift(args, ctx):
     """Camera -> point lift (point_to_cam) at the PointTriplane config: 6 cameras x [768,16,32] feature maps per
     sample, bs=2 sweeps of 34 720 points. A step = channels-last copy of the maps + the fused lift kernel."""
     from efficient_multimodal_perception_b200 import ops, synth
+    dev = ctx.dev
     B, ncam, Cf, Hf, Wf, n = 2, 6, 768, 16, 32, 34720
     rig = synth.camera_rig(1004)
     metas = [dict(img_shape=rig.img_shape, lidar2image=rig.lidar2image.numpy(), imgs_aug=rig.imgs_aug) for _ in range(B)]
@@ -432,39 +505,21 @@ def bench_lift(args, dev, barrier, sampler):
     feats = torch.randn(B, ncam, Cf, Hf, Wf, generator=torch.Generator().manual_seed(1004)).to(dev)
     cams = ops.pack_cameras(metas, dev)
     dims = rig.img_shape[::-1]
-
-    def step():
-        return ops.lift_cam(pts, off, feats, cams, dims)
-
-    for _ in range(3):
-        step()
-    nhwc = ops.features_to_channels_last(feats)
     steps = max(10, min(args.steps, 100))
-    sampler.active.set()
-
-    def run():
-        for _ in range(steps):
-            step()
-
-    ms = time_region(run, barrier) / steps
-
-    def run_k():
-        for _ in range(steps):
-            ops.lift_cam(pts, off, nhwc, cams, dims, channels_last=True)
-
-    ms_k = time_region(run_k, barrier) / steps
-    sampler.active.clear()
+    ms = time_steps(lambda: ops.lift_cam(pts, off, feats, cams, dims), steps, 3, ctx)
+    nhwc = ops.features_to_channels_last(feats)
+    ms_k = time_steps(lambda: ops.lift_cam(pts, off, nhwc, cams, dims, channels_last=True), steps, 3, ctx)
     # N'*(12 + 4*768) + the feature maps once
     return dict(n=B * n, steps=steps, ms_per_step=ms, kernel_ms=ms_k, launches=2 * steps,
                 bytes=B * n * (12 + 4 * Cf) + B * ncam * Cf * Hf * Wf * 4)
 
 
-def bench_occ_head(args, dev, barrier, sampler):
+def bench_occ_head(args, ctx):
     """configs/triplane_occ.py occupancy pipeline on the BASELINE lattice: decode (conversion + gather) followed by the
     Mlp head (dense_heads/mlp.py: 32 -> 64 -> 32 -> 5, three bias-free 1x1x1 convs) as ONE tensor-core kernel."""
     from efficient_multimodal_perception_b200 import ops, synth
+    dev = ctx.dev
     q = synth.occ_gt_lattice().reshape(1, -1, 3).contiguous().to(dev)
-    tri = synth.triplane_stacked(1, C_DEC, PLANE, seed=1002).to(dev)
     g = torch.Generator().manual_seed(7)
     w1 = (torch.randn(2 * C_DEC, C_DEC, 1, 1, 1, generator=g) / C_DEC ** 0.5).to(dev)
     w2 = (torch.randn(C_DEC, 2 * C_DEC, 1, 1, 1, generator=g) / (2 * C_DEC) ** 0.5).to(dev)
@@ -487,46 +542,16 @@ def bench_occ_head(args, dev, barrier, sampler):
     assert torch.equal(fused(0), both(0)), "fused decode + head differs from the two-kernel path"
     steps = max(16, min(args.steps, 200))
     out = {}
-    sampler.active.set()
+    ctx.sampler.active.set()
     for name, fn in (("head", head), ("decode_plus_head", both), ("fused", fused)):
-        barrier()
+        ctx.barrier()
         out[name] = kernel_time_ms(fn, steps, 2 * nsets)[0]  # CUDA-graph replays of 8 steps, events around each replay
-    barrier()
-    sampler.active.clear()
+    ctx.barrier()
+    ctx.sampler.active.clear()
     Q = q.shape[1]
     return dict(Q=Q, steps=steps, head_ms=out["head"], both_ms=out["decode_plus_head"], fused_ms=out["fused"],
-                head_bytes=Q * (4 * C_DEC + 4 * 5), flops=2 * Q * (C_DEC * 2 * C_DEC * 2 + C_DEC * 5))
-
-
-def bench_encode_point_sharded(args, dev, barrier, rank, world):
-    """N > 1 only: ONE 10-sweep sample (350 000 raw points) point-sharded over the ranks:
-    partial planes (-inf empties) -> NCCL all-reduce(max) of the 430 MB dense planes -> finalise."""
-    from efficient_multimodal_perception_b200 import dist as tpd
-    from efficient_multimodal_perception_b200 import synth
-    G = synth.GEOM_A
-    pts = synth.multi_sweep(10, 35000, seed=1005)[:, :3].contiguous()
-    feats = synth.point_features(pts.shape[0], G["channels"], seed=1005)
-    lo, hi = tpd.shard_bounds(pts.shape[0], rank, world)
-    my_pts, my_feats = pts[lo:hi].to(dev), feats[lo:hi].contiguous().to(dev)
-    off = synth.batch_offsets([hi - lo]).to(dev)
-
-    out = {}
-    for strategy in ("planes", "points"):
-        def step(strategy=strategy):
-            return tpd.encode_point_sharded(my_feats, my_pts, off, G["pc_range"], G["voxel_size"], G["grid_size"],
-                                            G["split"], reduce="max", strategy=strategy)
-
-        for _ in range(3):
-            step()
-        steps = max(5, min(args.steps, 30))
-
-        def run(step=step, steps=steps):
-            for _ in range(steps):
-                step()
-
-        out[strategy] = time_region(run, barrier) / steps
-    return dict(n=pts.shape[0], ms_per_step=out["planes"], ms_points=out["points"], steps=steps,
-                allreduce_bytes=4 * G["channels"] * 839680, gather_bytes=pts.shape[0] * (12 + 4 * G["channels"]))
+                head_bytes=Q * (4 * C_DEC + 4 * 5), fused_bytes=Q * (12 + 4 * 5) + 4 * C_DEC * 3 * PLANE * PLANE,
+                flops=2 * Q * (C_DEC * 2 * C_DEC * 2 + C_DEC * 5))
 
 
 def cpu_baseline_decode(q_host, budget_s=15.0):
@@ -536,205 +561,690 @@ def cpu_baseline_decode(q_host, budget_s=15.0):
     torch.set_num_threads(os.cpu_count() or 1)
     tri = synth.triplane_stacked(1, C_DEC, PLANE, seed=1002)
     pts = q_host.view(1, 1, -1, 3)
-    O.sample_points_triplane_stacked(tri, pts, OCC_LO, OCC_VS)  # warm-up
-    ts, t_start = [], time.perf_counter()
-    while len(ts) < 10 and (time.perf_counter() - t_start < budget_s or len(ts) < 2):
-        t0 = time.perf_counter()
-        ref = O.sample_points_triplane_stacked(tri, pts, OCC_LO, OCC_VS)
-        ts.append(time.perf_counter() - t0)
-    med = statistics.median(ts)
-    return dict(value=q_host.shape[1] / med, unit="queries/s", cores=torch.get_num_threads(), kind="port",
-                sample=f"{len(ts)} full passes of the {q_host.shape[1]}-query workload, median "
+    ref = O.sample_points_triplane_stacked(tri, pts, OCC_LO, OCC_VS)
+    med, n = cpu_time(lambda: O.sample_points_triplane_stacked(tri, pts, OCC_LO, OCC_VS), budget_s)
+    return dict(value=q_host.shape[1] / med, unit="queries/s", cores=os.cpu_count(), kind="port", host=host_cores(),
+                sample=f"{n} full passes of the {q_host.shape[1]}-query workload, median "
                        f"(oracle.sample_points_triplane_stacked = the reference's 3 x F.grid_sample path on torch-CPU)"), ref
 
 
-def bind_to_gpu_numa_node(local: int):
-    """Pin this rank's threads (and therefore its pinned host buffers, first-touch) to the NUMA node of its GPU:
-    the e2e leg moves ~96 MB per step over PCIe per rank and 8 ranks on the wrong socket share one inter-socket
-    link. Best effort: returns the node or None."""
-    try:
-        bus = torch.cuda.get_device_properties(local).pci_bus_id
-        dom = torch.cuda.get_device_properties(local).pci_domain_id
-        dev_id = torch.cuda.get_device_properties(local).pci_device_id
-        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0/numa_node"
-        node = int(open(path).read().strip())
-        if node < 0:
-            return None
-        cpus = set()
-        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
-            lo, _, hi = part.partition("-")
-            cpus.update(range(int(lo), int(hi or lo) + 1))
-        cpus &= os.sched_getaffinity(0)
-        if cpus:
-            os.sched_setaffinity(0, cpus)
-            return node
-    except Exception:
-        pass
-    return None
+def decode_config(args, Q, world, nsets=None):
+    return {"workload": f"configs/triplane_occ.py occupancy decode: {Q} voxel queries ({args.queries}) "
+                        f"x C={C_DEC} from 3 fp32 {PLANE}x{PLANE} triplanes, bs=1 per GPU",
+            "queries": args.queries, "Q": Q, "C": C_DEC, "planes": [PLANE, PLANE],
+            "query_tensor": (f"[1,{','.join(map(str, QUERY_DIMS[args.queries]))},3] through the 5-D entry point "
+                             "tp_sample3_grid_nhwc_f32 (per-block lattice detection on the device)"
+                             if QUERY_DIMS[args.queries] else "[1,Q,3] point list through tp_sample3_nhwc_f32"),
+            "step": "NCHW->NHWC conversion of the 3 planes (1 launch) + fused gather kernel (1 launch), CUDA-graph replay",
+            "l2": "rotating buffer sets, total footprint > 3x L2 (no flush kernel)",
+            "parallelism": f"queries sharded over {world} GPU(s), no collective"}
+
+
+def workload_decode(ctx):
+    args, dev, world = ctx.args, ctx.dev, ctx.world
+    dec = bench_decode_device(args, dev, ctx.barrier, ctx.sampler)
+    lift = bench_lift(args, ctx)
+    occ = bench_occ_head(args, ctx)
+    ms_total, k_avg, lift_ms, lift_k_ms = ctx.max_over_ranks(dec["ms_total"], dec["kernel_ms_avg"], lift["ms_per_step"], lift["kernel_ms"])
+    q_host = decode_queries(args.queries)
+    e2e = bench_decode_e2e(args, q_host, ctx)
+    e2e_head = bench_decode_head_e2e(args, ctx) if args.queries == "lattice640k" else None
+    if ctx.rank != 0:
+        return None
+    peak = ctx.peak
+    Q = dec["Q"]
+    ms_per_step = ms_total / args.steps
+    qps = world * Q * args.steps / (ms_total * 1e-3)
+    kbytes = decode_bytes(Q)
+    kernel_name = ("tp::sample3_grid_kernel<0,8,8,false>" if QUERY_DIMS[args.queries] else "tp::sample3_kernel<0,8>")
+    cpu, parity, torch_ms = None, None, None
+    if world == 1:
+        cpu, ref = cpu_baseline_decode(q_host, 10.0)
+        # live parity check of what was just timed (device result of set 0 and the e2e result)
+        tri0, q0, out0 = dec["sets"].sets[0]
+        dec["sets"].step(0)
+        torch.cuda.synchronize()
+        scale = float(ref.abs().max())
+        torch_ms = torch_cuda_decode(q0, tri0)
+        out_cpu_arith = dec["sets"].ops.sample3(tri0, q0, OCC_LO, OCC_VS, OCC_HALF, arith="cpu", grid_dims=QUERY_DIMS[args.queries])
+        parity = {"note": "oracle = torch-CPU op chain; arith='cpu' replays it, the timed arith='cuda' replays "
+                          "torch-CUDA's (x * fp32(1/vs)) and is checked bitwise-level against torch-CUDA in tests/",
+                  "device_cpu_arith_vs_oracle_normwise": float((out_cpu_arith.cpu() - ref[:, :, 0]).abs().max()) / scale,
+                  "device_vs_oracle_normwise": float((out0.cpu() - ref[:, :, 0]).abs().max()) / scale,
+                  "e2e_vs_oracle_normwise": float((e2e["out"] - ref[:, :, 0]).abs().max()) / scale, "bar": 1e-5}
+        assert parity["device_cpu_arith_vs_oracle_normwise"] <= 1e-5, parity
+    cfg = decode_config(args, Q, world)
+    line = {
+        "metric": "triplane decode queries/s (3-plane bilinear sample + sum, triplane_occ occupancy decode)",
+        "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": cfg,
+        "roofline": dict(ctx.roofline(kbytes, k_avg), kernel=kernel_name,
+                         traffic=profile_traffic(kernel_name.split("<")[0].replace("tp::", ""), args.queries),
+                         traffic_source="profiles/ (ncu --set full capture of the same kernel and inputs; not re-measured in this run)",
+                         kernel_ms_avg=k_avg, kernel_ms_median=dec["kernel_ms_med"], kernel_ms_min=dec["kernel_ms_min"],
+                         step_frac=kbytes / (ms_per_step * 1e-3) / 1e9 / peak),
+        "cpu_baseline": cpu,
+        "torch_cuda_reference": (None if torch_ms is None else {
+            "value": Q / (torch_ms * 1e-3), "unit": "queries/s", "ms_per_step": torch_ms,
+            "what": "the reference's op sequence (normalise + 3 x F.grid_sample + sum) run by torch-CUDA on this GPU, "
+                    "same queries and planes; reported, not a target"}),
+        "e2e": {"value": world * Q / (e2e["ms"] * 1e-3), "unit": "queries/s",
+                "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e["ms"],
+                "steps": e2e["steps"], "cpu_binding": ctx.numa,
+                "api": "tp_sample3_grid_host_f32 / tp_sample3_host_f32 (C ABI, pinned host buffers; H2D planes+queries, "
+                       "D2H full result, synchronised every step)"},
+        "gpu_launches": dec["launches"],
+        "variants_kernel_only": {k: dict(v, frac=v["achieved_gbs"] / peak) for k, v in dec["variants"].items()},
+        "parity": parity,
+    }
+    if e2e_head:
+        line["e2e_decode_plus_head"] = {
+            "value": world * e2e_head["Q"] / (e2e_head["ms"] * 1e-3), "unit": "queries/s", "ms_per_step": e2e_head["ms"],
+            "h2d_bytes_per_step": e2e_head["h2d"], "d2h_bytes_per_step": e2e_head["d2h"], "steps": e2e_head["steps"],
+            "api": "efficient_multimodal_perception_b200.ops.sample3_head with pinned host tensors: the occupancy consumer (Mlp head) "
+                   "runs on the device, only the [5,Q] logits return (PCIe: 20 MB per step instead of 96 MB)"}
+    line["lift"] = {
+        "metric": "camera->point lift points/s (point_to_cam: 6 cameras x [768,16,32] maps, bilinear gather + camera sum)",
+        "value": world * lift["n"] / (lift_ms * 1e-3), "unit": "points/s", "ms_per_step": lift_ms,
+        "kernel_ms": lift_k_ms, "workload": "bs=2 x 34720 pts per GPU, Cf=768; step = channels-last copy + lift kernel",
+        "roofline": dict(ctx.roofline(lift["bytes"], lift_k_ms), note="lift kernel alone (events around the loop of launches)"),
+        "steps": lift["steps"], "gpu_launches": lift["launches"]}
+    line["occupancy_head"] = {
+        "metric": "Mlp occupancy head queries/s (32 -> 64 -> 32 -> 5 per query, fused on the tensor cores: tcgen05 "
+                  "kind::tf32, TMEM accumulators) and decode + head",
+        "value": world * occ["Q"] / (occ["head_ms"] * 1e-3), "unit": "queries/s", "ms_per_step": occ["head_ms"],
+        "decode_plus_head_ms": occ["both_ms"], "decode_plus_head_queries_per_s": world * occ["Q"] / (occ["both_ms"] * 1e-3),
+        "fused_decode_head_ms": occ["fused_ms"],
+        "fused_decode_head_queries_per_s": world * occ["Q"] / (occ["fused_ms"] * 1e-3),
+        "fused_roofline": ctx.roofline(occ["fused_bytes"], occ["fused_ms"]),
+        "fused_note": "tp_sample3_grid_head_tf32: layout conversion + ONE kernel from planes and queries to logits (the "
+                      "[B,32,Q] features never reach HBM); bit-identical to decode_plus_head (asserted in this run); "
+                      "every leg: CUDA-graph replays over 4 rotating buffer sets (> 3x L2), layout conversion included",
+        "workload": f"{occ['Q']} queries (640k lattice), C=32, 5 classes; per-rank numbers, no cross-rank max",
+        "roofline": dict(ctx.roofline(occ["head_bytes"], occ["head_ms"]), tensor_tflops=occ["flops"] / (occ["head_ms"] * 1e-3) / 1e12,
+                         note="HBM-bound by a wide margin: 8.5 kflop per 148 bytes; the tensor cores are there to keep "
+                              "the 2C / C wide intermediates on the SM, not for their peak"),
+        "steps": occ["steps"], "gpu_launches": occ["steps"]}
+    return line
+
+
+# --------------------------------------------------------------------------------------------------
+# encode (configs[0]) at geometry A (config-exact) and B (BASELINE-named)
+# --------------------------------------------------------------------------------------------------
+def inside_mask(pts, rng):
+    return ((pts[:, 0] > rng[0]) & (pts[:, 0] < rng[3]) & (pts[:, 1] > rng[1]) & (pts[:, 1] < rng[4]) &
+            (pts[:, 2] > rng[2]) & (pts[:, 2] < rng[5]))
+
+
+def encode_cells(G):
+    from efficient_multimodal_perception_b200 import ops
+    pool = ops.pool_kernels(G["grid_size"], G["split"])
+    P = ops.pooled_sizes(G["grid_size"], pool)
+    X, Y, Z = G["grid_size"]
+    return X * Y * P[2] + Y * Z * P[0] + X * Z * P[1]
+
+
+def torch_encode_chain(feats, ind4, G, B):
+    """The reference's op chain (point_triplane_projector.py:99-115) with torch ops on whatever device the inputs live
+    on: torch.unique(dim=0) -> scatter amax per voxel (torch_scatter.scatter_max) -> three pooled dense tensors
+    (SparseMaxPool3d + .dense(): idx // k, zero fill) -> permute + flatten copies. Baseline beside the fused kernel."""
+    from efficient_multimodal_perception_b200 import ops
+    Cc = feats.shape[1]
+    grid = G["grid_size"]
+    pool = ops.pool_kernels(grid, G["split"])
+    P = ops.pooled_sizes(grid, pool)
+    unq, inv = torch.unique(ind4, return_inverse=True, dim=0)
+    vox = torch.zeros((unq.shape[0], Cc), device=feats.device).scatter_reduce_(0, inv[:, None].expand(-1, Cc), feats, "amax",
+                                                                               include_self=False)
+    u = unq.long()
+    outs = []
+    for axis, perm in ((2, (0, 2, 3, 4, 1)), (0, (0, 3, 4, 2, 1)), (1, (0, 2, 4, 3, 1))):
+        dims = [grid[0], grid[1], grid[2]]
+        dims[axis] = P[axis]
+        c = [u[:, 1], u[:, 2], u[:, 3]]
+        c[axis] = c[axis] // pool[axis]
+        ok = c[axis] < P[axis]
+        lin = ((u[:, 0] * dims[0] + c[0]) * dims[1] + c[1]) * dims[2] + c[2]
+        dense = torch.zeros((B * dims[0] * dims[1] * dims[2], Cc), device=feats.device)
+        dense.scatter_reduce_(0, lin[ok][:, None].expand(-1, Cc), vox[ok], "amax", include_self=False)
+        ncdhw = dense.view(B, dims[0], dims[1], dims[2], Cc).permute(0, 4, 1, 2, 3).contiguous()  # what .dense() returns
+        outs.append(ncdhw.permute(*perm).flatten(start_dim=3).contiguous())
+    return outs
+
+
+def workload_encode(ctx, geom_name="A"):
+    from efficient_multimodal_perception_b200 import _lib as L
+    from efficient_multimodal_perception_b200 import ops, synth
+    args, dev, world = ctx.args, ctx.dev, ctx.world
+    G = synth.GEOM_A if geom_name == "A" else synth.GEOM_B
+    n, Cc = 34720, G["channels"]
+    pts = synth.lidar_sweep(n, seed=1001)
+    xyz_h = pts[:, :3].contiguous()
+    feats_h = synth.point_features(n, Cc, seed=1001)
+    xyz, feats = xyz_h.to(dev), feats_h.to(dev)
+    off = synth.batch_offsets([n]).to(dev)
+    inside = int(inside_mask(pts, G["pc_range"]).sum())
+    cells = encode_cells(G)
+    nbytes = n * 12 + inside * 4 * Cc + 4 * Cc * cells  # SURVEY 8(d)
+
+    def step():
+        return ops.encode(feats, off, G["pc_range"], G["voxel_size"], G["grid_size"], G["split"], points=xyz)
+
+    steps = max(10, min(args.steps, 200))
+    ms = time_steps(step, steps, max(3, min(args.warmup, 10)), ctx)
+    (ms,) = ctx.max_over_ranks(ms)
+    # e2e: host buffers through the C ABI
+    lib = L.lib()
+    geom = L.make_geom(G["pc_range"], G["voxel_size"], G["grid_size"], ops.pool_kernels(G["grid_size"], G["split"]))
+    X, Y, Z = G["grid_size"]
+    P = ops.pooled_sizes(G["grid_size"], ops.pool_kernels(G["grid_size"], G["split"]))
+    xyz_p, feats_p = xyz_h.pin_memory(), feats_h.pin_memory()
+    off_h = synth.batch_offsets([n])
+    outs_h = [torch.empty(s).pin_memory() for s in ((1, X, Y, P[2] * Cc), (1, Y, Z, P[0] * Cc), (1, X, Z, P[1] * Cc))]
+
+    def call():
+        L.check(lib.tp_encode_host_f32(feats_p.data_ptr(), Cc, xyz_p.data_ptr(), 3, n, off_h.data_ptr(), 1, C.byref(geom),
+                                       L.TP_ARITH_TORCH_CUDA, L.TP_REDUCE_MAX, 0, outs_h[0].data_ptr(), outs_h[1].data_ptr(),
+                                       outs_h[2].data_ptr()), "tp_encode_host_f32")
+
+    e2e_steps = max(3, min(args.steps, 20))
+    e2e_ms = e2e_time(call, e2e_steps, ctx)
+    if ctx.rank != 0:
+        return None
+    cpu = torch_gpu = parity = None
+    if world == 1:
+        from oracle import triplane_oracle as O
+        torch.set_num_threads(os.cpu_count() or 1)
+
+        def cpu_chain():
+            cropped, ind = O.voxelize_points([pts], G["pc_range"], G["voxel_size"])
+            return O.encode_pooled(feats_h[inside_mask(pts, G["pc_range"])], O.cat_indices(ind), G["grid_size"], G["split"], 1)
+
+        ref = cpu_chain()
+        med, npass = cpu_time(cpu_chain, 6.0, 6)
+        cpu = dict(value=n / med, unit="points/s", cores=os.cpu_count(), kind="port", host=host_cores(),
+                   sample=f"{npass} full passes of the 1-sweep workload ({n} raw points), median: oracle.voxelize_points + "
+                          f"oracle.encode_pooled (torch.unique + scatter amax + 3 pooled dense tensors + permute/flatten) on torch-CPU")
+        # parity of what was timed: arith='cpu' replays the oracle's (torch-CPU) index chain bit for bit
+        got_cpu = ops.encode(feats, off, G["pc_range"], G["voxel_size"], G["grid_size"], G["split"], points=xyz, arith="cpu")
+        exact = all(torch.equal(a.cpu(), b) for a, b in zip(got_cpu, ref[:3]))
+        assert exact, "encode (arith='cpu') differs from the oracle"
+        got = step()
+        e2e_equal = all(torch.equal(a.cpu(), b) for a, b in zip(got, outs_h))
+        assert e2e_equal, "tp_encode_host_f32 differs from the device path"
+        diff_cells = sum(int(((a.cpu() != b).view(-1, Cc).any(1)).sum()) for a, b in zip(got, ref[:3]))
+        parity = {"device_cpu_arith_bit_exact_vs_oracle": exact, "e2e_equals_device": e2e_equal,
+                  "cells_differing_cuda_arith_vs_cpu_oracle": diff_cells,
+                  "note": "arith='cuda' (timed) replays torch-CUDA's x * fp32(1/vs): a handful of points on voxel boundaries index "
+                          "differently from torch-CPU's true division (SURVEY 7); bit-exact vs torch-CUDA in tests/"}
+        # the reference op chain run by torch-CUDA on this GPU
+        keep, idx = ops.voxel_index(xyz, G["pc_range"], G["voxel_size"])
+        k = keep.bool()
+        ind4 = torch.cat([torch.zeros((int(k.sum()), 1), dtype=torch.int32, device=dev), idx[k]], 1)
+        inb = ((ind4[:, 1:] >= 0) & (ind4[:, 1:] < torch.tensor(G["grid_size"], device=dev))).all(1)
+        f_in, ind4 = feats[k][inb], ind4[inb]
+        chain_out = torch_encode_chain(f_in, ind4, G, 1)
+        assert all(torch.equal(a, b) for a, b in zip(chain_out, got)), "torch-CUDA op chain differs from the fused encode"
+        t_ms = gpu_chain_ms(lambda: torch_encode_chain(f_in, ind4, G, 1), 5)
+        torch_gpu = {"value": n / (t_ms * 1e-3), "unit": "points/s", "ms_per_step": t_ms,
+                     "what": "torch.unique(dim=0) + scatter_reduce(amax) + 3 x (pooled dense scatter + .dense()-style NCDHW copy + "
+                             "permute/flatten copy) run by torch-CUDA on this GPU on the already cropped / indexed points; equal "
+                             "to the fused encode's output (asserted); reported, not a target"}
+    label = ("configs/point_triplane.py" if geom_name == "A" else "BASELINE 200x200x16")
+    return {
+        "metric": "triplane encode points/s (fused crop + voxel index + scatter-max into the three dense pooled planes)",
+        "value": world * n / (ms * 1e-3), "unit": "points/s", "n_gpus": world, "steps": steps, "warmup": max(3, min(args.warmup, 10)),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{label} geometry {X}x{Y}x{Z}, pool {'/'.join(map(str, ops.pool_kernels(G['grid_size'], G['split'])))}, "
+                               f"C={Cc}: 1 synthetic nuScenes sweep, {n} raw points ({inside} in range), bs=1 per GPU, {cells} pooled cells "
+                               f"dense out ({4 * Cc * cells / 1e6:.0f} MB)", "geometry": geom_name, "N": n, "N_in_range": inside, "cells": cells,
+                   "step": "count + alloc + fill + reduce (4 launches), raw points in (crop + index fused)",
+                   "l2": f"every step writes {4 * Cc * cells / 1e6:.0f} MB (> 3x L2): nothing survives in L2 between steps",
+                   "parallelism": f"samples sharded over {world} GPU(s), no collective"},
+        "roofline": dict(ctx.roofline(nbytes, ms), kernel="tp::encode_reduce_kernel<0> (+ count / alloc / fill)",
+                         traffic=profile_traffic("encode_reduce_kernel", "S1_geomA_C128") if geom_name == "A" else None,
+                         note="whole 4-launch step against the byte model N*12 + N'*4C + 4C*cells"),
+        "cpu_baseline": cpu, "torch_cuda_reference": torch_gpu,
+        "e2e": {"value": world * n / (e2e_ms * 1e-3), "unit": "points/s", "ms_per_step": e2e_ms, "steps": e2e_steps,
+                "h2d_bytes_per_step": n * 12 + n * Cc * 4 + 16, "d2h_bytes_per_step": 4 * Cc * cells,
+                "api": "tp_encode_host_f32 (C ABI, pinned host buffers: points + features up, the three dense planes down)"},
+        "gpu_launches": 4 * steps, "parity": parity}
+
+
+# --------------------------------------------------------------------------------------------------
+# surf_sam (configs[2]): bs=8 range-image points + SAM subsets + surface-query neighbourhood search
+# --------------------------------------------------------------------------------------------------
+def sam_points(batch, seed, keep=0.25):
+    """bs sweeps of 11-float points whose 6 SAM label columns are positive for ~15 % of the points per camera (a camera
+    sees ~1/6 of the sweep): subsets of ~3-6 k points per (sample, camera), SURVEY 8(d) S3."""
+    from efficient_multimodal_perception_b200 import synth
+    out = []
+    for b in range(batch):
+        p = synth.lidar_sweep(34720, seed=seed + b)
+        g = torch.Generator().manual_seed(seed * 7 + b)
+        p[:, 5:][torch.rand(p.shape[0], 6, generator=g) > keep] = 0.0
+        out.append(p)
+    return out
+
+
+def workload_surf_sam(ctx):
+    import efficient_multimodal_perception_b200 as emp
+    from efficient_multimodal_perception_b200 import ops, synth
+    import torch.nn.functional as F
+    args, dev, world = ctx.args, ctx.dev, ctx.world
+    B = 8
+    G = synth.GEOM_A
+    lo, vs = G["pc_range"], G["voxel_size"]
+    tri_h = synth.triplane_stacked(B, C_DEC, PLANE, seed=1003)
+    rp_h = synth.range_image_points(B, seed=1003)                      # [8,32,1024,3]
+    pts_h = sam_points(B, 1003)
+    tri, rp = tri_h.to(dev), rp_h.to(dev)
+    pts = [p.to(dev) for p in pts_h]
+    coords, labels, bidx = emp.sam_subsets(pts, lo)
+    sizes = [int(c.shape[0]) for c in coords]
+    q_cat = torch.cat(coords).contiguous()
+    seg_off = synth.batch_offsets(sizes).to(dev)
+    seg_b = torch.tensor(bidx, dtype=torch.int32, device=dev)
+    Q_range, Q_seg = B * rp.shape[1] * rp.shape[2], int(sum(sizes))
+    half = [PLANE / 2] * 3
+    # surface branch: 2048 non-manifold queries per sample against the sample's non-empty range pixels, r = 1.0
+    mask = (rp == 0).sum(-1) != 3
+    src = [rp[b][mask[b]] for b in range(B)]
+    gq = torch.Generator().manual_seed(1003)
+    qry = [s[torch.randperm(s.shape[0], generator=gq)[:2048].to(dev)] + 0.1 * torch.randn(2048, 3, generator=gq).to(dev) for s in src]
+    x_cat, y_cat = torch.cat(src).contiguous(), torch.cat(qry).contiguous()
+    x_off = synth.batch_offsets([s.shape[0] for s in src]).to(dev)
+    y_off = synth.batch_offsets([2048] * B).to(dev)
+
+    def step():
+        nhwc = ops.planes_to_channels_last([tri[:, 0], tri[:, 1], tri[:, 2]])
+        a = ops.sample3(nhwc, rp.view(B, -1, 3), lo[:3], vs, half, channels_last=True)
+        b = ops.sample3_segments(nhwc, q_cat, seg_off, seg_b, lo[:3], vs, half, channels_last=True)
+        return a, b
+
+    steps = max(10, min(args.steps, 200))
+    ms = time_steps(step, steps, 5, ctx)
+    ms_radius = time_steps(lambda: ops.radius(x_cat, x_off, y_cat, y_off, 1.0, 32), max(5, min(args.steps, 50)), 3, ctx)
+    ms, ms_radius = ctx.max_over_ranks(ms, ms_radius)
+    # e2e through the Python API with pinned host tensors
+    q_cat_h = q_cat.cpu().pin_memory()
+    tri_p, rp_p = tri_h.pin_memory(), rp_h.pin_memory()
+    out_a = torch.empty(B, C_DEC, rp.shape[1] * rp.shape[2]).pin_memory()
+    out_b = torch.empty(Q_seg, C_DEC).pin_memory()
+
+    def call():
+        t = tri_p.to(dev, non_blocking=True)
+        r = rp_p.to(dev, non_blocking=True)
+        qc = q_cat_h.to(dev, non_blocking=True)
+        nhwc = ops.planes_to_channels_last([t[:, 0], t[:, 1], t[:, 2]])
+        out_a.copy_(ops.sample3(nhwc, r.view(B, -1, 3), lo[:3], vs, half, channels_last=True), non_blocking=True)
+        out_b.copy_(ops.sample3_segments(nhwc, qc, seg_off, seg_b, lo[:3], vs, half, channels_last=True), non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_steps = max(3, min(args.steps, 30))
+    e2e_ms = e2e_time(call, e2e_steps, ctx)
+    if ctx.rank != 0:
+        return None
+    Q = Q_range + Q_seg
+    nbytes = Q * (12 + 4 * C_DEC) + B * 4 * C_DEC * 3 * PLANE * PLANE
+    cpu = torch_gpu = parity = None
+    if world == 1:
+        from oracle import triplane_oracle as O
+        torch.set_num_threads(os.cpu_count() or 1)
+
+        def cpu_chain():
+            a = O.sample_points_triplane_stacked(tri_h, rp_h, lo[:3], vs)
+            b = O.contrastive_features(lambda t, c: O.sample_points_triplane_stacked(t, c, lo[:3], vs), tri_h, pts_h, lo)
+            return a, b
+
+        ref_a, ref_b = cpu_chain()
+        med, npass = cpu_time(cpu_chain, 6.0, 6)
+        cpu = dict(value=Q / med, unit="queries/s", cores=os.cpu_count(), kind="port", host=host_cores(),
+                   sample=f"{npass} full passes, median: oracle.sample_points_triplane_stacked on [8,32,1024,3] + the reference's "
+                          f"per-(sample, camera) loop (oracle.contrastive_features, {len(sizes)} subsets) on torch-CPU")
+        nhwc = ops.planes_to_channels_last([tri[:, 0], tri[:, 1], tri[:, 2]])
+        got_a = ops.sample3(nhwc, rp.view(B, -1, 3), lo[:3], vs, half, channels_last=True, arith="cpu").view(B, C_DEC, 32, 1024)
+        got_b = ops.sample3_segments(nhwc, q_cat, seg_off, seg_b, lo[:3], vs, half, channels_last=True, arith="cpu")
+        scale = float(ref_a.abs().max())
+        err_a = float((got_a.cpu() - ref_a).abs().max()) / scale
+        err_b = float((got_b.cpu() - torch.cat([f for f, _ in ref_b])).abs().max()) / scale
+        assert len(ref_b) == len(sizes) and err_a <= 1e-5 and err_b <= 1e-5, (err_a, err_b)
+        rr, rc = O.radius(x_cat.cpu()[: int(x_off[1])], y_cat.cpu()[:2048], 1.0, torch.zeros(int(x_off[1]), dtype=torch.long),
+                          torch.zeros(2048, dtype=torch.long))
+        col, cnt = ops.radius(x_cat, x_off, y_cat, y_off, 1.0, 32)
+        radius_pairs_match = int(cnt[:2048].sum()) == rr.numel() and torch.equal(col[:2048][col[:2048] >= 0].cpu().long(), rc)
+        parity = {"range_points_vs_oracle_normwise": err_a, "segments_vs_reference_loop_normwise": err_b, "bar": 1e-5,
+                  "radius_sample0_pairs_equal_restatement": bool(radius_pairs_match)}
+
+        def gpu_chain():  # the reference's own ops on this GPU: one 3 x grid_sample call + the per-subset loop
+            def samp(t, p):
+                v = torch.zeros_like(p)
+                for a in range(3):
+                    v[..., a] = (p[..., a] - lo[a]) / vs[a]
+                v = v / half[0] - 1
+                return (F.grid_sample(t[:, 0], v[..., [0, 1]], align_corners=False) + F.grid_sample(t[:, 1], v[..., [1, 2]], align_corners=False)
+                        + F.grid_sample(t[:, 2], v[..., [0, 2]], align_corners=False))
+            samp(tri, rp)
+            for c, b in zip(coords, bidx):
+                samp(tri[b][None], c[None, None]).squeeze().permute(1, 0)
+
+        t_ms = gpu_chain_ms(gpu_chain, 3)
+        torch_gpu = {"value": Q / (t_ms * 1e-3), "unit": "queries/s", "ms_per_step": t_ms,
+                     "what": f"the reference's ops run by torch-CUDA on this GPU: one stacked sample_points_triplane call + {len(sizes)} "
+                             "per-(sample, camera) calls (subsets pre-built); reported, not a target"}
+    return {
+        "metric": "triplane decode queries/s, pre-training batch (range-image points + SAM-cluster subsets)",
+        "value": world * Q / (ms * 1e-3), "unit": "queries/s", "n_gpus": world, "steps": steps, "warmup": 5, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"configs/triplane_surf_sam.py pre-training, bs={B} per GPU: range_points [8,32,1024,3] ({Q_range} queries, ~30 % "
+                               f"empty pixels) + {len(sizes)} per-(sample, camera) SAM-labelled subsets ({Q_seg} queries, {min(sizes)}-{max(sizes)} each), "
+                               f"stacked triplane [8,3,32,128,128]", "Q_range": Q_range, "Q_segments": Q_seg, "segments": len(sizes), "C": C_DEC,
+                   "step": "NCHW->NHWC conversion (1 launch) + per-query kernel on the range points (1 launch) + ONE segment launch for all subsets",
+                   "l2": f"per step {nbytes / 1e6:.0f} MB of algorithmic traffic incl. 50 MB of planes converted every step; inputs are not rotated "
+                         "(planes are meant to be L2-resident during the gathers)",
+                   "parallelism": f"samples sharded over {world} GPU(s), no collective"},
+        "roofline": dict(ctx.roofline(nbytes, ms), kernel="tp::sample3_kernel<0,8> + tp::sample3_seg_kernel<0,false> + nchw_to_nhwc3_kernel",
+                         traffic=None, note="whole 3-launch step against Q*(12+4C) + planes"),
+        "cpu_baseline": cpu, "torch_cuda_reference": torch_gpu,
+        "e2e": {"value": world * Q / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms, "steps": e2e_steps,
+                "h2d_bytes_per_step": tri_h.numel() * 4 + rp_h.numel() * 4 + q_cat_h.numel() * 4, "d2h_bytes_per_step": (out_a.numel() + out_b.numel()) * 4,
+                "api": "ops.sample3 + ops.sample3_segments with pinned host tensors (planes, range points and subset coordinates up, both feature "
+                       "tensors down), synchronised every step"},
+        "gpu_launches": 3 * steps, "parity": parity,
+        "surface_radius_search": {"ms_per_step": ms_radius, "queries": B * 2048, "sources": int(x_cat.shape[0]), "r": 1.0, "max_num_neighbors": 32,
+                                  "queries_per_s": world * B * 2048 / (ms_radius * 1e-3),
+                                  "what": "InterpNet neighbourhood search (interpnet.py:65) for 2048 surface queries per sample, one launch (tp_radius_i32)"}}
+
+
+# --------------------------------------------------------------------------------------------------
+# range_cam (configs[3]): bs=8 voxelize -> lift -> projector; + interact / pixel scatter
+# --------------------------------------------------------------------------------------------------
+def workload_range_cam(ctx):
+    import efficient_multimodal_perception_b200 as emp
+    from efficient_multimodal_perception_b200 import ops, synth
+    args, dev, world = ctx.args, ctx.dev, ctx.world
+    B, ncam, Cf, Hf, Wf, n = 8, 6, 768, 16, 32, 34720
+    G = synth.GEOM_A
+    Cc = G["channels"]
+    rig = synth.camera_rig(1004)
+    metas = [dict(img_shape=rig.img_shape, lidar2image=rig.lidar2image.numpy(), imgs_aug=rig.imgs_aug) for _ in range(B)]
+    pts_h = [synth.lidar_sweep(n, seed=1004 + b) for b in range(B)]
+    img_h = torch.randn(B, ncam, Cf, Hf, Wf, generator=torch.Generator().manual_seed(1004))
+    torch.manual_seed(1004)
+    proj = emp.PointTriplaneProjector(G["grid_size"], in_channels=5, out_channels=Cc, base_channels=Cc, split=G["split"]).eval()
+    proj_dev = emp.PointTriplaneProjector(G["grid_size"], in_channels=5, out_channels=Cc, base_channels=Cc, split=G["split"]).eval().to(dev)
+    proj_dev.load_state_dict(proj.state_dict())
+    pts = [p.to(dev) for p in pts_h]
+    img = img_h.to(dev)
+    stage = {}
+
+    @torch.no_grad()
+    def step(timed=False):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timed else None
+        if timed:
+            ev[0].record()
+        cropped, grid_ind = emp.voxelize_points(pts, G["pc_range"], G["voxel_size"])
+        if timed:
+            ev[1].record()
+        cam = emp.point_to_cam(cropped, img, metas)
+        if timed:
+            ev[2].record()
+        out = proj_dev(cropped, grid_ind, cam)
+        if timed:
+            ev[3].record()
+            torch.cuda.synchronize()
+            for k, name in enumerate(("voxelize_ms", "lift_ms", "projector_ms")):
+                stage[name] = ev[k].elapsed_time(ev[k + 1])
+        return out, cropped
+
+    steps = max(5, min(args.steps, 30))
+    ms = time_steps(step, steps, 3, ctx)
+    out, cropped = step(timed=True)
+    n_in = int(sum(c.shape[0] for c in cropped))
+    # encode alone inside the projector, for the breakdown
+    with torch.no_grad():
+        f_cat = proj_dev.point_features(cropped, emp.point_to_cam(cropped, img, metas))
+        _, gi = emp.voxelize_points(pts, G["pc_range"], G["voxel_size"])
+        off = synth.batch_offsets([g.shape[0] for g in gi]).to(dev)
+        cat_ind = torch.cat(gi)
+        enc_ms = time_steps(lambda: ops.encode(f_cat, off, [0] * 6, (1, 1, 1), G["grid_size"], G["split"], grid_ind=cat_ind), 10, 2, ctx)
+    # SURVEY 8f #4 rows this config runs: interact + camera-pixel scatter at bs=8
+    Ci, Hi, Wi = 192, 32, 64
+    rp = synth.range_image_points(B, seed=1004).to(dev)
+    rimg = rp.norm(dim=-1)[:, None].contiguous()
+    rimg[torch.rand(rimg.shape, generator=torch.Generator().manual_seed(5)).to(dev) < 0.4] = 0
+    imgf = torch.randn(B, ncam, Ci, Hi, Wi, generator=torch.Generator().manual_seed(6)).to(dev)
+    pe = torch.nn.Sequential(torch.nn.Linear(3, 4 * Ci), torch.nn.ReLU(), torch.nn.Linear(4 * Ci, Ci)).to(dev)
+    with torch.no_grad():
+        inter_ms = time_steps(lambda: emp.interact(imgf, rimg, metas, rp, pe), 10, 2, ctx)
+        _, _, coors = emp.interact(imgf, rimg, metas, rp, pe)
+        feat32 = torch.randn(B, C_DEC, 32, 1024, generator=torch.Generator().manual_seed(7)).to(dev)
+        H, W = rig.img_shape[::-1]
+        scat_ms = time_steps(lambda: emp.cam_proj_feat(feat32, coors, (H, W)), 10, 2, ctx)
+    ms, enc_ms, inter_ms, scat_ms = ctx.max_over_ranks(ms, enc_ms, inter_ms, scat_ms)
+    # e2e: module API, pinned host inputs, the three planes come back
+    pts_p = [p.pin_memory() for p in pts_h]
+    img_p = img_h.pin_memory()
+    outs_h = [torch.empty(o.shape).pin_memory() for o in out]
+
+    @torch.no_grad()
+    def call():
+        pd = [p.to(dev, non_blocking=True) for p in pts_p]
+        im = img_p.to(dev, non_blocking=True)
+        cr, gi2 = emp.voxelize_points(pd, G["pc_range"], G["voxel_size"])
+        o = proj_dev(cr, gi2, emp.point_to_cam(cr, im, metas))
+        for h, d in zip(outs_h, o):
+            h.copy_(d, non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_steps = max(3, min(args.steps, 10))
+    e2e_ms = e2e_time(call, e2e_steps, ctx)
+    if ctx.rank != 0:
+        return None
+    cells = encode_cells(G)
+    lift_bytes = n_in * (12 + 4 * Cf) + B * ncam * Cf * Hf * Wf * 4
+    enc_bytes = n_in * 12 + n_in * 4 * Cc + 4 * Cc * cells * B
+    vox_bytes = B * n * 44 + n_in * (44 + 12)
+    nbytes = vox_bytes + lift_bytes + enc_bytes
+    cpu = parity = None
+    if world == 1:
+        from oracle import triplane_oracle as O
+        torch.set_num_threads(os.cpu_count() or 1)
+
+        @torch.no_grad()
+        def cpu_chain(nb=1):
+            cr, gi2 = O.voxelize_points(pts_h[:nb], G["pc_range"], G["voxel_size"])
+            cam = O.point_to_cam([c.clone() for c in cr], img_h[:nb], metas[:nb])
+            f = proj.point_features(cr, cam)
+            xy, yz, xz, _, _ = O.encode_pooled(f, O.cat_indices(gi2), G["grid_size"], G["split"], nb)
+            return [proj.mlp_xy(xy).permute(0, 3, 1, 2), proj.mlp_yz(yz).permute(0, 3, 1, 2), proj.mlp_xz(xz).permute(0, 3, 1, 2)]
+
+        ref = cpu_chain()
+        med, npass = cpu_time(cpu_chain, 6.0, 4)
+        cpu = dict(value=n / med, unit="points/s", cores=os.cpu_count(), kind="port", host=host_cores(),
+                   sample=f"{npass} passes over ONE of the {B} samples ({n} raw points), median: oracle.voxelize_points + oracle.point_to_cam + "
+                          "the module's own Linear/BatchNorm layers + oracle.encode_pooled on torch-CPU (the reference's forward with its two "
+                          "third-party ops restated)")
+        with torch.no_grad():  # arith='cpu' replays the oracle's torch-CPU index / projection chains (the timed path replays torch-CUDA's)
+            cr0, gi0 = emp.voxelize_points(pts[:1], G["pc_range"], G["voxel_size"], arith="cpu")
+            out0 = proj_dev(cr0, gi0, emp.point_to_cam(cr0, img[:1], metas[:1], arith="cpu"))
+        errs = [float((a.cpu() - b).abs().max() / b.abs().max()) for a, b in zip(out0, ref)]
+        assert max(errs) <= 1e-3, errs
+        parity = {"planes_sample0_vs_oracle_pipeline_normwise": errs, "bar": 1e-3,
+                  "note": "end of a 6-layer fp32 pipeline (torch-CUDA cuBLAS linears vs torch-CPU): scatter-max itself is bit-exact (tests/)"}
+    return {
+        "metric": "PointTriplane lift + encode points/s (voxelize_points -> point_to_cam -> PointTriplaneProjector.forward)",
+        "value": world * B * n / (ms * 1e-3), "unit": "points/s", "n_gpus": world, "steps": steps, "warmup": 3, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"configs/triplane_range_cam.py shapes on the PointTriplane lift + scatter path (SURVEY App. A): bs={B} per GPU, "
+                               f"{n} raw points per sample ({n_in} in range), 6 cameras x [768,16,32] feature maps, geometry 128x128x80 C=128",
+                   "step": "voxelize (4 launches, 1 host sync) + lift (2 launches) + module forward: point_mlp / reduce_cam_channels (PyTorch "
+                           "Linear, as in the reference) + fused encode (4 launches) + per-plane MLPs",
+                   "l2": f"every step writes {4 * Cc * cells * B / 1e9:.1f} GB of pooled planes: nothing survives in L2 between steps",
+                   "parallelism": f"samples sharded over {world} GPU(s), no collective"},
+        "roofline": dict(ctx.roofline(enc_bytes, enc_ms), kernel="tp::encode_reduce_kernel<0> (+ count / alloc / fill), bs=8",
+                         traffic=None, step_frac=nbytes / (ms * 1e-3) / 1e9 / ctx.peak, step_algorithmic_bytes=int(nbytes),
+                         note="achieved/frac: the fused encode of the 8 samples alone; step_frac: our kernels' algorithmic bytes over the WHOLE "
+                              "step, which also contains the module's cuBLAS Linear layers"),
+        "stages_ms": dict(stage, encode_ms=enc_ms),
+        "cpu_baseline": cpu,
+        "e2e": {"value": world * B * n / (e2e_ms * 1e-3), "unit": "points/s", "ms_per_step": e2e_ms, "steps": e2e_steps,
+                "h2d_bytes_per_step": sum(p.numel() for p in pts_h) * 4 + img_h.numel() * 4, "d2h_bytes_per_step": sum(o.numel() for o in outs_h) * 4,
+                "api": "voxelize_points + point_to_cam + PointTriplaneProjector.forward with pinned host inputs; the three [B,C,.,.] planes return"},
+        "gpu_launches": 10 * steps, "parity": parity,
+        "interact": {"ms_per_step": inter_ms, "what": f"JointEncoder.interact (joint_encoder.py:97-215) bs={B}: [8,32,1024] range image x 6 cameras, "
+                                                      f"image features [8,6,{Ci},{Hi},{Wi}]: projection + gather + position-embedding index-put (3 launches + "
+                                                      "the position_encoder MLP in PyTorch)",
+                     "roofline": ctx.roofline(B * 32 * 1024 * (16 + ncam * 12 + 4 * Ci) + 2 * imgf.numel() * 4, inter_ms)},
+        "cam_proj_feat": {"ms_per_step": scat_ms, "what": f"feature -> camera-pixel scatter (triplane.py:380-390) bs={B}: [8,32,32,1024] features into "
+                                                          f"[8,6,32,{H},{W}] images ({B * ncam * C_DEC * H * W * 4 / 1e6:.0f} MB written once)",
+                          "roofline": ctx.roofline(B * ncam * C_DEC * H * W * 4 + feat32.numel() * 4 + coors.numel() * 4, scat_ms)}}
+
+
+# --------------------------------------------------------------------------------------------------
+# point_sharded (configs[4]): 10-sweep samples, bs=64 over the GPUs; one sample point-sharded
+# --------------------------------------------------------------------------------------------------
+def workload_point_sharded(ctx):
+    from efficient_multimodal_perception_b200 import _lib as L
+    from efficient_multimodal_perception_b200 import dist as tpd
+    from efficient_multimodal_perception_b200 import ops, synth
+    args, dev, world, rank = ctx.args, ctx.dev, ctx.world, ctx.rank
+    G = synth.GEOM_A
+    Cc = G["channels"]
+    total_B = 64
+    per_rank = total_B // world if total_B % world == 0 else -(-total_B // world)
+    base = [synth.multi_sweep(10, 35000, seed=1005 + b) for b in range(4)]   # 4 distinct samples, tiled to the batch
+    sizes = [base[b % 4].shape[0] for b in range(per_rank)]
+    xyz = torch.cat([base[b % 4][:, :3] for b in range(per_rank)]).contiguous().to(dev)
+    fb = [synth.point_features(base[b].shape[0], Cc, seed=1005 + b).to(dev) for b in range(4)]
+    feats = torch.cat([fb[b % 4] for b in range(per_rank)]).contiguous()
+    off = synth.batch_offsets(sizes).to(dev)
+    inside = sum(int(inside_mask(base[b % 4], G["pc_range"]).sum()) for b in range(per_rank))
+    cells = encode_cells(G)
+    n = int(sum(sizes))
+
+    def step():
+        return ops.encode(feats, off, G["pc_range"], G["voxel_size"], G["grid_size"], G["split"], points=xyz)
+
+    steps = max(3, min(args.steps, 10))
+    ms = time_steps(step, steps, 2, ctx)
+    (ms,) = ctx.max_over_ranks(ms)
+    nbytes = n * 12 + inside * 4 * Cc + 4 * Cc * cells * per_rank
+    del feats, xyz
+    torch.cuda.empty_cache()
+    ops.clear_workspaces()
+    # ---- one 350k-point sample on one GPU vs point-sharded over the ranks ---------------------------------------
+    one_pts, one_f = base[0][:, :3].contiguous(), fb[0]
+    off1 = synth.batch_offsets([one_pts.shape[0]]).to(dev)
+    one_dev = one_pts.to(dev)
+    ms_one = time_steps(lambda: ops.encode(one_f, off1, G["pc_range"], G["voxel_size"], G["grid_size"], G["split"], points=one_dev), 10, 3, ctx)
+    sharded = None
+    if world > 1:
+        ref = ops.encode(one_f, off1, G["pc_range"], G["voxel_size"], G["grid_size"], G["split"], points=one_dev)
+        lo_i, hi_i = tpd.shard_bounds(one_pts.shape[0], rank, world)
+        my_pts, my_f = one_dev[lo_i:hi_i].contiguous(), one_f[lo_i:hi_i].contiguous()
+        my_off = synth.batch_offsets([hi_i - lo_i]).to(dev)
+        sharded = {}
+        for strategy in tpd.STRATEGIES:
+            def sstep(strategy=strategy):
+                return tpd.encode_point_sharded(my_f, my_pts, my_off, G["pc_range"], G["voxel_size"], G["grid_size"], G["split"],
+                                                reduce="max", strategy=strategy)
+            got = sstep()
+            ok = tpd.planes_equal(got, ref, strategy, rank, world)   # parity BEFORE timing, on every rank
+            flag = torch.tensor([1 if ok else 0], device=dev)
+            ctx.dist.all_reduce(flag, op=ctx.dist.ReduceOp.MIN)
+            assert int(flag) == 1, f"point-sharded encode ({strategy}) differs from the single-GPU planes"
+            del got
+            s_ms = time_steps(sstep, max(5, min(args.steps, 20)), 3, ctx)
+            (s_ms,) = ctx.max_over_ranks(s_ms)
+            sharded[strategy] = {"ms_per_step": s_ms, "equal_to_single_gpu": True, "points_per_s": one_pts.shape[0] / (s_ms * 1e-3),
+                                 "what": tpd.STRATEGIES[strategy]}
+        del ref
+    (ms_one,) = ctx.max_over_ranks(ms_one)
+    # e2e: one sample through the host-buffer entry point
+    lib = L.lib()
+    geom = L.make_geom(G["pc_range"], G["voxel_size"], G["grid_size"], ops.pool_kernels(G["grid_size"], G["split"]))
+    X, Y, Z = G["grid_size"]
+    P = ops.pooled_sizes(G["grid_size"], ops.pool_kernels(G["grid_size"], G["split"]))
+    n1 = one_pts.shape[0]
+    xyz_p, feats_p = one_pts.pin_memory(), one_f.cpu().pin_memory()
+    off_h = synth.batch_offsets([n1])
+    outs_h = [torch.empty(s).pin_memory() for s in ((1, X, Y, P[2] * Cc), (1, Y, Z, P[0] * Cc), (1, X, Z, P[1] * Cc))]
+
+    def call():
+        L.check(lib.tp_encode_host_f32(feats_p.data_ptr(), Cc, xyz_p.data_ptr(), 3, n1, off_h.data_ptr(), 1, C.byref(geom),
+                                       L.TP_ARITH_TORCH_CUDA, L.TP_REDUCE_MAX, 0, outs_h[0].data_ptr(), outs_h[1].data_ptr(),
+                                       outs_h[2].data_ptr()), "tp_encode_host_f32")
+
+    e2e_steps = max(3, min(args.steps, 10))
+    e2e_ms = e2e_time(call, e2e_steps, ctx)
+    if rank != 0:
+        return None
+    cpu = parity = None
+    if world == 1:
+        from oracle import triplane_oracle as O
+        torch.set_num_threads(os.cpu_count() or 1)
+        m0 = inside_mask(base[0], G["pc_range"])
+        f0 = fb[0].cpu()
+
+        def cpu_chain():
+            cropped, ind = O.voxelize_points([base[0]], G["pc_range"], G["voxel_size"])
+            return O.encode_pooled(f0[m0], O.cat_indices(ind), G["grid_size"], G["split"], 1)
+
+        ref = cpu_chain()
+        med, npass = cpu_time(cpu_chain, 6.0, 4)
+        cpu = dict(value=n1 / med, unit="points/s", cores=os.cpu_count(), kind="port", host=host_cores(),
+                   sample=f"{npass} passes over ONE of the {total_B} samples ({n1} raw points), median: oracle.voxelize_points + oracle.encode_pooled on torch-CPU")
+        got = ops.encode(one_f, off1, G["pc_range"], G["voxel_size"], G["grid_size"], G["split"], points=one_dev, arith="cpu")
+        exact = all(torch.equal(a.cpu(), b) for a, b in zip(got, ref[:3]))
+        assert exact, "10-sweep encode (arith='cpu') differs from the oracle"
+        parity = {"one_sample_cpu_arith_bit_exact_vs_oracle": exact}
+    return {
+        "metric": "triplane encode points/s, 10-sweep samples, bs=64 sharded over the GPUs",
+        "value": world * n / (ms * 1e-3), "unit": "points/s", "n_gpus": world, "steps": steps, "warmup": 2, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"10-sweep accumulated samples (~350k raw points each) x bs={total_B} sample-sharded over {world} GPU(s): {per_rank} samples "
+                               f"({n} points, {inside} in range) per GPU in one batched call, geometry 128x128x80 C=128, dense pooled output "
+                               f"{4 * Cc * cells * per_rank / 1e9:.1f} GB per GPU", "samples_total": total_B, "samples_per_gpu": per_rank,
+                   "data": "4 distinct synthetic 10-sweep samples tiled to the batch (each occurrence has its own memory)",
+                   "step": "count + alloc + fill + reduce (4 launches) over the rank's samples",
+                   "l2": "GBs written per step: nothing survives in L2 between steps",
+                   "parallelism": f"samples sharded over {world} GPU(s), no collective (the reference's data parallelism)"},
+        "roofline": dict(ctx.roofline(nbytes, ms), kernel="tp::encode_reduce_kernel<0> (+ count / alloc / fill)", traffic=None,
+                         note="whole batched step against N*12 + N'*4C + 4C*cells"),
+        "cpu_baseline": cpu,
+        "e2e": {"value": world * n1 / (e2e_ms * 1e-3), "unit": "points/s", "ms_per_step": e2e_ms, "steps": e2e_steps,
+                "h2d_bytes_per_step": n1 * 12 + n1 * Cc * 4 + 16, "d2h_bytes_per_step": 4 * Cc * cells,
+                "api": "tp_encode_host_f32 on ONE 10-sweep sample per step and rank (C ABI, pinned host buffers)"},
+        "gpu_launches": 4 * steps, "parity": parity,
+        "one_sample": {"single_gpu_ms": ms_one, "points": n1, "point_sharded": sharded,
+                       "what": "strong scaling of ONE 350k-point sample: the single-GPU fused encode vs the point-sharded strategies "
+                               "(every strategy asserted equal to the single-GPU planes before timing)"}}
+
+
+RUNNERS = {"decode": workload_decode, "encode": lambda c: workload_encode(c, "A"), "encode_b": lambda c: workload_encode(c, "B"),
+           "surf_sam": workload_surf_sam, "range_cam": workload_range_cam, "point_sharded": workload_point_sharded}
 
 
 def run_b200(args):
-    rank = int(os.environ.get("RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU path (use --impl reference)")
-    torch.cuda.set_device(local)
-    numa = bind_to_gpu_numa_node(local) if world > 1 else None
-    dev = torch.device("cuda", local)
-    import torch.distributed as dist
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-        barrier = lambda: dist.barrier()  # noqa: E731
-    else:
-        barrier = lambda: None  # noqa: E731
-    import efficient_multimodal_perception_b200 as emp
-    emp.lib()
-    peak, peak_src = measured_hbm_peak()
-    sampler = ClockSampler(local, getattr(torch.cuda.get_device_properties(dev), "uuid", None))
-    sampler.start()
-
-    dec = bench_decode_device(args, dev, barrier, sampler)
-    enc = bench_encode_device(args, dev, barrier, sampler)
-    encd = bench_encode_dense(args, dev, barrier, sampler)
-    lift = bench_lift(args, dev, barrier, sampler)
-    occ = bench_occ_head(args, dev, barrier, sampler)
-    eps = bench_encode_point_sharded(args, dev, barrier, rank, world) if world > 1 else None
-    # max over ranks (device time)
-    t = torch.tensor([dec["ms_total"], enc["ms_per_step"], dec["kernel_ms_avg"], eps["ms_per_step"] if eps else 0.0,
-                      encd["ms_per_step"], lift["ms_per_step"], lift["kernel_ms"], eps["ms_points"] if eps else 0.0],
-                     device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, enc_ms, k_avg, eps_ms, encd_ms, lift_ms, lift_k_ms, eps_pts_ms = (float(x) for x in t.tolist())
-    clocks = sampler.stop()
-
-    q_host = decode_queries(args.queries)
-    e2e = bench_decode_e2e(args, q_host, barrier)
-    te = torch.tensor([e2e["ms"]], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_ms = float(te.item())
-
-    if rank == 0:
-        Q = dec["Q"]
-        ms_per_step = ms_total / args.steps
-        qps = world * Q * args.steps / (ms_total * 1e-3)
-        kbytes = decode_bytes(Q)
-        achieved = kbytes / (k_avg * 1e-3) / 1e9
-        kernel_name = ("tp::sample3_grid_kernel<0,8,8>" if QUERY_DIMS[args.queries] else "tp::sample3_kernel<0,8>")
-        cpu, parity, torch_ms = None, None, None
-        if world == 1:
-            cpu, ref = cpu_baseline_decode(q_host)
-            # live parity check of what was just timed (device result of set 0 and the e2e result)
-            tri0, q0, out0 = dec["sets"].sets[0]
-            dec["sets"].step(0)
-            torch.cuda.synchronize()
-            scale = float(ref.abs().max())
-            torch_ms = torch_cuda_decode(q0, tri0)
-            out_cpu_arith = dec["sets"].ops.sample3(tri0, q0, OCC_LO, OCC_VS, OCC_HALF, arith="cpu",
-                                                    grid_dims=QUERY_DIMS[args.queries])
-            parity = {"note": "oracle = torch-CPU op chain; arith='cpu' replays it, the timed arith='cuda' replays "
-                              "torch-CUDA's (x * fp32(1/vs)) and is checked bitwise-level against torch-CUDA in tests/",
-                      "device_cpu_arith_vs_oracle_normwise": float((out_cpu_arith.cpu() - ref[:, :, 0]).abs().max()) / scale,
-                      "device_vs_oracle_normwise": float((out0.cpu() - ref[:, :, 0]).abs().max()) / scale,
-                      "e2e_vs_oracle_normwise": float((e2e["out"] - ref[:, :, 0]).abs().max()) / scale, "bar": 1e-5}
-        line = {
-            "metric": "triplane decode queries/s (3-plane bilinear sample + sum, triplane_occ occupancy decode)",
-            "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"configs/triplane_occ.py occupancy decode: {Q} voxel queries ({args.queries}) "
-                                   f"x C={C_DEC} from 3 fp32 {PLANE}x{PLANE} triplanes, bs=1 per GPU",
-                       "queries": args.queries, "Q": Q, "C": C_DEC, "planes": [PLANE, PLANE],
-                       "query_tensor": (f"[1,{','.join(map(str, QUERY_DIMS[args.queries]))},3] through the 5-D entry point "
-                                        "tp_sample3_grid_nhwc_f32 (per-block lattice detection on the device)"
-                                        if QUERY_DIMS[args.queries] else "[1,Q,3] point list through tp_sample3_nhwc_f32"),
-                       "step": "NCHW->NHWC conversion of the 3 planes (1 launch) + fused gather kernel (1 launch), CUDA-graph replay",
-                       "l2": f"{dec['nsets']} rotating buffer sets, total footprint "
-                             f"{dec['nsets'] * (kbytes + 4 * C_DEC * 3 * PLANE * PLANE) / 1e6:.0f} MB > 3x L2 (no flush kernel)",
-                       "parallelism": f"queries sharded over {world} GPU(s), no collective"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(kernel_name.split("<")[0].replace("tp::", ""), args.queries), "kernel": kernel_name,
-                         "algorithmic_bytes": kbytes,
-                         "kernel_ms_avg": k_avg, "kernel_ms_median": dec["kernel_ms_med"],
-                         "kernel_ms_min": dec["kernel_ms_min"], "peak_source": peak_src,
-                         "step_frac": kbytes / (ms_per_step * 1e-3) / 1e9 / peak},
-            "cpu_baseline": cpu,
-            "torch_cuda_reference": (None if torch_ms is None else {
-                "value": Q / (torch_ms * 1e-3), "unit": "queries/s", "ms_per_step": torch_ms,
-                "what": "the reference's op sequence (normalise + 3 x F.grid_sample + sum) run by torch-CUDA on this GPU, "
-                        "same queries and planes; reported, not a target"}),
-            "e2e": {"value": world * Q / (e2e_ms * 1e-3), "unit": "queries/s",
-                    "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e_ms,
-                    "steps": e2e["steps"], "numa_node_rank0": numa, "api": "tp_sample3_grid_host_f32 / tp_sample3_host_f32 (C ABI, pinned host buffers; H2D planes+queries, "
-                                                  "D2H full result, synchronised every step)"},
-            "gpu_launches": dec["launches"],
-            "variants_kernel_only": {k: dict(v, frac=v["achieved_gbs"] / peak) for k, v in dec["variants"].items()},
-            "clocks": clocks,
-            "parity": parity,
-            "encode": {"metric": "triplane encode points/s (fused crop+index+scatter-max into dense pooled planes)",
-                       "value": world * enc["n"] / (enc_ms * 1e-3), "unit": "points/s", "ms_per_step": enc_ms,
-                       "workload": f"configs/point_triplane.py geometry 128x128x80 pool 5/5/4 C=128, 1 sweep "
-                                   f"{enc['n']} raw pts ({enc['inside']} in range), bs=1 per GPU, "
-                                   f"{enc['cells']} pooled cells dense out",
-                       "roofline": {"bound": "hbm", "achieved": enc["bytes"] / (enc_ms * 1e-3) / 1e9, "peak": peak,
-                                    "unit": "GB/s", "frac": enc["bytes"] / (enc_ms * 1e-3) / 1e9 / peak,
-                                    "algorithmic_bytes": enc["bytes"],
-                                    "traffic": ncu_traffic("encode_reduce_kernel", "S1_geomA_C128"),
-                                    "note": "whole step: count + scan + fill + reduce (4 launches)"},
-                       "steps": enc["steps"], "gpu_launches": enc["launches"]},
-        }
-        line["encode_dense"] = {
-            "metric": "triplane encode points/s, 10-sweep samples (BASELINE.json configs[4] shape, sample-sharded)",
-            "value": world * encd["n"] / (encd_ms * 1e-3), "unit": "points/s", "ms_per_step": encd_ms,
-            "workload": f"{encd['B']} samples x ~350k raw pts per GPU ({encd['n']} pts, {encd['inside']} in range), geometry "
-                        f"128x128x80 C=128, one batched call, dense pooled output",
-            "roofline": {"bound": "hbm", "achieved": encd["bytes"] / (encd_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": encd["bytes"] / (encd_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": encd["bytes"]},
-            "steps": encd["steps"], "gpu_launches": encd["launches"]}
-        line["lift"] = {
-            "metric": "camera->point lift points/s (point_to_cam: 6 cameras x [768,16,32] maps, bilinear gather + camera sum)",
-            "value": world * lift["n"] / (lift_ms * 1e-3), "unit": "points/s", "ms_per_step": lift_ms,
-            "kernel_ms": lift_k_ms, "workload": f"bs=2 x 34720 pts per GPU, Cf=768; step = channels-last copy + lift kernel",
-            "roofline": {"bound": "hbm", "achieved": lift["bytes"] / (lift_k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": lift["bytes"] / (lift_k_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": lift["bytes"],
-                         "note": "lift kernel alone (events around the loop of launches)"},
-            "steps": lift["steps"], "gpu_launches": lift["launches"]}
-        line["occupancy_head"] = {
-            "metric": "Mlp occupancy head queries/s (32 -> 64 -> 32 -> 5 per query, fused on the tensor cores: tcgen05 "
-                      "kind::tf32, TMEM accumulators) and decode + head",
-            "value": world * occ["Q"] / (occ["head_ms"] * 1e-3), "unit": "queries/s", "ms_per_step": occ["head_ms"],
-            "decode_plus_head_ms": occ["both_ms"], "decode_plus_head_queries_per_s": world * occ["Q"] / (occ["both_ms"] * 1e-3),
-            "fused_decode_head_ms": occ["fused_ms"],
-            "fused_decode_head_queries_per_s": world * occ["Q"] / (occ["fused_ms"] * 1e-3),
-            "fused_note": "tp_sample3_grid_head_tf32: layout conversion + ONE kernel from planes and queries to logits (the "
-                          "[B,32,Q] features never reach HBM); bit-identical to decode_plus_head (asserted in this run); "
-                          "every leg: CUDA-graph replays over 4 rotating buffer sets (> 3x L2), layout conversion included",
-            "workload": f"{occ['Q']} queries (640k lattice), C=32, 5 classes; per-rank numbers, no cross-rank max",
-            "roofline": {"bound": "hbm", "achieved": occ["head_bytes"] / (occ["head_ms"] * 1e-3) / 1e9, "peak": peak,
-                         "unit": "GB/s", "frac": occ["head_bytes"] / (occ["head_ms"] * 1e-3) / 1e9 / peak,
-                         "algorithmic_bytes": occ["head_bytes"],
-                         "tensor_tflops": occ["flops"] / (occ["head_ms"] * 1e-3) / 1e12,
-                         "note": "HBM-bound by a wide margin: 8.5 kflop per 148 bytes; the tensor cores are there to keep "
-                                 "the 2C / C wide intermediates on the SM, not for their peak"},
-            "steps": occ["steps"], "gpu_launches": occ["steps"]}
-        if eps:
-            line["encode_point_sharded"] = {
-                "workload": f"ONE 10-sweep sample ({eps['n']} raw pts) point-sharded over {world} GPUs, geometry "
-                            f"128x128x80 C=128; strategy 'planes': partial planes -> NCCL all-reduce(max) of {eps['allreduce_bytes'] / 1e6:.0f} MB "
-                            f"-> finalise; strategy 'points': NCCL all-gather of the point shards -> full encode on every rank "
-                            f"(strong scaling of one sample; value = the faster; the sample-sharded path above needs no collective)",
-                "value": eps["n"] / (min(eps_ms, eps_pts_ms) * 1e-3), "unit": "points/s",
-                "ms_per_step": min(eps_ms, eps_pts_ms), "steps": eps["steps"],
-                "strategy_planes": {"ms_per_step": eps_ms, "allreduce_bytes_per_step": eps["allreduce_bytes"]},
-                "strategy_points": {"ms_per_step": eps_pts_ms, "allgather_bytes_per_step": eps["gather_bytes"],
-                                    "what": "all-gather of the point shards (12 + 4C bytes per point), full fused encode on "
-                                            "every rank: same planes, no partial planes / finalise pass"}}
+    ctx = Ctx(args)
+    names = WORKLOADS if args.workload == "all" else [args.workload]
+    lines = {}
+    for name in names:
+        torch.cuda.empty_cache()
+        lines[name] = RUNNERS[name](ctx)
+        torch.cuda.synchronize()
+    clocks = ctx.sampler.stop()
+    if ctx.rank == 0:
+        if args.workload == "all":
+            line = lines["decode"]
+            line["workloads"] = {k: v for k, v in lines.items() if k != "decode"}
+        else:
+            line = lines[args.workload]
+        line["clocks"] = clocks
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    ctx.close()
 
 
 # --------------------------------------------------------------------------------------------------
@@ -747,36 +1257,89 @@ def run_reference(args):
     from efficient_multimodal_perception_b200 import synth
     from oracle import triplane_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
-    q_host = decode_queries(args.queries)
-    Q = q_host.shape[1]
-    tri = synth.triplane_stacked(1, C_DEC, PLANE, seed=1002)
-    t0 = time.perf_counter()
-    O.sample_points_triplane_stacked(tri, q_host.view(1, 1, -1, 3), OCC_LO, OCC_VS)
-    t_full = time.perf_counter() - t0
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    Qs = int(max(4096, min(Q, Q * budget / max(t_full, 1e-6))))
-    sample = q_host[:, torch.randperm(Q, generator=torch.Generator().manual_seed(0))[:Qs]].contiguous().view(1, 1, -1, 3)
+    wl = "decode" if args.workload == "all" else args.workload
+    budget = 150.0 / max(1, args.steps + args.warmup)   # seconds per step so the whole run ends within minutes
+    if wl == "decode":
+        q_host = decode_queries(args.queries)
+        Q = q_host.shape[1]
+        tri = synth.triplane_stacked(1, C_DEC, PLANE, seed=1002)
+        t0 = time.perf_counter()
+        O.sample_points_triplane_stacked(tri, q_host.view(1, 1, -1, 3), OCC_LO, OCC_VS)
+        t_full = time.perf_counter() - t0
+        Qs = int(max(4096, min(Q, Q * budget / max(t_full, 1e-6))))
+        sample = q_host[:, torch.randperm(Q, generator=torch.Generator().manual_seed(0))[:Qs]].contiguous().view(1, 1, -1, 3)
+        fn = lambda: O.sample_points_triplane_stacked(tri, sample, OCC_LO, OCC_VS)  # noqa: E731
+        units, unit = Qs, "queries/s"
+        metric = "triplane decode queries/s (3-plane bilinear sample + sum, triplane_occ occupancy decode)"
+        config = decode_config(args, Q, args.gpus)
+        desc = (f"each step = {Qs} of the {Q} queries (random subset, seed 0) through oracle.sample_points_triplane_stacked "
+                f"(the reference's normalise + 3 x F.grid_sample + sum on torch-CPU)")
+    elif wl in ("encode", "encode_b", "point_sharded"):
+        G = synth.GEOM_B if wl == "encode_b" else synth.GEOM_A
+        pts = synth.multi_sweep(10, 35000, seed=1005) if wl == "point_sharded" else synth.lidar_sweep(34720, seed=1001)
+        feats = synth.point_features(pts.shape[0], G["channels"], seed=1001)
+        m = inside_mask(pts, G["pc_range"])
+
+        def fn():
+            cropped, ind = O.voxelize_points([pts], G["pc_range"], G["voxel_size"])
+            return O.encode_pooled(feats[m], O.cat_indices(ind), G["grid_size"], G["split"], 1)
+
+        units, unit = pts.shape[0], "points/s"
+        metric = "triplane encode points/s (reference op chain: voxelize_points + unique + scatter_max + 3 pooled dense planes)"
+        config = {"workload": f"{wl}: one sample of {pts.shape[0]} raw points, geometry {G['grid_size']}, C={G['channels']}"}
+        desc = f"each step = one full sample ({pts.shape[0]} raw points) through oracle.voxelize_points + oracle.encode_pooled on torch-CPU"
+    elif wl == "surf_sam":
+        tri = synth.triplane_stacked(8, C_DEC, PLANE, seed=1003)
+        rp = synth.range_image_points(8, seed=1003)
+        pts = sam_points(8, 1003)
+        G = synth.GEOM_A
+        nb = 2   # bounded sample: 2 of the 8 samples per step
+
+        def fn():
+            O.sample_points_triplane_stacked(tri[:nb], rp[:nb], G["pc_range"][:3], G["voxel_size"])
+            return O.contrastive_features(lambda t, c: O.sample_points_triplane_stacked(t, c, G["pc_range"][:3], G["voxel_size"]),
+                                          tri[:nb], pts[:nb], G["pc_range"])
+
+        units = nb * 32768 + sum(f.shape[0] for f, _ in fn())
+        unit = "queries/s"
+        metric = "triplane decode queries/s, pre-training batch (range-image points + SAM-cluster subsets)"
+        config = {"workload": "configs/triplane_surf_sam.py pre-training, bs=8: range points + per-(sample, camera) SAM subsets"}
+        desc = f"each step = {nb} of the 8 samples: the stacked sampler on [2,32,1024,3] + the per-(sample, camera) loop ({units} queries) on torch-CPU"
+    else:  # range_cam
+        import efficient_multimodal_perception_b200 as emp
+        G = synth.GEOM_A
+        rig = synth.camera_rig(1004)
+        metas = [dict(img_shape=rig.img_shape, lidar2image=rig.lidar2image.numpy(), imgs_aug=rig.imgs_aug)]
+        pts = [synth.lidar_sweep(34720, seed=1004)]
+        img = torch.randn(1, 6, 768, 16, 32, generator=torch.Generator().manual_seed(1004))
+        torch.manual_seed(1004)
+        proj = emp.PointTriplaneProjector(G["grid_size"], in_channels=5, out_channels=128, base_channels=128, split=G["split"]).eval()
+
+        @torch.no_grad()
+        def fn():
+            cr, gi = O.voxelize_points(pts, G["pc_range"], G["voxel_size"])
+            cam = O.point_to_cam([c.clone() for c in cr], img, metas)
+            f = proj.point_features(cr, cam)
+            xy, yz, xz, _, _ = O.encode_pooled(f, O.cat_indices(gi), G["grid_size"], G["split"], 1)
+            return proj.mlp_xy(xy), proj.mlp_yz(yz), proj.mlp_xz(xz)
+
+        units, unit = 34720, "points/s"
+        metric = "PointTriplane lift + encode points/s (voxelize_points -> point_to_cam -> PointTriplaneProjector.forward)"
+        config = {"workload": "configs/triplane_range_cam.py shapes on the PointTriplane lift + scatter path, bs=8 (one sample per step here)"}
+        desc = "each step = ONE of the 8 samples (34720 raw points): voxelize + point_to_cam + projector forward on torch-CPU"
     for _ in range(args.warmup):
-        O.sample_points_triplane_stacked(tri, sample, OCC_LO, OCC_VS)
+        fn()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.sample_points_triplane_stacked(tri, sample, OCC_LO, OCC_VS)
+        fn()
     dt = time.perf_counter() - t0
-    qps = Qs * args.steps / dt
-    desc = (f"each step = {Qs} of the {Q} queries (random subset, seed 0) through "
-            f"oracle.sample_points_triplane_stacked (the reference's normalise + 3 x F.grid_sample + sum on torch-CPU)")
+    val = units * args.steps / dt
     print(json.dumps({
-        "impl": "reference",
-        "metric": "triplane decode queries/s (3-plane bilinear sample + sum, triplane_occ occupancy decode)",
-        "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"configs/triplane_occ.py occupancy decode: {Q} voxel queries ({args.queries}) "
-                               f"x C={C_DEC} from 3 fp32 {PLANE}x{PLANE} triplanes, bs=1", "queries": args.queries,
-                   "Q": Q, "C": C_DEC, "sample_per_step": Qs},
-        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": desc},
-        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+        "cpu_baseline": {"value": val, "unit": unit, "cores": os.cpu_count(), "kind": "port", "host": host_cores(), "sample": desc},
+        "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }), flush=True)
 
@@ -787,6 +1350,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="all", choices=["all"] + WORKLOADS)
     ap.add_argument("--queries", default="lattice640k", choices=["lattice640k", "uniform640k", "roi"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -26,6 +26,19 @@ import torch
 import torch.distributed as dist
 
 
+#: point-sharded encode strategies (encode_point_sharded): name -> what crosses NVLink
+STRATEGIES = {
+    "planes": "partial planes (-inf empties) -> NCCL all-reduce(max) of the dense pooled planes -> finalise; every rank holds the full planes",
+    "points": "NCCL all-gather of the point shards (12 + 4C bytes per point) -> full fused encode on every rank; every rank holds the full planes",
+}
+
+
+def planes_equal(got, ref, strategy: str, rank: int, world: int) -> bool:
+    """Does this rank's result of encode_point_sharded equal the single-GPU planes `ref`? Both current strategies
+    replicate the full planes on every rank."""
+    return all(torch.equal(a, b) for a, b in zip(got, ref))
+
+
 def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous, balanced split of range(n): the first n % world shards get one extra element."""
     base, extra = divmod(n, world)

@@ -987,7 +987,7 @@ def workload_range_cam(ctx):
         cropped, grid_ind = emp.voxelize_points(pts, G["pc_range"], G["voxel_size"])
         if timed:
             ev[1].record()
-        cam = emp.point_to_cam(cropped, img, metas)
+        cam = emp.point_to_cam(cropped, img, metas, reduce=proj_dev.reduce_cam_channels)
         if timed:
             ev[2].record()
         out = proj_dev(cropped, grid_ind, cam)
@@ -1004,11 +1004,20 @@ def workload_range_cam(ctx):
     n_in = int(sum(c.shape[0] for c in cropped))
     # encode alone inside the projector, for the breakdown
     with torch.no_grad():
-        f_cat = proj_dev.point_features(cropped, emp.point_to_cam(cropped, img, metas))
+        f_cat = proj_dev.point_features(cropped, emp.point_to_cam(cropped, img, metas, reduce=proj_dev.reduce_cam_channels))
         _, gi = emp.voxelize_points(pts, G["pc_range"], G["voxel_size"])
         off = synth.batch_offsets([g.shape[0] for g in gi]).to(dev)
         cat_ind = torch.cat(gi)
         enc_ms = time_steps(lambda: ops.encode(f_cat, off, [0] * 6, (1, 1, 1), G["grid_size"], G["split"], grid_ind=cat_ind), 10, 2, ctx)
+        w1 = [proj_dev.mlp_xy[0].weight, proj_dev.mlp_yz[0].weight, proj_dev.mlp_xz[0].weight]
+        b1 = [proj_dev.mlp_xy[0].bias, proj_dev.mlp_yz[0].bias, proj_dev.mlp_xz[0].bias]
+        sp_ms = time_steps(lambda: ops.projector_sparse(f_cat, off, [0] * 6, (1, 1, 1), G["grid_size"], G["split"], w1, b1, grid_ind=cat_ind),
+                           10, 2, ctx)
+        proj_dev.sparse_linear = False   # the reference's data flow on this GPU: dense pooled tensors + cuBLAS Linear
+        dense_proj_ms = time_steps(lambda: proj_dev(cropped, gi, emp.point_to_cam(cropped, img, metas)), 5, 2, ctx)
+        proj_dev.sparse_linear = True
+        ops.clear_workspaces()
+        torch.cuda.empty_cache()
     # SURVEY 8f #4 rows this config runs: interact + camera-pixel scatter at bs=8
     Ci, Hi, Wi = 192, 32, 64
     rp = synth.range_image_points(B, seed=1004).to(dev)
@@ -1022,7 +1031,7 @@ def workload_range_cam(ctx):
         feat32 = torch.randn(B, C_DEC, 32, 1024, generator=torch.Generator().manual_seed(7)).to(dev)
         H, W = rig.img_shape[::-1]
         scat_ms = time_steps(lambda: emp.cam_proj_feat(feat32, coors, (H, W)), 10, 2, ctx)
-    ms, enc_ms, inter_ms, scat_ms = ctx.max_over_ranks(ms, enc_ms, inter_ms, scat_ms)
+    ms, enc_ms, inter_ms, scat_ms, sp_ms, dense_proj_ms = ctx.max_over_ranks(ms, enc_ms, inter_ms, scat_ms, sp_ms, dense_proj_ms)
     # e2e: module API, pinned host inputs, the three planes come back
     pts_p = [p.pin_memory() for p in pts_h]
     img_p = img_h.pin_memory()
@@ -1033,7 +1042,7 @@ def workload_range_cam(ctx):
         pd = [p.to(dev, non_blocking=True) for p in pts_p]
         im = img_p.to(dev, non_blocking=True)
         cr, gi2 = emp.voxelize_points(pd, G["pc_range"], G["voxel_size"])
-        o = proj_dev(cr, gi2, emp.point_to_cam(cr, im, metas))
+        o = proj_dev(cr, gi2, emp.point_to_cam(cr, im, metas, reduce=proj_dev.reduce_cam_channels))
         for h, d in zip(outs_h, o):
             h.copy_(d, non_blocking=True)
         torch.cuda.synchronize()
@@ -1043,10 +1052,12 @@ def workload_range_cam(ctx):
     if ctx.rank != 0:
         return None
     cells = encode_cells(G)
-    lift_bytes = n_in * (12 + 4 * Cf) + B * ncam * Cf * Hf * Wf * 4
+    lift_bytes = n_in * (12 + 4 * Cc) + B * ncam * (Cf + Cc) * Hf * Wf * 4      # maps read once (GEMM), reduced maps written, C floats per point out
     enc_bytes = n_in * 12 + n_in * 4 * Cc + 4 * Cc * cells * B
+    X, Y, Z = G["grid_size"]
+    sp_bytes = n_in * 12 + n_in * 4 * Cc + 4 * Cc * B * (X * Y + Y * Z + X * Z) + 4 * Cc * Cc * (20 + 25 + 25)
     vox_bytes = B * n * 44 + n_in * (44 + 12)
-    nbytes = vox_bytes + lift_bytes + enc_bytes
+    nbytes = vox_bytes + lift_bytes + sp_bytes
     cpu = parity = None
     if world == 1:
         from oracle import triplane_oracle as O
@@ -1068,7 +1079,7 @@ def workload_range_cam(ctx):
                           "third-party ops restated)")
         with torch.no_grad():  # arith='cpu' replays the oracle's torch-CPU index / projection chains (the timed path replays torch-CUDA's)
             cr0, gi0 = emp.voxelize_points(pts[:1], G["pc_range"], G["voxel_size"], arith="cpu")
-            out0 = proj_dev(cr0, gi0, emp.point_to_cam(cr0, img[:1], metas[:1], arith="cpu"))
+            out0 = proj_dev(cr0, gi0, emp.point_to_cam(cr0, img[:1], metas[:1], arith="cpu", reduce=proj_dev.reduce_cam_channels))
         errs = [float((a.cpu() - b).abs().max() / b.abs().max()) for a, b in zip(out0, ref)]
         assert max(errs) <= 1e-3, errs
         parity = {"planes_sample0_vs_oracle_pipeline_normwise": errs, "bar": 1e-3,
@@ -1079,15 +1090,22 @@ def workload_range_cam(ctx):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"configs/triplane_range_cam.py shapes on the PointTriplane lift + scatter path (SURVEY App. A): bs={B} per GPU, "
                                f"{n} raw points per sample ({n_in} in range), 6 cameras x [768,16,32] feature maps, geometry 128x128x80 C=128",
-                   "step": "voxelize (4 launches, 1 host sync) + lift (2 launches) + module forward: point_mlp / reduce_cam_channels (PyTorch "
-                           "Linear, as in the reference) + fused encode (4 launches) + per-plane MLPs",
+                   "step": "voxelize (4 launches, 1 host sync) + reduce_cam_channels weight on the feature maps (library GEMM) + lift at C=128 "
+                           "(2 launches) + module forward: point_mlp (PyTorch Linear/BatchNorm, as in the reference) + scatter-max and first "
+                           "per-plane Linear over the occupied cells (tp_projector_sparse_f32, 5 launches) + second per-plane Linear (library GEMM)",
                    "l2": f"every step writes {4 * Cc * cells * B / 1e9:.1f} GB of pooled planes: nothing survives in L2 between steps",
                    "parallelism": f"samples sharded over {world} GPU(s), no collective"},
-        "roofline": dict(ctx.roofline(enc_bytes, enc_ms), kernel="tp::encode_reduce_kernel<0> (+ count / alloc / fill), bs=8",
+        "roofline": dict(ctx.roofline(sp_bytes, sp_ms), kernel="tp_projector_sparse_f32: sparse_count / list / scatter / gemm / combine, bs=8",
                          traffic=None, step_frac=nbytes / (ms * 1e-3) / 1e9 / ctx.peak, step_algorithmic_bytes=int(nbytes),
-                         note="achieved/frac: the fused encode of the 8 samples alone; step_frac: our kernels' algorithmic bytes over the WHOLE "
-                              "step, which also contains the module's cuBLAS Linear layers"),
-        "stages_ms": dict(stage, encode_ms=enc_ms),
+                         fp32_gflops=None,
+                         note="achieved/frac: scatter-max + first per-plane Linear over the occupied cells (points in, [B,rows,C] hidden planes out) "
+                              "against HBM; its gemm pass is fp32-FMA bound, not HBM bound. step_frac: our kernels' algorithmic bytes over the "
+                              "WHOLE step, which also contains the module's PyTorch layers (point_mlp, second Linear)"),
+        "stages_ms": dict(stage, sparse_projector_ms=sp_ms, dense_encode_only_ms=enc_ms,
+                          dense_encode_roofline=ctx.roofline(enc_bytes, enc_ms),
+                          reference_dataflow_step_ms=dense_proj_ms,
+                          reference_dataflow_note="same module with sparse_linear=False and the 768-channel lift: dense pooled tensors (3.4 GB) + "
+                                                  "cuBLAS Linear over them, as the reference computes it (lift + projector only)"),
         "cpu_baseline": cpu,
         "e2e": {"value": world * B * n / (e2e_ms * 1e-3), "unit": "points/s", "ms_per_step": e2e_ms, "steps": e2e_steps,
                 "h2d_bytes_per_step": sum(p.numel() for p in pts_h) * 4 + img_h.numel() * 4, "d2h_bytes_per_step": sum(o.numel() for o in outs_h) * 4,

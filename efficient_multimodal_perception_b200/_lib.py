@@ -47,6 +47,9 @@ SIGNATURES = {
     "tp_encode_workspace_init": (C.c_int, [_vp, _i64, _vp]),
     "tp_encode_f32": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, _i64, _vp, _i32, C.POINTER(tp_geom), _i32,
                                 _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "tp_projector_sparse_workspace_bytes": (_i64, [C.POINTER(tp_geom), _i32, _i32]),
+    "tp_projector_sparse_f32": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, _i64, _vp, _i32, C.POINTER(tp_geom), _i32, _i32,
+                                          C.POINTER(_vp * 3), C.POINTER(_vp * 3), _i32, C.POINTER(_vp * 3), _vp, _i64, _vp]),
     "tp_encode_finalize_mean_f32": (C.c_int, [_vp, _vp, _i64, _i32, _vp]),
     "tp_encode_finalize_max_f32": (C.c_int, [_vp, _i64, _i32, _vp]),
     "tp_voxel_counts_i32": (C.c_int, [_vp, _i64, _vp, _i32, C.POINTER(tp_geom), _vp, _vp]),

@@ -57,9 +57,27 @@ class PointTriplaneProjector(nn.Module):
         self.mlp_yz = nn.Sequential(nn.Linear(ins[0], outs[0]), nn.ReLU(), nn.Linear(outs[0], outs[0]))
         self.mlp_xz = nn.Sequential(nn.Linear(ins[1], outs[1]), nn.ReLU(), nn.Linear(outs[1], outs[1]))
 
+    #: False forces the dense pooled tensors + nn.Linear (the reference's data flow) also without gradients
+    sparse_linear = True
+
+    def _sparse_ok(self, feats: torch.Tensor) -> bool:
+        if not (self.sparse_linear and feats.is_cuda and ops.sparse_projector_supported(feats.shape[1], self.grid_size, self.split)):
+            return False
+        pool = ops.pool_kernels(self.grid_size, self.split)
+        P = ops.pooled_sizes(self.grid_size, pool)
+        Cc = feats.shape[1]
+        return all(m[0].in_features == G * Cc and m[0].out_features == Cc and m[0].bias is not None
+                   for m, G in ((self.mlp_xy, P[2]), (self.mlp_yz, P[0]), (self.mlp_xz, P[1])))
+
     def point_features(self, points: Sequence[torch.Tensor], cam_point_features: Sequence[torch.Tensor]):
         cat_pt_fea = torch.cat([p[:, 0:5] for p in points], dim=0)
-        cat_cam = self.reduce_cam_channels(torch.cat(list(cam_point_features), dim=0))
+        cat_cam = torch.cat(list(cam_point_features), dim=0)
+        if all(getattr(c, "_tp_reduced", False) for c in cam_point_features) and cat_cam.shape[1] == self.reduce_cam_channels.out_features:
+            # point_to_cam(..., reduce=self.reduce_cam_channels) already applied the weight to the feature MAPS
+            # (a Linear without its bias commutes with the bilinear sample and the sum over cameras): add the bias
+            cat_cam = cat_cam + self.reduce_cam_channels.bias
+        else:
+            cat_cam = self.reduce_cam_channels(cat_cam)
         return self.point_mlp(cat_pt_fea) + cat_cam
 
     def forward(self, points, grid_ind, cam_point_features):
@@ -71,6 +89,15 @@ class PointTriplaneProjector(nn.Module):
         if torch.is_grad_enabled() and feats.requires_grad:
             from .autograd import encode_max_autograd
             xy, yz, xz = encode_max_autograd(feats, cat_ind, offsets, self.grid_size, self.split, self.clamp_zero)
+        elif self._sparse_ok(feats):
+            # inference: scatter-max + first Linear + ReLU over the occupied pooled cells only — the three dense
+            # [B,X,Y,Zp*C] tensors (430 MB per sample at the config geometry) are never written or read
+            h = ops.projector_sparse(feats, offsets, [0] * 6, (1, 1, 1), self.grid_size, self.split,
+                                     [self.mlp_xy[0].weight, self.mlp_yz[0].weight, self.mlp_xz[0].weight],
+                                     [self.mlp_xy[0].bias, self.mlp_yz[0].bias, self.mlp_xz[0].bias],
+                                     grid_ind=cat_ind, relu=True, clamp_zero=self.clamp_zero)
+            return [self.mlp_xy[2](h[0]).permute(0, 3, 1, 2), self.mlp_yz[2](h[1]).permute(0, 3, 1, 2),
+                    self.mlp_xz[2](h[2]).permute(0, 3, 1, 2)]
         else:
             xy, yz, xz = ops.encode(feats, offsets, [0] * 6, (1, 1, 1), self.grid_size, self.split,
                                     grid_ind=cat_ind, reduce="max", clamp_zero=self.clamp_zero)
@@ -93,6 +120,13 @@ class PointTriplaneProjector(nn.Module):
         feats = self.point_features(raw_points, cam_point_features)
         offsets = _offsets([p.shape[0] for p in raw_points], feats.device)
         pts = torch.cat([p[:, :3] for p in raw_points], dim=0)
+        if self._sparse_ok(feats):
+            h = ops.projector_sparse(feats, offsets, self.pc_range, self.voxel_size, self.grid_size, self.split,
+                                     [self.mlp_xy[0].weight, self.mlp_yz[0].weight, self.mlp_xz[0].weight],
+                                     [self.mlp_xy[0].bias, self.mlp_yz[0].bias, self.mlp_xz[0].bias],
+                                     points=pts, relu=True, clamp_zero=self.clamp_zero, arith=arith)
+            return [self.mlp_xy[2](h[0]).permute(0, 3, 1, 2), self.mlp_yz[2](h[1]).permute(0, 3, 1, 2),
+                    self.mlp_xz[2](h[2]).permute(0, 3, 1, 2)]
         xy, yz, xz = ops.encode(feats, offsets, self.pc_range, self.voxel_size, self.grid_size, self.split,
                                 points=pts, reduce="max", clamp_zero=self.clamp_zero, arith=arith)
         return [self.mlp_xy(xy).permute(0, 3, 1, 2), self.mlp_yz(yz).permute(0, 3, 1, 2),
@@ -159,25 +193,41 @@ def voxelize_points(points: Sequence[torch.Tensor], pc_range, voxel_size, arith:
     return cropped, grid_ind
 
 
-def point_to_cam(points: Sequence[torch.Tensor], img_features: torch.Tensor, img_metas, arith: str = "cuda"):
+def point_to_cam(points: Sequence[torch.Tensor], img_features: torch.Tensor, img_metas, arith: str = "cuda",
+                 reduce: nn.Linear = None):
     """point_triplane.py:164-241: list of [N_b, >=3] points, img_features [B,ncam,Cf,Hf,Wf], the
     reference's img_metas -> list of [N_b, Cf] camera features per point. One launch for the whole
-    batch and all cameras (plus the channels-last copy of the feature maps)."""
+    batch and all cameras (plus the channels-last copy of the feature maps).
+
+    reduce = the projector's ``reduce_cam_channels`` (Linear 768 -> C, point_triplane_projector.py:49,88): its WEIGHT is
+    applied to the 6 x 16 x 32 feature maps first (24 576 pixels per sample instead of ~29 000 points, and the lift moves
+    C instead of 768 floats per tap), the result rows are tagged and PointTriplaneProjector.point_features adds the bias
+    instead of running the Linear: the [N', 768] tensor (92 MB per sample) never exists. Equal to the reference order of
+    operations up to fp32 rounding (a bias-free Linear commutes with bilinear sampling and the camera sum)."""
     dev = img_features.device
     resize_dims = img_metas[0]["img_shape"][::-1]
     cams = ops.pack_cameras(img_metas, dev)
     sizes = [p.shape[0] for p in points]
     cat = torch.cat([p[:, :3] for p in points], dim=0) if len(points) > 1 else points[0][:, :3]
     offsets = _offsets(sizes, dev)
-    if torch.is_grad_enabled() and img_features.requires_grad:
-        from .autograd import lift_cam_autograd
-        out = lift_cam_autograd(cat, offsets, img_features, cams, resize_dims, arith)
+    if reduce is not None:
+        # [B,ncam,Cf,Hf,Wf] -> channels-last pixels x W^T (a plain library GEMM over 24 576 pixels per sample)
+        maps = torch.matmul(img_features.permute(0, 1, 3, 4, 2), reduce.weight.t()).permute(0, 1, 4, 2, 3)
     else:
-        out = ops.lift_cam(cat, offsets, img_features, cams, resize_dims, arith=arith)
+        maps = img_features
+    if torch.is_grad_enabled() and maps.requires_grad:
+        from .autograd import lift_cam_autograd
+        out = lift_cam_autograd(cat, offsets, maps, cams, resize_dims, arith)
+    else:
+        out = ops.lift_cam(cat, offsets, maps, cams, resize_dims, arith=arith)
     bounds = [0]
     for n in sizes:
         bounds.append(bounds[-1] + n)
-    return [out[bounds[i]:bounds[i + 1]] for i in range(len(points))]
+    rows = [out[bounds[i]:bounds[i + 1]] for i in range(len(points))]
+    if reduce is not None:
+        for r in rows:
+            r._tp_reduced = True
+    return rows
 
 
 def sample_points_triplane(triplane: Union[torch.Tensor, Sequence[torch.Tensor]], points: torch.Tensor, lo, vs,
@@ -439,8 +489,13 @@ class TriplaneHotPathMixin:
         rng, vs = self._tp_geometry()
         return voxelize_points(points, rng, vs, self.tp_arith)
 
+    #: apply the projector's reduce_cam_channels weight to the camera feature maps before the lift (see point_to_cam)
+    tp_reduce_cam_first = True
+
     def point_to_cam(self, points, img_features, img_metas):
-        return point_to_cam(points, img_features, img_metas, self.tp_arith)
+        proj = getattr(self, "point_triplane_projector", None)
+        reduce = proj.reduce_cam_channels if (self.tp_reduce_cam_first and isinstance(proj, PointTriplaneProjector)) else None
+        return point_to_cam(points, img_features, img_metas, self.tp_arith, reduce)
 
     def sample_points_triplane(self, triplane, points):
         lo, vs = self._tp_geometry()

@@ -222,6 +222,78 @@ def encode(feats: torch.Tensor, offsets: torch.Tensor, pc_range, voxel_size, gri
 def clear_workspaces() -> None:
     """Drop every cached encode workspace (frees the device memory once in-flight work has finished)."""
     _EncodeWorkspace.clear()
+    _sparse_ws.clear()
+
+
+_sparse_ws = {}
+
+
+def sparse_projector_supported(C_: int, grid_size, split) -> bool:
+    pool = pool_kernels(grid_size, split)
+    return C_ % 4 == 0 and 4 <= C_ <= 128 and all(1 <= p <= 64 for p in pooled_sizes(grid_size, pool))
+
+
+@_on_device
+def projector_sparse(feats: torch.Tensor, offsets: torch.Tensor, pc_range, voxel_size, grid_size, split, weights, biases, *,
+                     grid_ind: Optional[torch.Tensor] = None, points: Optional[torch.Tensor] = None, relu: bool = True,
+                     clamp_zero: bool = False, arith: str = "cuda"):
+    """Scatter-max + the first per-plane Linear of PointTriplaneProjector (point_triplane_projector.py:99-115, 60-64)
+    over the OCCUPIED pooled cells only (tp_projector_sparse_f32): the dense [B,X,Y,Zp*C] tensors never exist.
+    weights = (mlp_xy[0].weight [C, Zp*C], mlp_yz[0].weight [C, Xp*C], mlp_xz[0].weight [C, Yp*C]), biases likewise.
+    Returns (h_xy [B,X,Y,C], h_yz [B,Y,Z,C], h_xz [B,X,Z,C]) = act(Linear(dense pooled tensor))."""
+    global launch_count
+    _need_cuda(feats, "feats")
+    _need_cuda(offsets, "offsets", torch.int64)
+    if feats.dim() != 2:
+        raise TriplaneError(f"feats must be [N, C], got {tuple(feats.shape)}")
+    if feats.stride(1) != 1 or feats.stride(0) % 4 or feats.data_ptr() % 16:
+        feats = feats.contiguous()
+    n, Cc = feats.shape
+    if (grid_ind is None) == (points is None):
+        raise TriplaneError("projector_sparse: pass exactly one of grid_ind / points")
+    if grid_ind is not None:
+        _need_cuda(grid_ind, "grid_ind", torch.int32)
+        grid_ind = grid_ind.contiguous()
+    else:
+        _need_cuda(points, "points")
+        points = points.contiguous()
+    if not sparse_projector_supported(Cc, grid_size, split):
+        raise TriplaneError(f"projector_sparse: C={Cc} / pooled sizes unsupported (C % 4 == 0, C <= 128, <= 64 pooled cells per axis)")
+    batch = offsets.numel() - 1
+    pool = pool_kernels(grid_size, split)
+    P = pooled_sizes(grid_size, pool)
+    X, Y, Z = (int(g) for g in grid_size)
+    groups = (P[2], P[0], P[1])
+    geom = L.make_geom(pc_range, voxel_size, grid_size, pool)
+    dev = feats.device
+    stream = _stream(feats)
+    wts, bs = [], []
+    for k, (w, b, G) in enumerate(zip(weights, biases, groups)):
+        _need_cuda(w, f"weight {k}")
+        _need_cuda(b, f"bias {k}")
+        if tuple(w.shape) != (Cc, G * Cc) or tuple(b.shape) != (Cc,):
+            raise TriplaneError(f"projector_sparse: plane {k}: weight {tuple(w.shape)} / bias {tuple(b.shape)} do not form "
+                                f"Linear({G}*{Cc} -> {Cc})")
+        wts.append(w.detach().view(Cc, G, Cc).permute(1, 2, 0).contiguous())  # [g][k][n]
+        bs.append(b.detach().contiguous())
+    lib = L.lib()
+    need = lib.tp_projector_sparse_workspace_bytes(C.byref(geom), batch, Cc)
+    key = (dev.index, stream)
+    ws = _sparse_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        _sparse_ws[key] = ws
+    hidden = [torch.empty((batch, X, Y, Cc), dtype=torch.float32, device=dev),
+              torch.empty((batch, Y, Z, Cc), dtype=torch.float32, device=dev),
+              torch.empty((batch, X, Z, Cc), dtype=torch.float32, device=dev)]
+    arr = lambda ts: (C.c_void_p * 3)(*[t.data_ptr() for t in ts])  # noqa: E731
+    wa, ba, ha = arr(wts), arr(bs), arr(hidden)
+    L.check(lib.tp_projector_sparse_f32(feats.data_ptr(), feats.stride(0), Cc, _ptr(grid_ind), _ptr(points),
+                                        0 if points is None else points.shape[1], n, offsets.data_ptr(), batch, C.byref(geom),
+                                        _ARITH[arith], int(bool(clamp_zero)), C.byref(wa), C.byref(ba), int(bool(relu)),
+                                        C.byref(ha), ws.data_ptr(), ws.numel(), stream), "tp_projector_sparse_f32")
+    launch_count += 5 if n else 1
+    return tuple(hidden)
 
 
 @_on_device

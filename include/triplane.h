@@ -143,6 +143,24 @@ TP_API int tp_encode_f32(const float* feats, int64_t feat_stride, int32_t C,
                   float* out_xy, float* out_yz, float* out_xz, int32_t* cell_count,
                   void* workspace, int64_t workspace_bytes, void* stream);
 
+/* 8f#3 (i)  PointTriplaneProjector.forward up to the first per-plane Linear WITHOUT the dense pooled tensors —
+ * point_triplane_projector.py:99-115 + the first layer of mlp_xy / mlp_yz / mlp_xz (:60-64, 113-115):
+ *     hidden_p[b, row, :] = act( b1_p + sum over the occupied pooled cells (row, g) of W1_p[:, g*C:(g+1)*C] . max-pooled cell )
+ * which equals Linear(k*C -> C) applied to the dense flattened tensor of tp_encode_f32 (empty cells contribute 0).
+ * One C x C product per OCCUPIED cell (fp32 FMA), nothing of the 430 MB per sample is written or read.
+ * feats / idx / points / offsets / geom / arith / clamp_zero as tp_encode_f32 (max reduction). C % 4 == 0, C <= 128,
+ * at most 64 pooled cells per axis. w1t[p]: the Linear weight W1_p [C, G_p*C] re-laid as [G_p][C (in)][C (out)]
+ * (G_0 = Zp, G_1 = Xp, G_2 = Yp); b1[p] [C]; relu != 0 applies the ReLU that follows the Linear.
+ * hidden[0] [B, X*Y, C], hidden[1] [B, Y*Z, C], hidden[2] [B, X*Z, C]. Deterministic (fixed summation order).
+ * workspace: tp_projector_sparse_workspace_bytes() bytes (address space for the cell slots; only occupied slots are
+ * touched), no initialisation needed. */
+TP_API int64_t tp_projector_sparse_workspace_bytes(const tp_geom* geom, int32_t batch, int32_t C);
+TP_API int tp_projector_sparse_f32(const float* feats, int64_t feat_stride, int32_t C, const int32_t* idx,
+                            const float* points, int32_t point_stride, int64_t n_total, const int64_t* offsets,
+                            int32_t batch, const tp_geom* geom, int32_t arith, int32_t clamp_zero,
+                            const float* const w1t[3], const float* const b1[3], int32_t relu,
+                            float* const hidden[3], void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Divide partial SUM planes by counts (after a point-sharded all-reduce): out[cell,:] /= max(cnt,1). */
 TP_API int tp_encode_finalize_mean_f32(float* planes, const int32_t* cell_count, int64_t cells, int32_t C,
                                 void* stream);

@@ -257,3 +257,94 @@ def test_multigpu_nccl_parity():
            "--master-port", "29517", os.path.join(ROOT, "tests", "multigpu_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "MULTIGPU_CHECK PASS" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+# ---------------------------------------------------------------------------------------------
+# the projector's first Linear over occupied cells only (tp_projector_sparse_f32)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["projector_small", "projector_ragged"])
+@pytest.mark.parametrize("sparse", [True, False])
+def test_projector_sparse_and_dense_paths_vs_reference_golden(name, sparse):
+    """Reference class forward (golden) == the module through the sparse path (default) and through the dense pooled
+    tensors + nn.Linear (sparse_linear=False)."""
+    g = load_golden(name)
+    ns = int(g["nsamples"])
+    m = emp.PointTriplaneProjector(g["grid"].tolist(), in_channels=5, out_channels=int(g["C"]), base_channels=int(g["C"]),
+                                   split=g["split"].tolist())
+    m.load_state_dict({k[3:]: g.t(k) for k in g if k.startswith("sd.")})
+    m = m.to(DEV).eval()
+    m.sparse_linear = sparse
+    before = ops.launch_count
+    with torch.no_grad():
+        out = m([cu(g.t(f"points{i}")) for i in range(ns)], [cu(g.t(f"ind{i}")) for i in range(ns)],
+                [cu(g.t(f"cam{i}")) for i in range(ns)])
+    assert ops.launch_count - before == (5 if sparse else 4)
+    for a, key in zip(out, ("tpv_xy", "tpv_yz", "tpv_xz")):
+        assert a.shape == g[key].shape and normwise(a.cpu(), g.t(key)) < 1e-5
+
+
+@pytest.mark.parametrize("case", ["sweep", "dense10", "clamp"])
+def test_projector_sparse_equals_linear_of_dense_encode(case):
+    """Config geometry (128x128x80, pool 5/5/4, C=128), bs=2: hidden == Linear(dense pooled tensor) evaluated in fp64 from
+    the fused encode's own (bit-exact) dense output; shared cells (10 accumulated sweeps), empty sample rows, clamp_zero,
+    raw points in (fused crop + index)."""
+    G = synth.GEOM_A
+    C = G["channels"]
+    if case == "dense10":
+        pts = [synth.multi_sweep(10, 12000, seed=31)[:, :3].contiguous(), synth.lidar_sweep(500, seed=32)[:, :3].contiguous()]
+    else:
+        pts = [synth.lidar_sweep(34720, seed=33)[:, :3].contiguous(), synth.lidar_sweep(20000, seed=34)[:, :3].contiguous()]
+    n = sum(p.shape[0] for p in pts)
+    feats = cu(synth.point_features(n, C, seed=35) - (0.5 if case == "clamp" else 0.0))
+    off = cu(synth.batch_offsets([p.shape[0] for p in pts]))
+    xyz = cu(torch.cat(pts))
+    gen = torch.Generator().manual_seed(36)
+    Gs = (20, 25, 25)
+    ws = [cu(torch.randn(C, k * C, generator=gen) / (k * C) ** 0.5) for k in Gs]
+    bs = [cu(torch.randn(C, generator=gen)) for _ in Gs]
+    clamp = case == "clamp"
+    h = ops.projector_sparse(feats, off, G["pc_range"], G["voxel_size"], G["grid_size"], G["split"], ws, bs, points=xyz,
+                             relu=False, clamp_zero=clamp)
+    dense = ops.encode(feats, off, G["pc_range"], G["voxel_size"], G["grid_size"], G["split"], points=xyz, clamp_zero=clamp)
+    for hk, dk, w, b in zip(h, dense, ws, bs):
+        ref = torch.nn.functional.linear(dk.double(), w.double(), b.double())
+        assert hk.shape == ref.shape
+        assert normwise(hk, ref) < 2e-6, (case, normwise(hk, ref))
+    # deterministic: same bits on a second run; ReLU variant
+    h2 = ops.projector_sparse(feats, off, G["pc_range"], G["voxel_size"], G["grid_size"], G["split"], ws, bs, points=xyz,
+                              relu=True, clamp_zero=clamp)
+    for a, b2 in zip(h, h2):
+        assert torch.equal(torch.relu(a), b2)
+
+
+def test_projector_sparse_empty_input_gives_bias():
+    G = synth.GEOM_A
+    C = 32
+    ws = [cu(torch.randn(C, k * C)) for k in (20, 25, 25)]
+    bs = [cu(torch.randn(C)) for _ in range(3)]
+    h = ops.projector_sparse(cu(torch.zeros(0, C)), cu(torch.zeros(2, dtype=torch.int64)), G["pc_range"], G["voxel_size"],
+                             G["grid_size"], G["split"], ws, bs, points=cu(torch.zeros(0, 3)), relu=False)
+    for hk, b in zip(h, bs):
+        assert torch.equal(hk, b.expand_as(hk))
+
+
+def test_reduce_cam_channels_first_lift_matches_reference_order():
+    """SURVEY 8f #2 second half: reduce_cam_channels applied to the feature maps before the lift == the reference order
+    (lift 768 channels, then Linear) within fp32 rounding; the projector consumes the tagged rows by adding the bias."""
+    rig = synth.camera_rig(81)
+    metas = [dict(img_shape=rig.img_shape, lidar2image=rig.lidar2image.numpy(), imgs_aug=rig.imgs_aug) for _ in range(2)]
+    pts = [cu(synth.lidar_sweep(4000, seed=82 + b)) for b in range(2)]
+    img = cu(torch.randn(2, 6, 768, 16, 32, generator=torch.Generator().manual_seed(83)))
+    G = synth.GEOM_A
+    torch.manual_seed(84)
+    proj = emp.PointTriplaneProjector(G["grid_size"], in_channels=5, out_channels=128, base_channels=128, split=G["split"]).eval().to(DEV)
+    with torch.no_grad():
+        cropped, gi = emp.voxelize_points(pts, G["pc_range"], G["voxel_size"])
+        ref_cam = emp.point_to_cam(cropped, img, metas)
+        fused_cam = emp.point_to_cam(cropped, img, metas, reduce=proj.reduce_cam_channels)
+        assert fused_cam[0].shape[1] == 128 and ref_cam[0].shape[1] == 768
+        a = proj.point_features(cropped, ref_cam)
+        b = proj.point_features(cropped, fused_cam)
+        assert normwise(b, a) < 1e-5
+        for x, y in zip(proj(cropped, gi, fused_cam), proj(cropped, gi, ref_cam)):
+            assert normwise(x, y) < 1e-4

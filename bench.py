@@ -343,6 +343,9 @@ def bench_decode_device(args, dev, barrier, sampler):
     nsets = max(4, -(-3 * L2_BYTES // per_set))
     dims = QUERY_DIMS[args.queries]
     sets = DecodeSets(q_host, nsets, dev, dims)
+    lc0 = sets.ops.launch_count
+    sets.step(0)
+    launches_per_step = sets.ops.launch_count - lc0   # 1: the lattice kernel converts the planes itself; 2: conversion + gather
     sets.capture()
     sets.run_steps(args.warmup)
     sampler.active.set()
@@ -400,7 +403,7 @@ def bench_decode_device(args, dev, barrier, sampler):
                                              "note": "roi()-style lattice generated in-kernel: no 12 B/query read"}
     sampler.active.clear()
     return dict(Q=Q, nsets=nsets, ms_total=ms, kernel_ms_avg=k_avg, kernel_ms_med=k_med, kernel_ms_min=k_min,
-                launches=args.steps * 2, sets=sets, variants=variants)
+                launches=args.steps * launches_per_step, launches_per_step=launches_per_step, sets=sets, variants=variants)
 
 
 def torch_cuda_decode(q_dev, tri_dev, reps=5):
@@ -1167,7 +1170,7 @@ def workload_point_sharded(ctx):
         for strategy in tpd.STRATEGIES:
             def sstep(strategy=strategy):
                 return tpd.encode_point_sharded(my_f, my_pts, my_off, G["pc_range"], G["voxel_size"], G["grid_size"], G["split"],
-                                                reduce="max", strategy=strategy)
+                                                reduce="max", strategy=strategy, capacity=one_pts.shape[0])
             got = sstep()
             ok = tpd.planes_equal(got, ref, strategy, rank, world)   # parity BEFORE timing, on every rank
             flag = torch.tensor([1 if ok else 0], device=dev)

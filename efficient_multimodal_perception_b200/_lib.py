@@ -93,6 +93,8 @@ SIGNATURES = {
     "tp_mlp_head_tf32": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "tp_sample3_grid_head_tf32": (C.c_int, [C.POINTER(tp_plane * 3), _vp, C.POINTER(_i32 * 3), _i32,
                                             C.POINTER(tp_sample_geom), _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "tp_route_points_f32": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _i64, C.POINTER(tp_geom), _i32, _i32, _vp, _vp, _vp, _vp, _vp,
+                                      _vp, _vp, _i64, _vp]),
     "tp_sample3_host_f32": (C.c_int, [C.POINTER(_vp * 3), C.POINTER(_i32 * 6), C.POINTER(_i64 * 3), _i32, _vp,
                                       _i64, _i32, C.POINTER(tp_sample_geom), _i32, _vp]),
     "tp_sample3_grid_host_f32": (C.c_int, [C.POINTER(_vp * 3), C.POINTER(_i32 * 6), C.POINTER(_i64 * 3), _i32, _vp,

@@ -1,0 +1,119 @@
+// Point-sharded encode, "owner" exchange (encode by point): every rank PUSHES each of its points straight
+// into the receive buffers of the ranks that own the point's output rows, over NVLink peer memory, in one kernel:
+//   * rank r owns the x-slab [xb[r], xb[r+1]) of the xy and xz planes and the y-slab [yb[r], yb[r+1]) of the yz plane,
+//     so a point has at most two destinations and every pooled cell has exactly one owner: no partial planes, no
+//     all-reduce of 430 MB, no replicated output;
+//   * a destination slot comes from a system-scope atomicAdd on the owner's counter (peer memory), the row (voxel
+//     index relative to the slab + the C feature floats) is written with plain peer stores;
+//   * the owners then run the ordinary fused encode on what they received (rows never written keep index -1 and are
+//     dropped), each producing its slab of the three planes.
+// The host side (dist.py) allocates the buffers as torch symmetric memory, resets them, and brackets this kernel with
+// two device-side barriers. The reference has no counterpart (data parallel only, tools/euler_train.sh:3-11).
+#include "tp_common.cuh"
+
+namespace tp {
+
+constexpr int kRouteMaxWorld = 8;
+
+struct RouteParams {
+  const float* points;
+  const float* feats;
+  int64_t n, feat_stride, cap;
+  int point_stride, C4, world;
+  GeomDev g;
+  int xb[kRouteMaxWorld + 1], yb[kRouteMaxWorld + 1];
+  int32_t* cnt[kRouteMaxWorld];     // [2]: rows received for the x-slab planes, for the y-slab plane
+  int32_t* idx_x[kRouteMaxWorld];   // [cap, 3]
+  float* feat_x[kRouteMaxWorld];    // [cap, C]
+  int32_t* idx_y[kRouteMaxWorld];
+  float* feat_y[kRouteMaxWorld];
+};
+
+__device__ __forceinline__ int slab_owner(const int* b, int world, int i) {
+  int r = 0;
+  while (r + 1 < world && i >= b[r + 1]) ++r;
+  return r;
+}
+
+// one warp per point: lane 0 claims the two slots, all lanes copy the feature row twice
+template <int ARITH>
+__global__ void __launch_bounds__(256)
+route_points_kernel(const RouteParams P) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int C = P.C4 * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < P.n; i += nwarp) {
+    const float* p = P.points + i * P.point_stride;
+    int ix, iy, iz;
+    bool keep = tp_crop_index<ARITH>(P.g, __ldg(p), __ldg(p + 1), __ldg(p + 2), ix, iy, iz);
+    keep = keep & (ix >= 0) & (ix < P.g.grid[0]) & (iy >= 0) & (iy < P.g.grid[1]) & (iz >= 0) & (iz < P.g.grid[2]);
+    if (!keep) continue;  // warp-uniform: every lane evaluated the same point
+    const int dx = slab_owner(P.xb, P.world, ix), dy = slab_owner(P.yb, P.world, iy);
+    int sx = 0, sy = 0;
+    if (lane == 0) {
+      sx = atomicAdd_system(P.cnt[dx], 1);
+      sy = atomicAdd_system(P.cnt[dy] + 1, 1);
+    }
+    sx = __shfl_sync(0xffffffffu, sx, 0);
+    sy = __shfl_sync(0xffffffffu, sy, 0);
+    const float4* frow = reinterpret_cast<const float4*>(P.feats + i * P.feat_stride);
+    const bool okx = sx < P.cap, oky = sy < P.cap;  // capacity is the global point count: cannot overflow
+    float4* ox = reinterpret_cast<float4*>(P.feat_x[dx] + (int64_t)sx * C);
+    float4* oy = reinterpret_cast<float4*>(P.feat_y[dy] + (int64_t)sy * C);
+    for (int v = lane; v < P.C4; v += 32) {
+      const float4 f = __ldg(frow + v);
+      if (okx) ox[v] = f;
+      if (oky) oy[v] = f;
+    }
+    if (lane == 0) {
+      if (okx) {
+        int32_t* d = P.idx_x[dx] + (int64_t)sx * 3;
+        d[0] = ix - P.xb[dx]; d[1] = iy; d[2] = iz;
+      }
+      if (oky) {
+        int32_t* d = P.idx_y[dy] + (int64_t)sy * 3;
+        d[0] = ix; d[1] = iy - P.yb[dy]; d[2] = iz;
+      }
+    }
+  }
+}
+
+}  // namespace tp
+
+using namespace tp;
+
+extern "C" int tp_route_points_f32(const float* points, int32_t point_stride, const float* feats, int64_t feat_stride,
+                                   int32_t C, int64_t n, const tp_geom* geom, int32_t arith, int32_t world,
+                                   const int32_t* x_bounds, const int32_t* y_bounds, void* const* peer_cnt,
+                                   void* const* peer_idx_x, void* const* peer_feat_x, void* const* peer_idx_y,
+                                   void* const* peer_feat_y, int64_t capacity, void* stream) {
+  if (!geom || !x_bounds || !y_bounds || !peer_cnt || !peer_idx_x || !peer_feat_x || !peer_idx_y || !peer_feat_y)
+    return fail(TP_E_NULL, "tp_route_points_f32: null argument");
+  if (world < 1 || world > kRouteMaxWorld) return fail(TP_E_SHAPE, "tp_route_points_f32: world=%d must be in 1..%d", world, kRouteMaxWorld);
+  if (C <= 0 || (C & 3) || n < 0 || capacity <= 0 || point_stride < 3) return fail(TP_E_SHAPE, "tp_route_points_f32: bad C=%d n=%lld", C, (long long)n);
+  if (arith != TP_ARITH_TORCH_CUDA && arith != TP_ARITH_TORCH_CPU) return fail(TP_E_ENUM, "tp_route_points_f32: unknown arith %d", arith);
+  for (int a = 0; a < 3; ++a)
+    if (!(geom->vs[a] > 0.f) || geom->grid[a] <= 0) return fail(TP_E_SHAPE, "tp_route_points_f32: bad geometry on axis %d", a);
+  if (n == 0) return 0;
+  if (!points || !feats || (feat_stride & 3) || ((uintptr_t)feats & 15)) return fail(TP_E_SHAPE, "tp_route_points_f32: feats must be 16-byte aligned rows");
+  RouteParams P;
+  P.points = points; P.feats = feats; P.n = n; P.feat_stride = feat_stride; P.cap = capacity;
+  P.point_stride = point_stride; P.C4 = C / 4; P.world = world;
+  P.g = make_geom_dev(*geom);
+  for (int r = 0; r <= world; ++r) { P.xb[r] = x_bounds[r]; P.yb[r] = y_bounds[r]; }
+  if (P.xb[0] != 0 || P.xb[world] != geom->grid[0] || P.yb[0] != 0 || P.yb[world] != geom->grid[1])
+    return fail(TP_E_SHAPE, "tp_route_points_f32: slab bounds must cover [0, X) and [0, Y)");
+  for (int r = 0; r < world; ++r) {
+    if (!peer_cnt[r] || !peer_idx_x[r] || !peer_feat_x[r] || !peer_idx_y[r] || !peer_feat_y[r])
+      return fail(TP_E_NULL, "tp_route_points_f32: peer %d has a null buffer", r);
+    P.cnt[r] = (int32_t*)peer_cnt[r];
+    P.idx_x[r] = (int32_t*)peer_idx_x[r]; P.feat_x[r] = (float*)peer_feat_x[r];
+    P.idx_y[r] = (int32_t*)peer_idx_y[r]; P.feat_y[r] = (float*)peer_feat_y[r];
+  }
+  const int64_t wb = (n + 7) / 8;
+  const int grid = (int)(wb < (int64_t)kSMs * 8 ? wb : (int64_t)kSMs * 8);
+  if (arith == TP_ARITH_TORCH_CUDA) route_points_kernel<TP_ARITH_TORCH_CUDA><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+  else route_points_kernel<TP_ARITH_TORCH_CPU><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+  TP_LAUNCH_CHECK("route_points_kernel");
+  return 0;
+}

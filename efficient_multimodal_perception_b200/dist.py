@@ -30,13 +30,22 @@ import torch.distributed as dist
 STRATEGIES = {
     "planes": "partial planes (-inf empties) -> NCCL all-reduce(max) of the dense pooled planes -> finalise; every rank holds the full planes",
     "points": "NCCL all-gather of the point shards (12 + 4C bytes per point) -> full fused encode on every rank; every rank holds the full planes",
+    "owner": "every rank pushes its points (12 B index + 4C B features, to at most two owners) into the owners' receive buffers over NVLink peer "
+             "memory in one kernel (tp_route_points_f32, torch symmetric memory, two device-side barriers) -> each rank encodes ITS slab of the "
+             "three planes; the planes stay distributed (rank r: x-slab of xy / xz, y-slab of yz), nothing is replicated",
 }
 
 
-def planes_equal(got, ref, strategy: str, rank: int, world: int) -> bool:
-    """Does this rank's result of encode_point_sharded equal the single-GPU planes `ref`? Both current strategies
-    replicate the full planes on every rank."""
-    return all(torch.equal(a, b) for a, b in zip(got, ref))
+def planes_equal(got, ref, strategy: str, rank: int, world: int, rtol: float = 0.0) -> bool:
+    """Does this rank's result of encode_point_sharded equal the single-GPU planes `ref` = (xy, yz, xz)? 'planes' and
+    'points' replicate the full planes on every rank; 'owner' leaves rank r with the x-slab of xy / xz and the y-slab of yz."""
+    if strategy == "owner":
+        X, Y = ref[0].shape[1], ref[1].shape[1]
+        (x0, x1), (y0, y1) = shard_bounds(X, rank, world), shard_bounds(Y, rank, world)
+        ref = (ref[0][:, x0:x1], ref[1][:, y0:y1], ref[2][:, x0:x1])
+    if rtol == 0.0:
+        return all(a.shape == b.shape and torch.equal(a, b) for a, b in zip(got, ref))
+    return all(a.shape == b.shape and float((a - b).abs().max()) <= rtol * float(b.abs().max()) for a, b in zip(got, ref))
 
 
 def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
@@ -128,19 +137,106 @@ def gather_point_shards(feats: torch.Tensor, points: torch.Tensor, offsets: torc
     return cat(f_out, feats).contiguous(), cat(p_out, points).contiguous(), off_all
 
 
+class _OwnerExchange:
+    """Symmetric-memory receive buffers of the 'owner' strategy, one per (device, group, capacity, C): every rank can
+    address every other rank's buffers (NVLink peer mappings). Layout of a rank's buffer (bytes):
+    [cnt int32 x 64 | idx_x int32 [cap,3] | idx_y int32 [cap,3] | feat_x f32 [cap,C] | feat_y f32 [cap,C]]."""
+    cache = {}
+
+    def __init__(self, device, group, cap: int, C: int):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.cap, self.C = cap, C
+        pad = lambda b: (b + 255) // 256 * 256  # noqa: E731
+        self.off_idx_x = 256
+        self.off_idx_y = self.off_idx_x + pad(cap * 12)
+        self.off_feat_x = self.off_idx_y + pad(cap * 12)
+        self.off_feat_y = self.off_feat_x + pad(cap * C * 4)
+        nbytes = self.off_feat_y + pad(cap * C * 4)
+        self.buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.world, self.rank = self.hdl.world_size, self.hdl.rank
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        import ctypes as C_
+        arr = lambda off: (C_.c_void_p * self.world)(*[p + off for p in ptrs])  # noqa: E731
+        self.p_cnt, self.p_idx_x, self.p_idx_y = arr(0), arr(self.off_idx_x), arr(self.off_idx_y)
+        self.p_feat_x, self.p_feat_y = arr(self.off_feat_x), arr(self.off_feat_y)
+        view = lambda off, n, dt: self.buf[off:off + n * 4].view(dt)  # noqa: E731
+        self.head = self.buf[:self.off_feat_x]                       # counters + both index regions: reset every call
+        self.idx_x = view(self.off_idx_x, cap * 3, torch.int32).view(cap, 3)
+        self.idx_y = view(self.off_idx_y, cap * 3, torch.int32).view(cap, 3)
+        self.feat_x = view(self.off_feat_x, cap * C, torch.float32).view(cap, C)
+        self.feat_y = view(self.off_feat_y, cap * C, torch.float32).view(cap, C)
+        self.offsets = torch.tensor([0, cap], dtype=torch.int64, device=device)
+
+    @classmethod
+    def get(cls, device, group, cap: int, C: int) -> "_OwnerExchange":
+        key = (device.index, id(group), C)
+        ex = cls.cache.get(key)
+        if ex is None or ex.cap < cap:
+            ex = cls(device, group, cap, C)
+            cls.cache[key] = ex
+        return ex
+
+
+def _encode_owner(feats, points, offsets, pc_range, voxel_size, grid_size, split, reduce, clamp_zero, arith, group, capacity):
+    import ctypes as C_
+    from . import _lib as L
+    from . import ops
+    if offsets.numel() != 2:
+        raise ValueError("strategy 'owner' handles one sample per call (rows of several samples cannot be told apart on arrival)")
+    if not feats.is_cuda:
+        raise ValueError("strategy 'owner' needs CUDA tensors (NVLink peer memory)")
+    dev = feats.device
+    n, Cc = feats.shape
+    if capacity is None:  # global point count: one small all-reduce + host sync; pass capacity= to avoid it
+        t = torch.tensor([n], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, group=group)
+        capacity = int(t.item())
+    ex = _OwnerExchange.get(dev, group, max(int(capacity), 1), Cc)
+    world, rank = ex.world, ex.rank
+    X, Y, Z = (int(g) for g in grid_size)
+    xb = [shard_bounds(X, r, world)[0] for r in range(world)] + [X]
+    yb = [shard_bounds(Y, r, world)[0] for r in range(world)] + [Y]
+    pool = ops.pool_kernels(grid_size, split)
+    geom = L.make_geom(pc_range, voxel_size, grid_size, pool)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    feats = feats if (feats.stride(1) == 1 and feats.stride(0) % 4 == 0 and feats.data_ptr() % 16 == 0) else feats.contiguous()
+    points = points.contiguous()
+    with torch.cuda.device(dev):
+        ex.head.fill_(255)                 # index regions = -1 (rows never written are dropped by the encode) ...
+        ex.head[:256].zero_()              # ... counters = 0
+        ex.hdl.barrier(channel=0)          # every rank has reset before anybody pushes
+        xba, yba = (C_.c_int32 * (world + 1))(*xb), (C_.c_int32 * (world + 1))(*yb)
+        L.check(L.lib().tp_route_points_f32(points.data_ptr(), points.shape[1], feats.data_ptr(), feats.stride(0), Cc, n,
+                                            C_.byref(geom), ops._ARITH[arith], world, xba, yba, ex.p_cnt, ex.p_idx_x, ex.p_feat_x,
+                                            ex.p_idx_y, ex.p_feat_y, ex.cap, stream), "tp_route_points_f32")
+        ops.launch_count += 1 if n else 0
+        ex.hdl.barrier(channel=1)          # every push has landed before the owners read
+    xs, ys = xb[rank + 1] - xb[rank], yb[rank + 1] - yb[rank]
+    kw = dict(reduce=reduce, clamp_zero=clamp_zero, arith=arith, pool=pool)
+    xy, _, xz = ops.encode(ex.feat_x, ex.offsets, [0] * 6, (1, 1, 1), (xs, Y, Z), split, grid_ind=ex.idx_x, planes=(True, False, True), **kw)
+    _, yz, _ = ops.encode(ex.feat_y, ex.offsets, [0] * 6, (1, 1, 1), (X, ys, Z), split, grid_ind=ex.idx_y, planes=(False, True, False), **kw)
+    return xy, yz, xz
+
+
 def encode_point_sharded(feats: torch.Tensor, points: torch.Tensor, offsets: torch.Tensor, pc_range, voxel_size,
                          grid_size, split, reduce: str = "max", clamp_zero: bool = False, arith: str = "cuda",
-                         group=None, strategy: str = "planes"):
+                         group=None, strategy: str = "planes", capacity: Optional[int] = None):
     """Each rank passes ITS shard of the points (feats [N_r, C], raw points [N_r, >=3], offsets [B+1] of
-    the shard); every rank returns the complete planes (xy, yz, xz). strategy: "planes" (all-reduce of
-    partial planes) or "points" (all-gather of the shards, then the full encode on every rank)."""
+    the shard). strategy "planes" (all-reduce of partial planes) and "points" (all-gather of the shards, then the full
+    encode on every rank) return the complete planes (xy, yz, xz) on every rank; "owner" (push over NVLink peer memory,
+    see STRATEGIES) returns this rank's slabs: xy[:, x0:x1], yz[:, y0:y1], xz[:, x0:x1] with (x0, x1) =
+    shard_bounds(X, rank, world), (y0, y1) = shard_bounds(Y, rank, world). capacity (owner): the global point count."""
     from . import ops
+    if strategy == "owner":
+        return _encode_owner(feats, points[:, :3], offsets, pc_range, voxel_size, grid_size, split, reduce, clamp_zero, arith,
+                             group, capacity)
     if strategy == "points":
         f_all, p_all, off_all = gather_point_shards(feats, points[:, :3].contiguous(), offsets, group)
         return ops.encode(f_all, off_all, pc_range, voxel_size, grid_size, split, points=p_all, reduce=reduce,
                           clamp_zero=clamp_zero, arith=arith)
     if strategy != "planes":
-        raise ValueError(f"strategy must be 'planes' or 'points', got {strategy!r}")
+        raise ValueError(f"strategy must be 'planes', 'points' or 'owner', got {strategy!r}")
     if reduce == "max":
         xy, yz, xz = ops.encode(feats, offsets, pc_range, voxel_size, grid_size, split, points=points,
                                 reduce="max_partial", arith=arith)

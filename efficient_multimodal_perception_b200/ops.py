@@ -164,12 +164,13 @@ class _EncodeWorkspace:
 def encode(feats: torch.Tensor, offsets: torch.Tensor, pc_range, voxel_size, grid_size, split, *,
            grid_ind: Optional[torch.Tensor] = None, points: Optional[torch.Tensor] = None,
            reduce: str = "max", clamp_zero: bool = False, want_counts: bool = False, arith: str = "cuda",
-           planes: Sequence[bool] = (True, True, True)):
+           planes: Sequence[bool] = (True, True, True), pool: Optional[Sequence[int]] = None):
     """Fused triplane encode (point_triplane_projector.py:99-115).
 
     feats [N, C]; offsets [B+1] int64; either grid_ind [N,3] int32 (reference signature) or raw
     points [N, >=3] (crop + index fused in-kernel). Returns (xy [B,X,Y,Zp*C], yz [B,Y,Z,Xp*C],
-    xz [B,X,Z,Yp*C][, counts int32 [cells]])."""
+    xz [B,X,Z,Yp*C][, counts int32 [cells]]). pool overrides int(grid_size / split) (a slab of a larger grid keeps the
+    full grid's pooling kernels: dist.encode_point_sharded, strategy 'owner')."""
     global launch_count
     _need_cuda(feats, "feats")
     _need_cuda(offsets, "offsets", torch.int64)
@@ -191,7 +192,7 @@ def encode(feats: torch.Tensor, offsets: torch.Tensor, pc_range, voxel_size, gri
         if points.shape[0] != n or points.shape[1] < 3:
             raise TriplaneError(f"points must be [{n}, >=3], got {tuple(points.shape)}")
     batch = offsets.numel() - 1
-    pool = pool_kernels(grid_size, split)
+    pool = pool_kernels(grid_size, split) if pool is None else tuple(int(v) for v in pool)
     P = pooled_sizes(grid_size, pool)
     X, Y, Z = (int(g) for g in grid_size)
     geom = L.make_geom(pc_range, voxel_size, grid_size, pool)

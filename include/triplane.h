@@ -381,6 +381,28 @@ TP_API int tp_radius_i32(const float* x, const int64_t* x_offsets, const float* 
                   void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Multi-GPU, point-sharded encode (the reference is data-parallel only and has no counterpart).
+ *
+ * Partial planes: tp_encode_f32(reduce = TP_REDUCE_MAX_PARTIAL / TP_REDUCE_SUM) on every rank, an all-reduce of the
+ * planes by the caller's communication library (the Python host uses torch.distributed / NCCL, dist.py), then
+ * tp_encode_finalize_max_f32 / tp_encode_finalize_mean_f32.
+ *
+ * Owner exchange, tp_route_points_f32: every rank pushes its points into the owners' receive buffers over peer memory.
+ * Rank r owns rows [x_bounds[r], x_bounds[r+1]) of the xy and xz planes and rows [y_bounds[r], y_bounds[r+1]) of the
+ * yz plane. peer_*[r] are THIS process's device pointers to rank r's buffers (CUDA IPC / VMM mappings, e.g. torch
+ * symmetric memory): peer_cnt[r] int32[2] zeroed, peer_idx_x/y[r] int32 [capacity, 3] filled with -1, peer_feat_x/y[r]
+ * float [capacity, C]; capacity >= the global point count. The caller separates reset, route and the owners' encodes
+ * with cross-rank barriers. Afterwards every owner runs tp_encode_f32 twice on its buffers with n_total = capacity:
+ * idx_x (x relative to the slab) with grid (x_bounds[r+1]-x_bounds[r], Y, Z) for xy and xz, idx_y with grid
+ * (X, y_bounds[r+1]-y_bounds[r], Z) for yz, same pool: the results are the slabs of the single-GPU planes, bit for bit.
+ * world <= 8, one sample per call (arrival order is arbitrary, so rows of several samples cannot be told apart). */
+TP_API int tp_route_points_f32(const float* points, int32_t point_stride, const float* feats, int64_t feat_stride,
+                        int32_t C, int64_t n, const tp_geom* geom, int32_t arith, int32_t world,
+                        const int32_t* x_bounds, const int32_t* y_bounds, void* const* peer_cnt,
+                        void* const* peer_idx_x, void* const* peer_feat_x, void* const* peer_idx_y,
+                        void* const* peer_feat_y, int64_t capacity, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Host-buffer entry points (what a non-PyTorch caller binds; bench.py's `e2e` leg).
  * All pointers are HOST memory (pinned recommended). They allocate a per-thread cached device
  * arena, copy in, run the kernels above, copy out and synchronise the internal stream.

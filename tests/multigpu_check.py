@@ -40,6 +40,16 @@ def main():
                 ok &= bool(good)
                 if not good:
                     print(f"[rank {rank}] {reduce}/{strategy}: mismatch, max diff {float((a - b).abs().max())}", flush=True)
+        # owner exchange over NVLink peer memory: one sample per call; every rank ends up with its slabs of the planes
+        ref1 = ops.encode(feats[0].to(dev), synth.batch_offsets([30000]).to(dev), G["pc_range"], G["voxel_size"], G["grid_size"],
+                          G["split"], points=raw[0].to(dev), reduce=reduce)
+        for rep in range(2):  # twice: the buffers are reused and must be reset correctly
+            got = tpd.encode_point_sharded(my_feats[0].to(dev), my_raw[0].to(dev), synth.batch_offsets([my_raw[0].shape[0]]).to(dev),
+                                           G["pc_range"], G["voxel_size"], G["grid_size"], G["split"], reduce=reduce, strategy="owner")
+            good = tpd.planes_equal(got, ref1, "owner", rank, world, rtol=0.0 if reduce == "max" else 1e-5)
+            ok &= bool(good)
+            if not good:
+                print(f"[rank {rank}] {reduce}/owner (pass {rep}): mismatch", flush=True)
     # decode: each rank samples its slice of the queries; gathered result == full result
     tri = synth.triplane_stacked(1, 32, 128, seed=9).to(dev)
     q = synth.uniform_queries(100003, seed=10)[None].to(dev)

@@ -76,6 +76,28 @@ def test_encode_backward_vs_oracle_autograd(grid, split, C, n_per):
             assert normwise(g_got.cpu(), g_ref) <= TOL
 
 
+def test_encode_backward_ties_documented_behaviour():
+    """Exact ties (duplicated rows in one voxel: repeated returns in accumulated sweeps). torch_scatter.scatter_max
+    routes a voxel's gradient to ONE arg-max point (which one is unspecified on CUDA), spconv's pool backward fans out
+    to every tied voxel; this library gives every point that attains the pooled maximum the cell's gradient (documented
+    in include/triplane.h). The sum over the tied points is therefore multiplicity x the reference's: asserted here so
+    a change of the rule is a conscious one. Untied points are unaffected."""
+    grid, split = [16, 16, 8], [4, 4, 2]
+    g = torch.Generator().manual_seed(11)
+    ind = torch.stack([torch.randint(0, grid[a], (300,), generator=g) for a in range(3)], 1).int()
+    f = torch.randn(300, 8, generator=g)
+    ind2, f2 = torch.cat([ind, ind[:40]]), torch.cat([f, f[:40]])     # rows 300..339 duplicate rows 0..39
+    fa, fb = cu(f).requires_grad_(), cu(f2).requires_grad_()
+    oa = encode_max_autograd(fa, cu(ind), cu(synth.batch_offsets([300])), grid, split)
+    ob = encode_max_autograd(fb, cu(ind2), cu(synth.batch_offsets([340])), grid, split)
+    for x, y in zip(oa, ob):
+        assert torch.equal(x, y)                                      # duplicates do not change the forward
+    ws = [torch.randn(o.shape, device=DEV, generator=torch.Generator(DEV).manual_seed(12)) for o in oa]
+    (ga,) = torch.autograd.grad(sum((o * w).sum() for o, w in zip(oa, ws)), [fa])
+    (gb,) = torch.autograd.grad(sum((o * w).sum() for o, w in zip(ob, ws)), [fb])
+    assert torch.equal(gb[:300], ga) and torch.equal(gb[300:], ga[:40])  # each copy receives the full cell gradient
+
+
 def test_encode_backward_clamp_zero_blocks_negative_maxima():
     grid, split = [16, 16, 8], [4, 4, 2]
     g = torch.Generator().manual_seed(3)

@@ -95,6 +95,10 @@ SIGNATURES = {
                                             C.POINTER(tp_sample_geom), _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "tp_route_points_f32": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _i64, C.POINTER(tp_geom), _i32, _i32, _vp, _vp, _vp, _vp, _vp,
                                       _vp, _vp, _i64, _vp]),
+    "tp_comm_unique_id": (C.c_int, [_vp]),
+    "tp_comm_init": (C.c_int, [C.POINTER(_vp), _i32, _i32, _vp]),
+    "tp_comm_destroy": (C.c_int, [_vp]),
+    "tp_allreduce_planes": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _i64, _vp]),
     "tp_sample3_host_f32": (C.c_int, [C.POINTER(_vp * 3), C.POINTER(_i32 * 6), C.POINTER(_i64 * 3), _i32, _vp,
                                       _i64, _i32, C.POINTER(tp_sample_geom), _i32, _vp]),
     "tp_sample3_grid_host_f32": (C.c_int, [C.POINTER(_vp * 3), C.POINTER(_i32 * 6), C.POINTER(_i64 * 3), _i32, _vp,

@@ -35,44 +35,60 @@ __device__ __forceinline__ int slab_owner(const int* b, int world, int i) {
   return r;
 }
 
-// one warp per point: lane 0 claims the two slots, all lanes copy the feature row twice
+// One warp per 32 points. Slots are claimed with ONE system-scope atomic per (warp, destination) — a remote atomic is
+// a multi-microsecond NVLink round trip, so per-point atomics would serialise the kernel — then the warp copies the 32
+// feature rows (all lanes on one 4*C-byte row at a time: full-width peer stores).
 template <int ARITH>
 __global__ void __launch_bounds__(256)
 route_points_kernel(const RouteParams P) {
   const int lane = threadIdx.x & 31;
   const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int C = P.C4 * 4;
-  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < P.n; i += nwarp) {
-    const float* p = P.points + i * P.point_stride;
-    int ix, iy, iz;
-    bool keep = tp_crop_index<ARITH>(P.g, __ldg(p), __ldg(p + 1), __ldg(p + 2), ix, iy, iz);
-    keep = keep & (ix >= 0) & (ix < P.g.grid[0]) & (iy >= 0) & (iy < P.g.grid[1]) & (iz >= 0) & (iz < P.g.grid[2]);
-    if (!keep) continue;  // warp-uniform: every lane evaluated the same point
-    const int dx = slab_owner(P.xb, P.world, ix), dy = slab_owner(P.yb, P.world, iy);
-    int sx = 0, sy = 0;
-    if (lane == 0) {
-      sx = atomicAdd_system(P.cnt[dx], 1);
-      sy = atomicAdd_system(P.cnt[dy] + 1, 1);
+  for (int64_t i0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; i0 < P.n; i0 += nwarp * 32) {
+    const int64_t i = i0 + lane;
+    int ix = 0, iy = 0, iz = 0;
+    bool keep = false;
+    if (i < P.n) {
+      const float* p = P.points + i * P.point_stride;
+      keep = tp_crop_index<ARITH>(P.g, __ldg(p), __ldg(p + 1), __ldg(p + 2), ix, iy, iz);
+      keep = keep & (ix >= 0) & (ix < P.g.grid[0]) & (iy >= 0) & (iy < P.g.grid[1]) & (iz >= 0) & (iz < P.g.grid[2]);
     }
-    sx = __shfl_sync(0xffffffffu, sx, 0);
-    sy = __shfl_sync(0xffffffffu, sy, 0);
-    const float4* frow = reinterpret_cast<const float4*>(P.feats + i * P.feat_stride);
-    const bool okx = sx < P.cap, oky = sy < P.cap;  // capacity is the global point count: cannot overflow
-    float4* ox = reinterpret_cast<float4*>(P.feat_x[dx] + (int64_t)sx * C);
-    float4* oy = reinterpret_cast<float4*>(P.feat_y[dy] + (int64_t)sy * C);
-    for (int v = lane; v < P.C4; v += 32) {
-      const float4 f = __ldg(frow + v);
-      if (okx) ox[v] = f;
-      if (oky) oy[v] = f;
-    }
-    if (lane == 0) {
-      if (okx) {
-        int32_t* d = P.idx_x[dx] + (int64_t)sx * 3;
-        d[0] = ix - P.xb[dx]; d[1] = iy; d[2] = iz;
+    const int dx = keep ? slab_owner(P.xb, P.world, ix) : -1, dy = keep ? slab_owner(P.yb, P.world, iy) : -1;
+    int sx = -1, sy = -1;
+    for (int r = 0; r < P.world; ++r) {
+      const unsigned mx = __ballot_sync(0xffffffffu, dx == r), my = __ballot_sync(0xffffffffu, dy == r);
+      int bx = 0, by = 0;
+      if (lane == 0) {
+        if (mx) bx = atomicAdd_system(P.cnt[r], __popc(mx));
+        if (my) by = atomicAdd_system(P.cnt[r] + 1, __popc(my));
       }
-      if (oky) {
-        int32_t* d = P.idx_y[dy] + (int64_t)sy * 3;
-        d[0] = ix; d[1] = iy - P.yb[dy]; d[2] = iz;
+      bx = __shfl_sync(0xffffffffu, bx, 0);
+      by = __shfl_sync(0xffffffffu, by, 0);
+      if (dx == r) sx = bx + __popc(mx & ((1u << lane) - 1u));
+      if (dy == r) sy = by + __popc(my & ((1u << lane) - 1u));
+    }
+    if (sx >= P.cap) sx = -1;  // capacity is the global point count: cannot happen
+    if (sy >= P.cap) sy = -1;
+    if (sx >= 0) {
+      int32_t* d = P.idx_x[dx] + (int64_t)sx * 3;
+      d[0] = ix - P.xb[dx]; d[1] = iy; d[2] = iz;
+    }
+    if (sy >= 0) {
+      int32_t* d = P.idx_y[dy] + (int64_t)sy * 3;
+      d[0] = ix; d[1] = iy - P.yb[dy]; d[2] = iz;
+    }
+    // feature rows: the warp walks its kept points; 32 lanes x 16 B per row and destination
+    for (unsigned m = __ballot_sync(0xffffffffu, keep); m; m &= m - 1) {
+      const int src = __ffs(m) - 1;
+      const int pdx = __shfl_sync(0xffffffffu, dx, src), pdy = __shfl_sync(0xffffffffu, dy, src);
+      const int psx = __shfl_sync(0xffffffffu, sx, src), psy = __shfl_sync(0xffffffffu, sy, src);
+      const float4* frow = reinterpret_cast<const float4*>(P.feats + (i0 + src) * P.feat_stride);
+      float4* ox = psx >= 0 ? reinterpret_cast<float4*>(P.feat_x[pdx] + (int64_t)psx * C) : nullptr;
+      float4* oy = psy >= 0 ? reinterpret_cast<float4*>(P.feat_y[pdy] + (int64_t)psy * C) : nullptr;
+      for (int v = lane; v < P.C4; v += 32) {
+        const float4 f = __ldg(frow + v);
+        if (ox) ox[v] = f;
+        if (oy) oy[v] = f;
       }
     }
   }
@@ -110,7 +126,7 @@ extern "C" int tp_route_points_f32(const float* points, int32_t point_stride, co
     P.idx_x[r] = (int32_t*)peer_idx_x[r]; P.feat_x[r] = (float*)peer_feat_x[r];
     P.idx_y[r] = (int32_t*)peer_idx_y[r]; P.feat_y[r] = (float*)peer_feat_y[r];
   }
-  const int64_t wb = (n + 7) / 8;
+  const int64_t wb = (n + 255) / 256;   // 8 warps per CTA, 32 points per warp
   const int grid = (int)(wb < (int64_t)kSMs * 8 ? wb : (int64_t)kSMs * 8);
   if (arith == TP_ARITH_TORCH_CUDA) route_points_kernel<TP_ARITH_TORCH_CUDA><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
   else route_points_kernel<TP_ARITH_TORCH_CPU><<<grid, 256, 0, (cudaStream_t)stream>>>(P);

@@ -402,6 +402,19 @@ TP_API int tp_route_points_f32(const float* points, int32_t point_stride, const 
                         void* const* peer_idx_x, void* const* peer_feat_x, void* const* peer_idx_y,
                         void* const* peer_feat_y, int64_t capacity, void* stream);
 
+/* Collective hooks for callers without torch.distributed (the Python host uses torch.distributed / NCCL for the same
+ * exchange). NCCL is opened at run time (dlopen "libnccl.so.2"); errors: 1000 + ncclResult_t.
+ *   tp_comm_unique_id: rank 0 creates the 128-byte id and ships it to the other ranks by its own means;
+ *   tp_comm_init: collective over `world` processes (one GPU each, the current device); tp_comm_destroy frees it;
+ *   tp_allreduce_planes: in place over n_floats contiguous floats of partial planes (the three planes may live in one
+ *     buffer) with max (reduce = TP_REDUCE_MAX / _MAX_PARTIAL) or sum (TP_REDUCE_SUM / _MEAN), plus, when n_counts > 0,
+ *     a sum of the int32 cell counts in the same NCCL group; follow with tp_encode_finalize_max_f32 / _mean_f32. */
+TP_API int tp_comm_unique_id(void* id_out_128_bytes);
+TP_API int tp_comm_init(void** comm_out, int32_t world, int32_t rank, const void* unique_id_128_bytes);
+TP_API int tp_comm_destroy(void* comm);
+TP_API int tp_allreduce_planes(void* comm, float* planes, int64_t n_floats, int32_t reduce, int32_t* cell_count,
+                        int64_t n_counts, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Host-buffer entry points (what a non-PyTorch caller binds; bench.py's `e2e` leg).
  * All pointers are HOST memory (pinned recommended). They allocate a per-thread cached device

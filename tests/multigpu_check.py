@@ -50,6 +50,28 @@ def main():
             ok &= bool(good)
             if not good:
                 print(f"[rank {rank}] {reduce}/owner (pass {rep}): mismatch", flush=True)
+    # C-ABI collective hooks (tp_comm_*, tp_allreduce_planes): same result as torch.distributed
+    import ctypes as C_
+    from efficient_multimodal_perception_b200 import _lib as L
+    lib = L.lib()
+    idbuf = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        L.check(lib.tp_comm_unique_id(idbuf.data_ptr()), "tp_comm_unique_id")
+    idd = idbuf.to(dev)
+    dist.broadcast(idd, 0)
+    idbuf = idd.cpu()
+    comm = C_.c_void_p()
+    L.check(lib.tp_comm_init(C_.byref(comm), world, rank, idbuf.data_ptr()), "tp_comm_init")
+    part = torch.randn(1 << 20, device=dev, generator=torch.Generator(dev).manual_seed(100 + rank))
+    cnts = torch.full((4096,), rank + 1, dtype=torch.int32, device=dev)
+    want_max, want_cnt = part.clone(), cnts.clone()
+    dist.all_reduce(want_max, op=dist.ReduceOp.MAX)
+    dist.all_reduce(want_cnt, op=dist.ReduceOp.SUM)
+    L.check(lib.tp_allreduce_planes(comm, part.data_ptr(), part.numel(), L.TP_REDUCE_MAX_PARTIAL, cnts.data_ptr(), cnts.numel(),
+                                    torch.cuda.current_stream().cuda_stream), "tp_allreduce_planes")
+    torch.cuda.synchronize()
+    ok &= torch.equal(part, want_max) and torch.equal(cnts, want_cnt)
+    L.check(lib.tp_comm_destroy(comm), "tp_comm_destroy")
     # decode: each rank samples its slice of the queries; gathered result == full result
     tri = synth.triplane_stacked(1, 32, 128, seed=9).to(dev)
     q = synth.uniform_queries(100003, seed=10)[None].to(dev)

@@ -65,6 +65,13 @@ SIGNATURES = {
                                            C.POINTER(tp_sample_geom), _i32, _vp, _vp, _i64, _vp]),
     "tp_sample3_lattice_nhwc_f32": (C.c_int, [C.POINTER(tp_plane * 3), _i32, C.POINTER(_i32 * 3), C.POINTER(C.c_float * 3),
                                               C.POINTER(C.c_float * 3), _i32, C.POINTER(tp_sample_geom), _i32, _vp, _vp]),
+    "tp_sample3_lattice_nchw_f32": (C.c_int, [C.POINTER(tp_plane * 3), _i32, C.POINTER(_i32 * 3), C.POINTER(C.c_float * 3),
+                                              C.POINTER(C.c_float * 3), _i32, C.POINTER(tp_sample_geom), _i32, _vp, _vp, _i64,
+                                              _vp]),
+    "tp_sample3_seg_nchw_f32": (C.c_int, [C.POINTER(tp_plane * 3), _i32, _vp, _i64, _vp, _vp, _i32, _i32,
+                                          C.POINTER(tp_sample_geom), _i32, _vp, _vp, _i64, _vp]),
+    "tp_sample3_grid_head_nchw_tf32": (C.c_int, [C.POINTER(tp_plane * 3), _vp, C.POINTER(_i32 * 3), _i32,
+                                                 C.POINTER(tp_sample_geom), _i32, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp]),
     "tp_sample3_seg_nhwc_f32": (C.c_int, [C.POINTER(tp_plane * 3), _i32, _vp, _i64, _vp, _vp, _i32, _i32,
                                           C.POINTER(tp_sample_geom), _i32, _vp, _vp]),
     "tp_sample3_seg_backward_nhwc_f32": (C.c_int, [C.POINTER(tp_plane * 3), _i32, _vp, _i64, _vp, _vp, _i32, _i32,

@@ -43,6 +43,32 @@ inline cudaError_t opt_in_smem(int bytes) {
   return e;
 }
 
+// ---- programmatic dependent launch: layout conversion -> decode inside one C-ABI call ----------
+// The *_nchw_* entry points launch the NCHW -> channels-last conversion and then the decode kernel with
+// programmaticStreamSerializationAllowed: the conversion calls pdl_launch_dependents() first thing, so the decode
+// grid is scheduled while the conversion is still running and does everything that does not need the planes (query
+// load, lattice check, tap records, all-zero blocks) before its first pdl_wait(). The attribute is only ever set on
+// a launch that directly follows our own conversion kernel (itself launched with full stream ordering), so nothing
+// but that conversion can overlap the decode. pdl_wait() is a no-op in a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- the reference's coordinate chain, op by op, never contracted -----------------------------
 // (p - lo) (/) vs : torch-CUDA multiplies by the fp32 reciprocal of the Python-float divisor,
 // torch-CPU divides (SURVEY §7 "bit-exact voxel indices").

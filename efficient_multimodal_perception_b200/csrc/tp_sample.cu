@@ -85,36 +85,16 @@ nchw_to_nhwc_kernel(const float* __restrict__ src, int64_t src_bstride, float* _
   }
 }
 
-struct Planes3 {
-  const float* src[3];
-  float* dst[3];
-  int64_t src_bstride[3];
-  int HW[3];
-  int tiles_x[3];  // ceil(HW/32) per plane; blockIdx.x runs over the three planes back to back
-};
-
-// all three planes in one launch. grid = (sum_p ceil(HW_p/32), ceil(C/32), B)
+// All three planes in one launch (slabs: tp_sample_dev.cuh), one wave of CTAs for the configs' plane sizes (384 slabs at
+// B = 1, C = 32, 128x128), grid-stride beyond that. The first instruction releases the dependent decode launch (see
+// tp_common.cuh); the grid never exceeds one wave, so every CTA is resident when the dependent grid starts taking SMs.
 __global__ void __launch_bounds__(256)
-nchw_to_nhwc3_kernel(const Planes3 P, int C) {
-  __shared__ float tile[32][33];
-  int bx = blockIdx.x, k = 0;
-  if (bx >= P.tiles_x[0]) { bx -= P.tiles_x[0]; k = 1; if (bx >= P.tiles_x[1]) { bx -= P.tiles_x[1]; k = 2; } }
-  const int HW = P.HW[k];
-  const int b = blockIdx.z;
-  const int p0 = bx * 32, c0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const float* s = P.src[k] + (int64_t)b * P.src_bstride[k];
-  float* d = P.dst[k] + (int64_t)b * C * HW;
-#pragma unroll
-  for (int j = 0; j < 32; j += 8) {
-    int c = c0 + ty + j, p = p0 + tx;
-    if (c < C && p < HW) tile[ty + j][tx] = __ldg(s + (int64_t)c * HW + p);
-  }
-  __syncthreads();
-#pragma unroll
-  for (int j = 0; j < 32; j += 8) {
-    int p = p0 + ty + j, c = c0 + tx;
-    if (c < C && p < HW) d[(int64_t)p * C + c] = tile[tx][ty + j];
+nchw_to_nhwc3_kernel(const Planes3 P) {
+  __shared__ float tile[128 * 33];
+  pdl_launch_dependents();
+  for (int s = blockIdx.x; s < P.nslabs; s += gridDim.x) {
+    convert_slab(P, s, tile);
+    __syncthreads();
   }
 }
 
@@ -122,24 +102,39 @@ nchw_to_nhwc3_kernel(const Planes3 P, int C) {
 
 using namespace tp;
 
-extern "C" int tp_planes3_nchw_to_nhwc_f32(const tp_plane planes_nchw[3], float* const dst[3], int32_t batch,
-                                           int32_t C, void* stream) {
-  if (!planes_nchw || !dst) return fail(TP_E_NULL, "tp_planes3_nchw_to_nhwc_f32: null argument");
-  if (batch <= 0 || C <= 0) return fail(TP_E_SHAPE, "tp_planes3_nchw_to_nhwc_f32: bad shape B=%d C=%d", batch, C);
-  Planes3 P;
-  int tx = 0;
+int tp::planes3_fill(Planes3& P, const char* who, const tp_plane planes_nchw[3], float* const dst[3], int32_t batch, int32_t C) {
+  if (!planes_nchw || !dst) return fail(TP_E_NULL, "%s: null argument", who);
+  if (batch <= 0 || C <= 0) return fail(TP_E_SHAPE, "%s: bad shape B=%d C=%d", who, batch, C);
+  P.C = C;
+  P.cgroups = (C + 31) / 32;
+  int64_t total = 0;
+  bool vec = (C & 3) == 0;
   for (int k = 0; k < 3; ++k) {
-    if (!planes_nchw[k].data || !dst[k]) return fail(TP_E_NULL, "tp_planes3_nchw_to_nhwc_f32: plane %d is null", k);
-    if (planes_nchw[k].H <= 0 || planes_nchw[k].W <= 0) return fail(TP_E_SHAPE, "tp_planes3_nchw_to_nhwc_f32: plane %d shape", k);
+    if (!planes_nchw[k].data || !dst[k]) return fail(TP_E_NULL, "%s: plane %d is null", who, k);
+    if (planes_nchw[k].H <= 0 || planes_nchw[k].W <= 0) return fail(TP_E_SHAPE, "%s: plane %d shape", who, k);
     P.src[k] = planes_nchw[k].data;
     P.dst[k] = dst[k];
     P.src_bstride[k] = planes_nchw[k].batch_stride;
-    P.HW[k] = planes_nchw[k].H * planes_nchw[k].W;
-    P.tiles_x[k] = (P.HW[k] + 31) / 32;
-    tx += P.tiles_x[k];
+    const int64_t hw = (int64_t)planes_nchw[k].H * planes_nchw[k].W;
+    if (hw >= ((int64_t)1 << 31)) return fail(TP_E_SHAPE, "%s: plane %d too large", who, k);
+    P.HW[k] = (int)hw;
+    P.pgroups[k] = (int)((hw + 127) / 128);
+    total += (int64_t)batch * P.cgroups * P.pgroups[k];
+    if (total >= ((int64_t)1 << 31)) return fail(TP_E_SHAPE, "%s: too many slabs", who);
+    P.slab_end[k] = (int)total;
+    vec = vec && ((uintptr_t)dst[k] & 15) == 0;
   }
-  dim3 grid(tx, (C + 31) / 32, batch);
-  nchw_to_nhwc3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P, C);
+  P.nslabs = (int)total;
+  P.vec = vec ? 1 : 0;
+  return 0;
+}
+
+extern "C" int tp_planes3_nchw_to_nhwc_f32(const tp_plane planes_nchw[3], float* const dst[3], int32_t batch,
+                                           int32_t C, void* stream) {
+  Planes3 P;
+  if (int rc = planes3_fill(P, "tp_planes3_nchw_to_nhwc_f32", planes_nchw, dst, batch, C)) return rc;
+  const int grid = P.nslabs < kSMs * 8 ? P.nslabs : kSMs * 8;
+  nchw_to_nhwc3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
   TP_LAUNCH_CHECK("nchw_to_nhwc3_kernel");
   return 0;
 }
@@ -157,9 +152,8 @@ extern "C" int tp_planes_nchw_to_nhwc_f32(const float* src, int64_t src_batch_st
   return 0;
 }
 
-extern "C" int tp_sample3_nhwc_f32(const tp_plane planes[3], int32_t C, const float* queries,
-                                   int64_t Q, int32_t batch, const tp_sample_geom* sg,
-                                   int32_t arith, float* out, void* stream) {
+int tp::sample3_flat(const tp_plane planes[3], int32_t C, const float* queries, int64_t Q, int32_t batch,
+                     const tp_sample_geom* sg, int32_t arith, float* out, void* stream, bool pdl) {
   if (C <= 0 || (C & 3)) return fail(TP_E_SHAPE, "tp_sample3_nhwc_f32: C=%d must be a positive multiple of 4", C);
   if (batch <= 0 || Q < 0) return fail(TP_E_SHAPE, "tp_sample3_nhwc_f32: bad B=%d Q=%lld", batch, (long long)Q);
   if (Q == 0) return 0;
@@ -196,7 +190,7 @@ extern "C" int tp_sample3_nhwc_f32(const tp_plane planes[3], int32_t C, const fl
   static std::atomic<unsigned> next_slot{0};
   const int slot = (int)(next_slot.fetch_add(1) % kSchedSlots);
   cudaStream_t s = (cudaStream_t)stream;
-#define TP_SAMPLE(A, C4T) sample3_kernel<A, C4T><<<grid, kWarpsPerCta * 32, 0, s>>>(P, slot)
+#define TP_SAMPLE(A, C4T) launch_kernel(sample3_kernel<A, C4T>, grid, kWarpsPerCta * 32, 0, s, pdl, P, slot)
 #define TP_SAMPLE_C(A)                                                   \
   switch (C) { case 32: TP_SAMPLE(A, 8); break; case 96: TP_SAMPLE(A, 24); break; \
                case 128: TP_SAMPLE(A, 32); break; default: TP_SAMPLE(A, 0); break; }
@@ -212,18 +206,22 @@ extern "C" int tp_sample3_nhwc_f32(const tp_plane planes[3], int32_t C, const fl
   return 0;
 }
 
-extern "C" int tp_sample3_nchw_f32(const tp_plane planes_nchw[3], int32_t C, const float* queries,
+extern "C" int tp_sample3_nhwc_f32(const tp_plane planes[3], int32_t C, const float* queries,
                                    int64_t Q, int32_t batch, const tp_sample_geom* sg,
-                                   int32_t arith, float* out, float* ws, int64_t ws_floats,
-                                   void* stream) {
-  if (!planes_nchw || !ws) return fail(TP_E_NULL, "tp_sample3_nchw_f32: null argument");
-  tp_plane nhwc[3];
+                                   int32_t arith, float* out, void* stream) {
+  return sample3_flat(planes, C, queries, Q, batch, sg, arith, out, stream, false);
+}
+
+// channels-last copies of reference-layout planes live in the caller's workspace, plane after plane
+int tp::planes3_workspace(const char* who, const tp_plane planes_nchw[3], int32_t C, int32_t batch, float* ws,
+                          int64_t ws_floats, tp_plane nhwc[3], float* dsts[3]) {
+  if (!planes_nchw || !ws) return fail(TP_E_NULL, "%s: null argument", who);
+  if (batch <= 0 || C <= 0) return fail(TP_E_SHAPE, "%s: bad shape B=%d C=%d", who, batch, C);
   int64_t need = 0;
   for (int k = 0; k < 3; ++k) need += (int64_t)batch * C * planes_nchw[k].H * planes_nchw[k].W;
   if (ws_floats < need)
-    return fail(TP_E_WORKSPACE, "tp_sample3_nchw_f32: workspace %lld < %lld floats", (long long)ws_floats, (long long)need);
+    return fail(TP_E_WORKSPACE, "%s: workspace %lld < %lld floats", who, (long long)ws_floats, (long long)need);
   float* w = ws;
-  float* dsts[3];
   for (int k = 0; k < 3; ++k) {
     dsts[k] = w;
     nhwc[k].data = w;
@@ -232,6 +230,22 @@ extern "C" int tp_sample3_nchw_f32(const tp_plane planes_nchw[3], int32_t C, con
     nhwc[k].batch_stride = (int64_t)C * planes_nchw[k].H * planes_nchw[k].W;
     w += (int64_t)batch * nhwc[k].batch_stride;
   }
-  if (int rc = tp_planes3_nchw_to_nhwc_f32(planes_nchw, dsts, batch, C, stream)) return rc;
-  return tp_sample3_nhwc_f32(nhwc, C, queries, Q, batch, sg, arith, out, stream);
+  return 0;
+}
+
+// ... converted by one launch that releases its dependent (the decode launch that follows)
+int tp::planes3_to_workspace(const char* who, const tp_plane planes_nchw[3], int32_t C, int32_t batch, float* ws,
+                             int64_t ws_floats, tp_plane nhwc[3], void* stream) {
+  float* dsts[3];
+  if (int rc = planes3_workspace(who, planes_nchw, C, batch, ws, ws_floats, nhwc, dsts)) return rc;
+  return tp_planes3_nchw_to_nhwc_f32(planes_nchw, dsts, batch, C, stream);
+}
+
+extern "C" int tp_sample3_nchw_f32(const tp_plane planes_nchw[3], int32_t C, const float* queries,
+                                   int64_t Q, int32_t batch, const tp_sample_geom* sg,
+                                   int32_t arith, float* out, float* ws, int64_t ws_floats,
+                                   void* stream) {
+  tp_plane nhwc[3];
+  if (int rc = planes3_to_workspace("tp_sample3_nchw_f32", planes_nchw, C, batch, ws, ws_floats, nhwc, stream)) return rc;
+  return sample3_flat(nhwc, C, queries, Q, batch, sg, arith, out, stream, true);
 }

@@ -125,6 +125,7 @@ sample3_grid_kernel(const __grid_constant__ GridParams G) {
       const float4* const pl1 = reinterpret_cast<const float4*>(P.plane[1] + (int64_t)b * P.bstride[1]) + l8;
       const float4* const pl2 = reinterpret_cast<const float4*>(P.plane[2] + (int64_t)b * P.bstride[2]) + l8;
       const bool jk_ok = (jj < nj) && (kg * 4 < nk);
+      if (G.pdl && (vote & 7)) pdl_wait();  // first read of the planes; a block outside all of them never waits
       float* const o_jk = P.out + (int64_t)b * C * P.Q + ((int64_t)i0 * G.w + j0 + jj) * G.d + k0 + kg * 4;
 
       for (int ch = 0; ch < nchunk; ++ch) {
@@ -176,12 +177,12 @@ sample3_grid_kernel(const __grid_constant__ GridParams G) {
 }
 
 template <int ARITH, int C4T, int BI, bool GEN>
-static void launch_grid(const GridParams& G, int batch, cudaStream_t s) {
+static void launch_grid(const GridParams& G, int batch, cudaStream_t s, bool pdl) {
   // persistent CTAs (kGridCtasPerSm per SM)
   const int64_t blocks = G.nblocks < kGridCtasPerSm * kSMs ? G.nblocks : kGridCtasPerSm * kSMs;
   auto kern = sample3_grid_kernel<ARITH, C4T, BI, GEN>;
   opt_in_smem<sample3_grid_kernel<ARITH, C4T, BI, GEN>>(GridCfg<BI>::kSmemBytes);  // a failure surfaces at the launch check
-  kern<<<(unsigned)blocks, kGridThreads, GridCfg<BI>::kSmemBytes, s>>>(G);
+  launch_kernel(kern, (unsigned)blocks, kGridThreads, GridCfg<BI>::kSmemBytes, s, pdl, G);
 }
 
 }  // namespace tp
@@ -191,8 +192,11 @@ using namespace tp;
 // queries == nullptr: generated lattice (lat_org / lat_step), no fallback to the per-query kernel
 static int grid_entry(const tp_plane planes[3], int32_t C, const float* queries, const float* lat_org,
                       const float* lat_step, const int32_t dims[3], int32_t batch, const tp_sample_geom* sg,
-                      int32_t arith, float* out, void* stream) {
+                      int32_t arith, float* out, void* stream, const tp_plane* planes_nchw = nullptr,
+                      float* const* nhwc_dst = nullptr) {
+  // planes_nchw != nullptr: `planes` describes the (not yet written) channels-last workspace copies nhwc_dst[3]
   const bool gen = queries == nullptr;
+  bool pdl = false;
   if (!dims) return fail(TP_E_NULL, "tp_sample3_grid_nhwc_f32: null dims");
   const int h = dims[0], w = dims[1], d = dims[2];
   if (h < 0 || w < 0 || d < 0) return fail(TP_E_SHAPE, "tp_sample3_grid_nhwc_f32: bad dims %d %d %d", h, w, d);
@@ -200,7 +204,10 @@ static int grid_entry(const tp_plane planes[3], int32_t C, const float* queries,
   // lattice path needs 16-byte aligned k-runs; anything else goes through the per-query kernel
   if ((d & 3) || (reinterpret_cast<uintptr_t>(out) & 15) || arith == 2 || Q == 0 || Q * 3 >= ((int64_t)1 << 31)) {
     if (gen) return Q == 0 ? 0 : fail(TP_E_SHAPE, "tp_sample3_lattice_nhwc_f32: needs d %% 4 == 0, a 16-byte aligned out and h*w*d*3 < 2^31 (got %d %d %d)", h, w, d);
-    return tp_sample3_nhwc_f32(planes, C, queries, Q, batch, sg, arith, out, stream);
+    if (Q == 0) return 0;
+    if (planes_nchw)
+      if (int rc = tp_planes3_nchw_to_nhwc_f32(planes_nchw, nhwc_dst, batch, C, stream)) return rc;
+    return sample3_flat(planes, C, queries, Q, batch, sg, arith, out, stream, planes_nchw != nullptr);
   }
   if (C <= 0 || (C & 3)) return fail(TP_E_SHAPE, "tp_sample3_grid_nhwc_f32: C=%d must be a positive multiple of 4", C);
   if (batch <= 0) return fail(TP_E_SHAPE, "tp_sample3_grid_nhwc_f32: bad B=%d", batch);
@@ -248,8 +255,18 @@ static int grid_entry(const tp_plane planes[3], int32_t C, const float* queries,
   if (nblocks(bi) >= ((int64_t)1 << 30)) return fail(TP_E_SHAPE, "tp_sample3_grid_nhwc_f32: too many queries");
   G.nblocks = (int)nblocks(bi);
   cudaStream_t s = (cudaStream_t)stream;
+  if (planes_nchw) {
+    // Conversion launch first. The decode becomes its programmatic dependent only when every CTA gets a single block
+    // (roi: 13.4 vs 15.1 us): dependents are placed on the SMs in the order the conversion CTAs retire, and the
+    // persistent grid's static block -> CTA map then no longer spreads the expensive blocks (all three planes in
+    // range) evenly over the SMs — 640k lattice 28.5 us as a dependent vs 27.0 us in plain stream order, wherever the
+    // wait is placed (top of the kernel, after the first block's footprints, before the first gather).
+    if (int rc = tp_planes3_nchw_to_nhwc_f32(planes_nchw, nhwc_dst, batch, C, stream)) return rc;
+    pdl = G.nblocks <= kGridCtasPerSm * kSMs;
+  }
+  G.pdl = pdl ? 1 : 0;
 #define TP_GRID_G(A, C4T, BI) \
-  if (gen) launch_grid<A, C4T, BI, true>(G, batch, s); else launch_grid<A, C4T, BI, false>(G, batch, s);
+  if (gen) launch_grid<A, C4T, BI, true>(G, batch, s, pdl); else launch_grid<A, C4T, BI, false>(G, batch, s, pdl);
 #define TP_GRID_B(A, C4T) \
   switch (cfg) { case 0: TP_GRID_G(A, C4T, 8) break; default: TP_GRID_G(A, C4T, 4) break; }
 #define TP_GRID_C(A)                                                      \
@@ -285,22 +302,20 @@ extern "C" int tp_sample3_grid_nchw_f32(const tp_plane planes_nchw[3], int32_t C
                                         const int32_t dims[3], int32_t batch, const tp_sample_geom* sg,
                                         int32_t arith, float* out, float* ws, int64_t ws_floats,
                                         void* stream) {
-  if (!planes_nchw || !ws) return fail(TP_E_NULL, "tp_sample3_grid_nchw_f32: null argument");
+  if (!queries) return fail(TP_E_NULL, "tp_sample3_grid_nchw_f32: null queries");
   tp_plane nhwc[3];
-  int64_t need = 0;
-  for (int k = 0; k < 3; ++k) need += (int64_t)batch * C * planes_nchw[k].H * planes_nchw[k].W;
-  if (ws_floats < need)
-    return fail(TP_E_WORKSPACE, "tp_sample3_grid_nchw_f32: workspace %lld < %lld floats", (long long)ws_floats, (long long)need);
-  float* wp = ws;
   float* dsts[3];
-  for (int k = 0; k < 3; ++k) {
-    dsts[k] = wp;
-    nhwc[k].data = wp;
-    nhwc[k].H = planes_nchw[k].H;
-    nhwc[k].W = planes_nchw[k].W;
-    nhwc[k].batch_stride = (int64_t)C * planes_nchw[k].H * planes_nchw[k].W;
-    wp += (int64_t)batch * nhwc[k].batch_stride;
-  }
-  if (int rc = tp_planes3_nchw_to_nhwc_f32(planes_nchw, dsts, batch, C, stream)) return rc;
-  return tp_sample3_grid_nhwc_f32(nhwc, C, queries, dims, batch, sg, arith, out, stream);
+  if (int rc = planes3_workspace("tp_sample3_grid_nchw_f32", planes_nchw, C, batch, ws, ws_floats, nhwc, dsts)) return rc;
+  return grid_entry(nhwc, C, queries, nullptr, nullptr, dims, batch, sg, arith, out, stream, planes_nchw, dsts);
+}
+
+extern "C" int tp_sample3_lattice_nchw_f32(const tp_plane planes_nchw[3], int32_t C, const int32_t dims[3],
+                                           const float origin[3], const float step[3], int32_t batch,
+                                           const tp_sample_geom* sg, int32_t arith, float* out, float* ws,
+                                           int64_t ws_floats, void* stream) {
+  if (!origin || !step) return fail(TP_E_NULL, "tp_sample3_lattice_nchw_f32: null lattice");
+  tp_plane nhwc[3];
+  float* dsts[3];
+  if (int rc = planes3_workspace("tp_sample3_lattice_nchw_f32", planes_nchw, C, batch, ws, ws_floats, nhwc, dsts)) return rc;
+  return grid_entry(nhwc, C, nullptr, origin, step, dims, batch, sg, arith, out, stream, planes_nchw, dsts);
 }

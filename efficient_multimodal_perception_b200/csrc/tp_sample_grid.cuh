@@ -13,6 +13,7 @@ struct GridParams {
   int vec_ok;
   // generated lattice (tp_sample3_lattice_nhwc_f32): q_a(n) = (n + 0.5) * gen_step[a] + gen_org[a], S.queries == nullptr
   float gen_org[3], gen_step[3];
+  int pdl;  // launched as the programmatic dependent of the layout conversion: wait before the first plane read
 };
 
 // roi()'s voxel centres, op by op (triplane_occ.py:311-316: three separate fp32 tensor ops, never contracted)

@@ -315,6 +315,7 @@ sample3_grid_head_kernel(const __grid_constant__ HeadParams HP) {
       blk = next;
       continue;
     }
+    pdl_wait();  // first read of the planes (tp_common.cuh); blocks outside all of them never get here
     if (!separable) {
       phase = fallback_block<ARITH>(P, q00, wd, G.d, ni, nj, nk, pl0, pl1, pl2, smem, tmem, mbar1, phase, lg, HP.ncls, e_ok);
       zeroed = 0;  // (the tables themselves are untouched, but keep the invariant simple)
@@ -460,10 +461,9 @@ sample3_grid_head_kernel(const __grid_constant__ HeadParams HP) {
 
 using namespace tp;
 
-extern "C" int tp_sample3_grid_head_tf32(const tp_plane planes[3], const float* queries, const int32_t dims[3],
-                                         int32_t batch, const tp_sample_geom* sg, int32_t arith, const float* w1,
-                                         const float* w2, const float* w3, int32_t num_classes, float* logits,
-                                         void* stream) {
+static int grid_head_entry(const tp_plane planes[3], const float* queries, const int32_t dims[3], int32_t batch,
+                           const tp_sample_geom* sg, int32_t arith, const float* w1, const float* w2, const float* w3,
+                           int32_t num_classes, float* logits, void* stream, bool pdl) {
   constexpr int C = kMlpC;
   if (!dims) return fail(TP_E_NULL, "tp_sample3_grid_head_tf32: null dims");
   const int h = dims[0], w = dims[1], d = dims[2];
@@ -520,8 +520,26 @@ extern "C" int tp_sample3_grid_head_tf32(const tp_plane planes[3], const float* 
   const int ai = arith == TP_ARITH_TORCH_CUDA ? 0 : 1;
   if (ai == 0) TP_CUDA(opt_in_smem<sample3_grid_head_kernel<TP_ARITH_TORCH_CUDA>>(kHeadSmem));
   else TP_CUDA(opt_in_smem<sample3_grid_head_kernel<TP_ARITH_TORCH_CPU>>(kHeadSmem));
-  if (ai == 0) sample3_grid_head_kernel<TP_ARITH_TORCH_CUDA><<<grid, kGridThreads, kHeadSmem, s>>>(HP);
-  else sample3_grid_head_kernel<TP_ARITH_TORCH_CPU><<<grid, kGridThreads, kHeadSmem, s>>>(HP);
+  if (ai == 0) launch_kernel(sample3_grid_head_kernel<TP_ARITH_TORCH_CUDA>, grid, kGridThreads, kHeadSmem, s, pdl, HP);
+  else launch_kernel(sample3_grid_head_kernel<TP_ARITH_TORCH_CPU>, grid, kGridThreads, kHeadSmem, s, pdl, HP);
   TP_LAUNCH_CHECK("sample3_grid_head_kernel");
   return 0;
+}
+
+extern "C" int tp_sample3_grid_head_tf32(const tp_plane planes[3], const float* queries, const int32_t dims[3],
+                                         int32_t batch, const tp_sample_geom* sg, int32_t arith, const float* w1,
+                                         const float* w2, const float* w3, int32_t num_classes, float* logits,
+                                         void* stream) {
+  return grid_head_entry(planes, queries, dims, batch, sg, arith, w1, w2, w3, num_classes, logits, stream, false);
+}
+
+extern "C" int tp_sample3_grid_head_nchw_tf32(const tp_plane planes_nchw[3], const float* queries,
+                                              const int32_t dims[3], int32_t batch, const tp_sample_geom* sg,
+                                              int32_t arith, const float* w1, const float* w2, const float* w3,
+                                              int32_t num_classes, float* logits, float* ws, int64_t ws_floats,
+                                              void* stream) {
+  if (dims && (int64_t)dims[0] * dims[1] * dims[2] == 0) return 0;
+  tp_plane nhwc[3];
+  if (int rc = planes3_to_workspace("tp_sample3_grid_head_nchw_tf32", planes_nchw, kMlpC, batch, ws, ws_floats, nhwc, stream)) return rc;
+  return grid_head_entry(nhwc, queries, dims, batch, sg, arith, w1, w2, w3, num_classes, logits, stream, true);
 }

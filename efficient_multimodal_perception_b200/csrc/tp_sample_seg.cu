@@ -86,6 +86,7 @@ sample3_seg_kernel(const SegParams G) {
     const bool tile_empty = __all_sync(0xffffffffu, anymask == 0);
     __syncwarp();
     if (BACKWARD && tile_empty) continue;
+    if (!BACKWARD && !tile_empty) pdl_wait();  // first read of the planes (tp_common.cuh)
     for (int ch = 0; ch < nchunk; ++ch) {
       const bool cvalid = ch * 32 + l8 * 4 < C;
 #pragma unroll 2
@@ -175,10 +176,9 @@ static int seg_fill(SegParams& G, const char* who, const tp_plane planes[3], int
 
 using namespace tp;
 
-extern "C" int tp_sample3_seg_nhwc_f32(const tp_plane planes[3], int32_t C, const float* queries, int64_t total,
-                                       const int64_t* seg_offsets, const int32_t* seg_batch, int32_t nseg,
-                                       int32_t batch, const tp_sample_geom* sg, int32_t arith, float* out,
-                                       void* stream) {
+static int seg_entry(const tp_plane planes[3], int32_t C, const float* queries, int64_t total,
+                     const int64_t* seg_offsets, const int32_t* seg_batch, int32_t nseg, int32_t batch,
+                     const tp_sample_geom* sg, int32_t arith, float* out, void* stream, bool pdl) {
   if (total == 0) return 0;
   SegParams G;
   if (int rc = seg_fill(G, "tp_sample3_seg_nhwc_f32", planes, C, queries, total, seg_offsets, seg_batch, nseg, batch, sg,
@@ -189,10 +189,27 @@ extern "C" int tp_sample3_seg_nhwc_f32(const tp_plane planes[3], int32_t C, cons
   const int64_t cap = (int64_t)kSMs * 8;
   const int grid = (int)(need < cap ? need : cap);
   cudaStream_t s = (cudaStream_t)stream;
-  if (arith == TP_ARITH_TORCH_CUDA) sample3_seg_kernel<TP_ARITH_TORCH_CUDA, false><<<grid, kSegWarps * 32, 0, s>>>(G);
-  else sample3_seg_kernel<TP_ARITH_TORCH_CPU, false><<<grid, kSegWarps * 32, 0, s>>>(G);
+  if (arith == TP_ARITH_TORCH_CUDA) launch_kernel(sample3_seg_kernel<TP_ARITH_TORCH_CUDA, false>, grid, kSegWarps * 32, 0, s, pdl, G);
+  else launch_kernel(sample3_seg_kernel<TP_ARITH_TORCH_CPU, false>, grid, kSegWarps * 32, 0, s, pdl, G);
   TP_LAUNCH_CHECK("sample3_seg_kernel");
   return 0;
+}
+
+extern "C" int tp_sample3_seg_nhwc_f32(const tp_plane planes[3], int32_t C, const float* queries, int64_t total,
+                                       const int64_t* seg_offsets, const int32_t* seg_batch, int32_t nseg,
+                                       int32_t batch, const tp_sample_geom* sg, int32_t arith, float* out,
+                                       void* stream) {
+  return seg_entry(planes, C, queries, total, seg_offsets, seg_batch, nseg, batch, sg, arith, out, stream, false);
+}
+
+extern "C" int tp_sample3_seg_nchw_f32(const tp_plane planes_nchw[3], int32_t C, const float* queries, int64_t total,
+                                       const int64_t* seg_offsets, const int32_t* seg_batch, int32_t nseg,
+                                       int32_t batch, const tp_sample_geom* sg, int32_t arith, float* out, float* ws,
+                                       int64_t ws_floats, void* stream) {
+  if (total == 0) return 0;
+  tp_plane nhwc[3];
+  if (int rc = planes3_to_workspace("tp_sample3_seg_nchw_f32", planes_nchw, C, batch, ws, ws_floats, nhwc, stream)) return rc;
+  return seg_entry(nhwc, C, queries, total, seg_offsets, seg_batch, nseg, batch, sg, arith, out, stream, true);
 }
 
 extern "C" int tp_sample3_seg_backward_nhwc_f32(const tp_plane gplanes_nhwc[3], int32_t C, const float* queries,

@@ -443,11 +443,12 @@ def sample3(planes: Union[torch.Tensor, Sequence[torch.Tensor]], queries: torch.
                 L.check(L.lib().tp_sample3_grid_nchw_f32(C.byref(arr), Cc, queries.data_ptr(), C.byref(dims), B, C.byref(sg),
                                                          _ARITH[arith], out.data_ptr(), ws.data_ptr(), ws_floats,
                                                          _stream(queries)), "tp_sample3_grid_nchw_f32")
+                launch_count += 2
             else:
                 L.check(L.lib().tp_sample3_nchw_f32(C.byref(arr), Cc, queries.data_ptr(), Q, B, C.byref(sg), _ARITH[arith],
                                                     out.data_ptr(), ws.data_ptr(), ws_floats, _stream(queries)),
                         "tp_sample3_nchw_f32")
-            launch_count += 2
+                launch_count += 2
         return out
     nhwc = list(planes)
     Cc = nhwc[0].shape[-1]
@@ -657,15 +658,30 @@ def sample3_head(planes, queries: torch.Tensor, lo, vs, half, w1: torch.Tensor, 
     h, w, d = (int(v) for v in grid_dims)
     if h * w * d != Q:
         raise TriplaneError(f"sample3_head: grid_dims {tuple(grid_dims)} do not multiply to Q={Q}")
-    nhwc = list(planes) if channels_last else planes_to_channels_last(planes)
     ws = []
     for k, wt in enumerate((w1, w2, w3)):
         _need_cuda(wt, f"w{k + 1}")
         ws.append(wt.reshape(wt.shape[0], wt.shape[1]).contiguous())
-    Cc, ncls = nhwc[0].shape[-1], ws[2].shape[0]
-    if Cc != 32 or tuple(ws[0].shape) != (64, 32) or tuple(ws[1].shape) != (32, 64) or ws[2].shape[1] != 32:
-        raise TriplaneError(f"sample3_head: this build fuses C=32 -> 64 -> 32 -> ncls; got C={Cc}, weights "
-                            f"{[tuple(x.shape) for x in ws]}")
+    ncls = ws[2].shape[0]
+    sg = L.make_sample_geom(lo, vs, half)
+    dims = (C.c_int32 * 3)(h, w, d)
+    if not channels_last:
+        arr, nws, nws_floats, Bp, Cc, keep = _nchw_planes(planes, "sample3_head")
+    else:
+        nhwc = list(planes)
+        Cc, Bp = nhwc[0].shape[-1], nhwc[0].shape[0]
+    if Bp != B or Cc != 32 or tuple(ws[0].shape) != (64, 32) or tuple(ws[1].shape) != (32, 64) or ws[2].shape[1] != 32:
+        raise TriplaneError(f"sample3_head: this build fuses C=32 -> 64 -> 32 -> ncls on B={B} samples; got B={Bp}, C={Cc}, "
+                            f"weights {[tuple(x.shape) for x in ws]}")
+    out = torch.empty((B, ncls, Q), dtype=torch.float32, device=queries.device)
+    if not channels_last:
+        if Q:
+            L.check(L.lib().tp_sample3_grid_head_nchw_tf32(C.byref(arr), queries.data_ptr(), C.byref(dims), B, C.byref(sg),
+                                                           _ARITH[arith], ws[0].data_ptr(), ws[1].data_ptr(), ws[2].data_ptr(),
+                                                           ncls, out.data_ptr(), nws.data_ptr(), nws_floats, _stream(queries)),
+                    "tp_sample3_grid_head_nchw_tf32")
+            launch_count += 2
+        return out
     arr = (L.tp_plane * 3)()
     for k, p in enumerate(nhwc):
         _need_cuda(p, f"plane {k}")
@@ -674,9 +690,6 @@ def sample3_head(planes, queries: torch.Tensor, lo, vs, half, w1: torch.Tensor, 
         arr[k].data = p.data_ptr()
         arr[k].batch_stride = p.stride(0)
         arr[k].H, arr[k].W = p.shape[1], p.shape[2]
-    sg = L.make_sample_geom(lo, vs, half)
-    dims = (C.c_int32 * 3)(h, w, d)
-    out = torch.empty((B, ncls, Q), dtype=torch.float32, device=queries.device)
     L.check(L.lib().tp_sample3_grid_head_tf32(C.byref(arr), queries.data_ptr(), C.byref(dims), B, C.byref(sg), _ARITH[arith],
                                               ws[0].data_ptr(), ws[1].data_ptr(), ws[2].data_ptr(), ncls, out.data_ptr(),
                                               _stream(queries)), "tp_sample3_grid_head_tf32")
@@ -733,6 +746,31 @@ def _nhwc_planes(planes, B: Optional[int], channels_last: bool, who: str):
     return nhwc, arr
 
 
+def _nchw_planes(planes, who: str):
+    """Reference-layout planes for the *_nchw_* entry points (conversion + decode chained inside ONE C-ABI call by
+    programmatic dependent launch) -> (tp_plane array, workspace, workspace floats, B, C, keep-alive list)"""
+    if isinstance(planes, torch.Tensor):
+        if planes.dim() != 5 or planes.shape[1] != 3:
+            raise TriplaneError(f"{who}: stacked triplane must be [B,3,C,H,W], got {tuple(planes.shape)}")
+        planes = [planes[:, 0], planes[:, 1], planes[:, 2]]
+    if len(planes) != 3:
+        raise TriplaneError(f"{who}: expected three planes")
+    srcs = []
+    for k, p in enumerate(planes):
+        _need_cuda(p, f"plane {k}")
+        if p.dim() != 4:
+            raise TriplaneError(f"{who}: plane {k} must be [B,C,H,W], got {tuple(p.shape)}")
+        if p.stride(3) != 1 or p.stride(2) != p.shape[3] or p.stride(1) != p.shape[2] * p.shape[3]:
+            p = p.contiguous()
+        srcs.append(p)
+    B, Cc = srcs[0].shape[0], srcs[0].shape[1]
+    if any(p.shape[0] != B or p.shape[1] != Cc for p in srcs):
+        raise TriplaneError(f"{who}: planes must share batch and channel sizes")
+    ws_floats = sum(B * Cc * p.shape[2] * p.shape[3] for p in srcs)
+    ws = torch.empty(ws_floats, dtype=torch.float32, device=srcs[0].device)
+    return _plane_array(srcs), ws, ws_floats, B, Cc, srcs
+
+
 @_on_device
 def sample3_lattice(planes, dims: Sequence[int], origin, step, lo, vs, half, *, arith: str = "cuda",
                     channels_last: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -740,15 +778,24 @@ def sample3_lattice(planes, dims: Sequence[int], origin, step, lo, vs, half, *, 
     [B,h,w,d,3] tensor: the coordinates are generated in the kernel. Returns [B, C, h*w*d], bit-identical to
     sample3(planes, roi_points, grid_dims=dims)."""
     global launch_count
-    nhwc, arr = _nhwc_planes(planes, None, channels_last, "sample3_lattice")
-    B, Cc = nhwc[0].shape[0], nhwc[0].shape[-1]
     h, w, d = (int(v) for v in dims)
     Q = h * w * d
-    out = _check_out(out, B, Cc, Q, nhwc[0].device)
     sg = L.make_sample_geom(lo, vs, half)
     cd = (C.c_int32 * 3)(h, w, d)
     org = (C.c_float * 3)(*[float(v) for v in origin[:3]])
     stp = (C.c_float * 3)(*[float(v) for v in step[:3]])
+    if not channels_last:
+        arr, ws, ws_floats, B, Cc, keep = _nchw_planes(planes, "sample3_lattice")
+        out = _check_out(out, B, Cc, Q, keep[0].device)
+        if Q:
+            L.check(L.lib().tp_sample3_lattice_nchw_f32(C.byref(arr), Cc, C.byref(cd), C.byref(org), C.byref(stp), B,
+                                                        C.byref(sg), _ARITH[arith], out.data_ptr(), ws.data_ptr(), ws_floats,
+                                                        _stream(keep[0])), "tp_sample3_lattice_nchw_f32")
+            launch_count += 2
+        return out
+    nhwc, arr = _nhwc_planes(planes, None, True, "sample3_lattice")
+    B, Cc = nhwc[0].shape[0], nhwc[0].shape[-1]
+    out = _check_out(out, B, Cc, Q, nhwc[0].device)
     L.check(L.lib().tp_sample3_lattice_nhwc_f32(C.byref(arr), Cc, C.byref(cd), C.byref(org), C.byref(stp), B, C.byref(sg),
                                                 _ARITH[arith], out.data_ptr(), _stream(nhwc[0])), "tp_sample3_lattice_nhwc_f32")
     launch_count += 1 if Q else 0
@@ -772,11 +819,20 @@ def sample3_segments(planes, queries: torch.Tensor, seg_offsets: torch.Tensor, s
     nseg = seg_offsets.numel() - 1
     if nseg < 1 or (seg_batch is not None and seg_batch.numel() != nseg):
         raise TriplaneError("sample3_segments: seg_offsets must be [S+1] with S >= 1 and seg_batch [S]")
-    nhwc, arr = _nhwc_planes(planes, None, channels_last, "sample3_segments")
-    B, Cc = nhwc[0].shape[0], nhwc[0].shape[-1]
     T = queries.shape[0]
-    out = torch.empty((T, Cc), dtype=torch.float32, device=queries.device)
     sg = L.make_sample_geom(lo, vs, half)
+    if not channels_last:
+        arr, ws, ws_floats, B, Cc, keep = _nchw_planes(planes, "sample3_segments")
+        out = torch.empty((T, Cc), dtype=torch.float32, device=queries.device)
+        if T:
+            L.check(L.lib().tp_sample3_seg_nchw_f32(C.byref(arr), Cc, queries.data_ptr(), T, seg_offsets.data_ptr(),
+                                                    _ptr(seg_batch), nseg, B, C.byref(sg), _ARITH[arith], out.data_ptr(),
+                                                    ws.data_ptr(), ws_floats, _stream(queries)), "tp_sample3_seg_nchw_f32")
+            launch_count += 2
+        return out
+    nhwc, arr = _nhwc_planes(planes, None, True, "sample3_segments")
+    B, Cc = nhwc[0].shape[0], nhwc[0].shape[-1]
+    out = torch.empty((T, Cc), dtype=torch.float32, device=queries.device)
     L.check(L.lib().tp_sample3_seg_nhwc_f32(C.byref(arr), Cc, queries.data_ptr(), T, seg_offsets.data_ptr(), _ptr(seg_batch),
                                             nseg, B, C.byref(sg), _ARITH[arith], out.data_ptr(), _stream(queries)),
             "tp_sample3_seg_nhwc_f32")

@@ -227,6 +227,24 @@ TP_API int tp_sample3_lattice_nhwc_f32(const tp_plane planes_nhwc[3], int32_t C,
                                 const float origin[3], const float step[3], int32_t batch,
                                 const tp_sample_geom* sg, int32_t arith, float* out, void* stream);
 
+/* Reference-layout (NCHW) planes in, for every decode entry point: ONE C-ABI call = the NCHW -> channels-last conversion
+ * launch + the decode launch, chained by programmatic dependent launch (the decode grid is scheduled while the
+ * conversion runs and does everything that does not need the planes -- query load, lattice check, tap records, blocks
+ * outside all planes -- before it waits for the converted copy). nhwc_workspace >= sum_p B*C*H_p*W_p floats. Results
+ * are those of the *_nhwc_* entry point on the converted planes, bit for bit. */
+TP_API int tp_sample3_lattice_nchw_f32(const tp_plane planes_nchw[3], int32_t C, const int32_t dims[3],
+                                const float origin[3], const float step[3], int32_t batch,
+                                const tp_sample_geom* sg, int32_t arith, float* out,
+                                float* nhwc_workspace, int64_t nhwc_workspace_floats, void* stream);
+TP_API int tp_sample3_seg_nchw_f32(const tp_plane planes_nchw[3], int32_t C, const float* queries, int64_t total,
+                            const int64_t* seg_offsets, const int32_t* seg_batch, int32_t nseg, int32_t batch,
+                            const tp_sample_geom* sg, int32_t arith, float* out,
+                            float* nhwc_workspace, int64_t nhwc_workspace_floats, void* stream);
+TP_API int tp_sample3_grid_head_nchw_tf32(const tp_plane planes_nchw[3], const float* queries, const int32_t dims[3],
+                                   int32_t batch, const tp_sample_geom* sg, int32_t arith, const float* w1,
+                                   const float* w2, const float* w3, int32_t num_classes, float* logits,
+                                   float* nhwc_workspace, int64_t nhwc_workspace_floats, void* stream);
+
 /* Ragged point subsets in ONE launch: the per-(sample, camera) loops around sample_points_triplane in the contrastive
  * branches (triplane.py:438-458: B x 6 SAM-labelled subsets; point_triplane.py:365-372, 389-403). queries [T, 3] = the
  * segments concatenated; seg_offsets [S+1] int64 (device); seg_batch [S] int32 (device; NULL: segment s reads sample

@@ -348,3 +348,107 @@ def test_reduce_cam_channels_first_lift_matches_reference_order():
         assert normwise(b, a) < 1e-5
         for x, y in zip(proj(cropped, gi, fused_cam), proj(cropped, gi, ref_cam)):
             assert normwise(x, y) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------
+# reference-layout (NCHW) entry points: conversion -> decode chained by programmatic dependent launch
+# ---------------------------------------------------------------------------------------------
+def test_nchw_entry_points_equal_channels_last_entry_points_back_to_back():
+    """Every *_nchw_* entry point (the decode grid starts while the conversion kernel is still running and waits for the
+    converted planes on the device) gives, bit for bit, what the *_nhwc_* entry point gives on pre-converted planes —
+    20 back-to-back iterations with different planes each time and no host synchronisation in between, so a decode that
+    read the workspace before the conversion finished (or a conversion that overwrote it early) would show."""
+    gen = torch.Generator().manual_seed(11)
+    B, Cc, S = 2, 32, 128
+    dims = (40, 24, 16)
+    lo, vs, half = synth.OCC["triplane_range"][:3], synth.OCC["triplane_voxel_size"], [S / 2] * 3
+    pts = cu(synth.lattice(dims, (0.7, 0.9, 0.5), (-14.0, -11.0, -5.0)).reshape(1, -1, 3).repeat(B, 1, 1))
+    flat = cu((torch.rand(B, 5000, 3, generator=gen) - 0.5) * torch.tensor([60.0, 60.0, 10.0]))
+    segq = flat.reshape(-1, 3)[:7000].contiguous()
+    seg_off = cu(torch.tensor([0, 0, 2500, 2501, 7000], dtype=torch.int64))
+    seg_b = cu(torch.tensor([1, 0, 1, 0], dtype=torch.int32))
+    head = emp.Mlp(32, 5).to(DEV)
+    w = [head.conv1[0].weight, head.conv2[0].weight, head.conv3[0].weight]
+    tris = [cu(torch.randn(B, 3, Cc, S, S, generator=gen)) for _ in range(20)]
+    got = []
+    with torch.no_grad():
+        for t in tris:
+            got.append((ops.sample3(t, pts, lo, vs, half, grid_dims=dims),
+                        ops.sample3(t, flat, lo, vs, half),
+                        ops.sample3_lattice(t, dims, (-14.0, -11.0, -5.0), (0.7, 0.9, 0.5), lo, vs, half),
+                        ops.sample3_segments(t, segq, seg_off, seg_b, lo, vs, half),
+                        ops.sample3_head(t, pts, lo, vs, half, *w, grid_dims=dims)))
+        torch.cuda.synchronize()
+        for t, g in zip(tris, got):
+            nhwc = ops.planes_to_channels_last([t[:, 0], t[:, 1], t[:, 2]])
+            torch.cuda.synchronize()
+            want = (ops.sample3(nhwc, pts, lo, vs, half, grid_dims=dims, channels_last=True),
+                    ops.sample3(nhwc, flat, lo, vs, half, channels_last=True),
+                    ops.sample3_lattice(nhwc, dims, (-14.0, -11.0, -5.0), (0.7, 0.9, 0.5), lo, vs, half, channels_last=True),
+                    ops.sample3_segments(nhwc, segq, seg_off, seg_b, lo, vs, half, channels_last=True),
+                    ops.sample3_head(nhwc, pts, lo, vs, half, *w, grid_dims=dims, channels_last=True))
+            for a, b in zip(g, want):
+                assert torch.equal(a, b)
+    assert float(got[0][0].abs().max()) > 0 and float(got[0][3].abs().max()) > 0
+
+
+def test_nchw_entry_point_under_graph_replay_sees_new_planes():
+    """The conversion -> decode pair captured into a CUDA graph (the programmatic edge survives capture): replays after
+    the planes were overwritten in place return the new planes' samples."""
+    gen = torch.Generator().manual_seed(12)
+    dims = (48, 48, 16)
+    lo, vs, half = synth.OCC["triplane_range"][:3], synth.OCC["triplane_voxel_size"], [64.0] * 3
+    pts = cu(synth.lattice(dims, (1.0, 1.0, 0.5), (-24.0, -24.0, -5.0)).reshape(1, -1, 3))
+    tri = cu(torch.randn(1, 3, 32, 128, 128, generator=gen))
+    out = torch.empty(1, 32, pts.shape[1], device=DEV)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        ops.sample3(tri, pts, lo, vs, half, grid_dims=dims, out=out)  # warm-up (smem opt-in) outside capture
+        s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            ops.sample3(tri, pts, lo, vs, half, grid_dims=dims, out=out)
+        for it in range(6):
+            tri.copy_(torch.randn(1, 3, 32, 128, 128, generator=gen))
+            g.replay()
+            s.synchronize()
+            nhwc = ops.planes_to_channels_last([tri[:, 0], tri[:, 1], tri[:, 2]])
+            want = ops.sample3(nhwc, pts, lo, vs, half, grid_dims=dims, channels_last=True)
+            assert torch.equal(out, want), f"replay {it}"
+
+
+def test_nchw_lattice_entry_two_streams_and_fallback_blocks():
+    """tp_sample3_grid_nchw_f32 from two streams at once (two conversion -> dependent decode pairs sharing the GPU),
+    with jittered blocks (per-query fallback inside the launch) and a large batch: bit-identical to the channels-last
+    entry point."""
+    gen = torch.Generator().manual_seed(21)
+    lo, vs, half = synth.OCC["triplane_range"][:3], synth.OCC["triplane_voxel_size"], [64.0] * 3
+    lat = synth.occ_gt_lattice()
+    dims = tuple(lat.shape[:3])
+    pts = cu(lat.reshape(1, -1, 3))
+    jit = pts.clone()
+    jit[0, 5000:5400, 0] += 0.013  # some blocks are no lattice any more
+    tris = [cu(torch.randn(1, 3, 32, 128, 128, generator=gen)) for _ in range(4)]
+    want, want_j = [], []
+    for t in tris:
+        nhwc = ops.planes_to_channels_last([t[:, 0], t[:, 1], t[:, 2]])
+        want.append(ops.sample3(nhwc, pts, lo, vs, half, grid_dims=dims, channels_last=True))
+        want_j.append(ops.sample3(nhwc, jit, lo, vs, half, grid_dims=dims, channels_last=True))
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = {}
+    for rep in range(6):
+        for k, (st, q) in enumerate(((s1, pts), (s2, jit))):
+            with torch.cuda.stream(st):
+                outs[(rep, k)] = ops.sample3(tris[(rep + k) % 4], q, lo, vs, half, grid_dims=dims)
+    torch.cuda.synchronize()
+    for rep in range(6):
+        assert torch.equal(outs[(rep, 0)], want[rep % 4])
+        assert torch.equal(outs[(rep, 1)], want_j[(rep + 1) % 4])
+    B = 8
+    tri8 = cu(torch.randn(B, 3, 32, 128, 128, generator=gen))
+    roi = synth.roi_lattice()
+    p8 = cu(roi.reshape(1, -1, 3).repeat(B, 1, 1))
+    got = ops.sample3(tri8, p8, lo, vs, half, grid_dims=tuple(roi.shape[:3]))
+    nhwc = ops.planes_to_channels_last([tri8[:, 0], tri8[:, 1], tri8[:, 2]])
+    assert torch.equal(got, ops.sample3(nhwc, p8, lo, vs, half, grid_dims=tuple(roi.shape[:3]), channels_last=True))

@@ -32,7 +32,14 @@ namespace tp {
 constexpr int kTileFloats = 4096;  // 16 KB of output per tile
 constexpr int kMaxCpt = 256;       // cells per tile is capped (small C): bounds the per-buffer counters
 constexpr int kRedThreads = 128;   // small CTAs, ~10 resident per SM: that many tile chains in flight
-constexpr int kRedCtasPerSm = 10;
+#ifndef TP_RED_CTAS
+#define TP_RED_CTAS 10
+#endif
+#ifndef TP_RED_ROWS
+#define TP_RED_ROWS 4
+#endif
+constexpr int kRedCtasPerSm = TP_RED_CTAS;
+constexpr int kRows = TP_RED_ROWS;  // rows a warp has in flight (C = 128 path)
 constexpr int kGrab = 4;           // tiles taken per scheduler atomic
 constexpr int kHeavy = 48;         // tiles with at least this many points are reduced first
 constexpr int kSplit = 384;        // tiles with at least this many points are cut into items of kSub list entries,
@@ -231,8 +238,8 @@ encode_fill_kernel(const EncodeParams P) {
 // order-preserving float <-> uint32 (max on keys == max on floats; +NaN is the largest key, so a NaN
 // feature propagates like torch.amax; -0 < +0)
 __device__ __forceinline__ unsigned f2key(float f) {
-  unsigned u = __float_as_uint(f);
-  return u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u);
+  const unsigned u = __float_as_uint(f);
+  return u ^ ((unsigned)((int)u >> 31) | 0x80000000u);  // negative: flip all bits; else: flip the sign (shift + one LOP3)
 }
 __device__ __forceinline__ float key2f(unsigned k) {
   return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu));
@@ -256,6 +263,12 @@ __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+__device__ __forceinline__ float ld_keep_f1(const float* p, unsigned long long pol) {
+  float r;
+  asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol));
+  return r;
+}
+
 __device__ __forceinline__ float4 add4(float4 a, float4 b) {
   return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
 }
@@ -271,20 +284,20 @@ __device__ unsigned long long g_enc_sched[kEncSchedSlots][4];  // [next tile, fi
 // metadata -> CSR entries -> point rows, three dependent global loads (~3 us); the stream of dense
 // output needs a 16 KB tile per SM every ~0.4 us, so many independent tile chains must be in flight
 // per SM — measured: 3 CTAs/SM with 32 KB tiles 117 us, one 16-warp CTA per SM 210 us (profiles/).
-template <int REDUCE>
+// C128: the configs' channel count (a row = 32 lanes x 4 floats, 32 cells per tile) known at compile time.
+template <int REDUCE, bool C128>
 __global__ void __launch_bounds__(kRedThreads, kRedCtasPerSm)
 encode_reduce_kernel(const EncodeParams P, int sched_slot) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* s_work = reinterpret_cast<float*>(smem_raw);           // kTileFloats, zero outside touched cells
   int* s_cnt = reinterpret_cast<int*>(s_work + kTileFloats);    // kMaxCpt: points per cell of the tile
   __shared__ long long s_t0;
-  __shared__ int s_npts[kGrab], s_start[kGrab];
-  __shared__ int s_heavy[1][3];  // phase 1: (tile, points, CSR start)
-  __shared__ int s_last, s_split;
+  __shared__ int s_tile[kGrab], s_npts[kGrab], s_start[kGrab], s_split[kGrab];  // the batch of work items in hand
+  __shared__ int s_last;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int kWarps = kRedThreads / 32;
-  const int C = P.C, C4 = P.C4, cpt = P.cpt;
+  const int C = C128 ? 128 : P.C, C4 = C128 ? 32 : P.C4, cpt = C128 ? 32 : P.cpt;
   unsigned long long* sched = g_enc_sched[sched_slot];
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const float fillv = P.partial ? __uint_as_float(0xff800000u) : 0.f;  // -inf or 0 for empty cells
@@ -331,6 +344,42 @@ encode_reduce_kernel(const EncodeParams P, int sched_slot) {
     // (the ATOMS pipe, 4 x 32 lanes per row, was the busiest unit of the previous version)
     for (int e = tid; e < npts; e += kRedThreads) atomicAdd(s_cnt + __ldg(ent + e).y, 1);
     __syncthreads();
+    if (C128) {
+      for (int e0 = warp * kRows; e0 < npts; e0 += kWarps * kRows) {
+        int2 en[kRows];
+#pragma unroll
+        for (int j = 0; j < kRows; ++j) en[j] = (e0 + j < npts) ? __ldg(ent + e0 + j) : make_int2(-1, 0);
+        // Lane l owns words l, l + 32, l + 64, l + 96 of the row: four coalesced 128-byte loads per row, and the four
+        // shared-memory atomics (or stores) of a row are conflict-free — with 16 bytes per lane they were 4-way bank
+        // conflicts (ncu: 12 M of 22 M shared wavefronts on a 10-sweep sample) and the ATOMS pipe the busiest unit.
+        float x[kRows][4];
+#pragma unroll
+        for (int j = 0; j < kRows; ++j) {
+          if (en[j].x < 0) continue;
+          const float* r = P.feats + (int64_t)en[j].x * P.feat_stride + lane;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) x[j][k] = ld_keep_f1(r + 32 * k, pol_in);
+        }
+#pragma unroll
+        for (int j = 0; j < kRows; ++j) {
+          if (en[j].x < 0) continue;
+          float* w = s_work + en[j].y * 128 + lane;
+          if (s_cnt[en[j].y] == 1) {  // warp-uniform: sole owner of the row
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (REDUCE == TP_REDUCE_MAX) reinterpret_cast<unsigned*>(w)[32 * k] = f2key(x[j][k]);
+              else w[32 * k] = x[j][k];
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (REDUCE == TP_REDUCE_MAX) atomicMax(reinterpret_cast<unsigned*>(w) + 32 * k, f2key(x[j][k]));
+              else atomicAdd(w + 32 * k, x[j][k]);
+            }
+          }
+        }
+      }
+    } else
     for (int e0 = warp * 4; e0 < npts; e0 += kWarps * 4) {
       int2 en[4];
 #pragma unroll
@@ -451,79 +500,72 @@ encode_reduce_kernel(const EncodeParams P, int sched_slot) {
     if (tid == 0) { bulk_store(gdst, s_work, (unsigned)ncell * (unsigned)C * 4u, pol_out); in_flight = true; }
   };
 
-  // ---- phase 1: longest tiles first. A tile that collects hundreds of points (the ground plane
-  // folds onto one z row of the yz / xz planes) is a ~50 us chain of gathers for one CTA; started
-  // last it is the tail of the kernel, started first it hides under the streaming of the rest. The
-  // scan pass listed them; CTAs pop them one at a time.
-  // ---- phase 0: items of the split tiles (the longest chains of all, cut into kSub-entry pieces) ------
+  // Work order. Phase 0: items of the split tiles (the longest chains of all, cut into kSub-entry pieces). Phase 1:
+  // the other long tiles — a tile that collects hundreds of points (the ground plane folds onto one z row of the
+  // yz / xz planes) is a ~50 us chain of gathers for one CTA; started last it is the tail of the kernel, started first
+  // it hides under the streaming of the rest (the alloc pass listed them; CTAs pop them one at a time). Phase 2:
+  // everything else in memory order, kGrab tiles per scheduler atomic. ONE call site of process_tile for all three
+  // (inlined three times the kernel was 67 KB of SASS).
   const int nitems = P.split_ctr[1];
-  for (;;) {
-    __syncthreads();
-    if (tid == 0) {
-      const long long i = (long long)atomicAdd(&sched[3], 1ull);
-      s_t0 = i;
-      if (i < nitems) {
-        const int2 it = P.split_item[i];
-        const int t = P.split_tile[it.x];
-        const int np = P.tile_cnt[t];  // stays >= kSplit until the last CTA of the launch cleans up
-        s_heavy[0][0] = t;
-        s_heavy[0][1] = min(kSub, np - it.y * kSub);
-        s_heavy[0][2] = P.tile_start[t] + it.y * kSub;
-        s_split = it.x;
-      }
-    }
-    __syncthreads();
-    if (s_t0 >= nitems) break;
-    process_tile(s_heavy[0][0], s_heavy[0][1], s_heavy[0][2], s_split);
-  }
-
   const int nheavy = P.heavy[0];
-  for (;;) {
+  for (int phase = 0;;) {
     __syncthreads();
-    if (tid == 0) {
-      const long long i = (long long)atomicAdd(&sched[2], 1ull);
-      s_t0 = i;
-      if (i < nheavy) {
-        const int t = P.heavy[1 + i];
-        s_heavy[0][0] = t;
-        s_heavy[0][1] = P.tile_cnt[t];  // stays >= kHeavy until the last CTA cleans up: phase 2 of
-        s_heavy[0][2] = P.tile_start[t];  // other CTAs may already be running and must keep skipping it
-      }
-    }
-    __syncthreads();
-    if (s_t0 >= nheavy) break;
-    process_tile(s_heavy[0][0], s_heavy[0][1], s_heavy[0][2], -1);
-  }
-
-  // ---- phase 2: everything else, in order -----------------------------------------------------
-  for (;;) {
-    __syncthreads();
-    if (tid < kGrab) {
-      long long t0 = 0;
-      if (tid == 0) t0 = (long long)atomicAdd(&sched[0], (unsigned long long)kGrab);
-      t0 = __shfl_sync((1u << kGrab) - 1u, t0, 0);
-      if (tid == 0) s_t0 = t0;
-      const long long t = t0 + tid;
-      int np = 0, st = 0;
-      if (t < P.tiles_total) {
-        np = P.tile_cnt[t];
-        if (np > 0 && np < kHeavy) {
-          st = P.tile_start[t];
-          P.tile_cnt[t] = 0;  // leave the counters clean for the next call
+    int nbatch = 1;
+    if (phase < 2) {
+      if (tid == 0) {
+        const long long i = (long long)atomicAdd(&sched[phase == 0 ? 3 : 2], 1ull);
+        s_t0 = i;
+        if (phase == 0 && i < nitems) {
+          const int2 it = P.split_item[i];
+          const int t = P.split_tile[it.x];
+          const int np = P.tile_cnt[t];  // stays >= kSplit until the last CTA of the launch cleans up
+          s_tile[0] = t;
+          s_npts[0] = min(kSub, np - it.y * kSub);
+          s_start[0] = P.tile_start[t] + it.y * kSub;
+          s_split[0] = it.x;
+        } else if (phase == 1 && i < nheavy) {
+          const int t = P.heavy[1 + i];
+          s_tile[0] = t;
+          s_npts[0] = P.tile_cnt[t];  // stays >= kHeavy until the last CTA cleans up: phase 2 of other CTAs may
+          s_start[0] = P.tile_start[t];  // already be running and must keep skipping it
+          s_split[0] = -1;
         }
       }
-      s_npts[tid] = np;
-      s_start[tid] = st;
+      __syncthreads();
+      if (s_t0 >= (phase == 0 ? nitems : nheavy)) {
+        ++phase;
+        continue;
+      }
+    } else {
+      if (tid < kGrab) {
+        long long t0 = 0;
+        if (tid == 0) t0 = (long long)atomicAdd(&sched[0], (unsigned long long)kGrab);
+        t0 = __shfl_sync((1u << kGrab) - 1u, t0, 0);
+        if (tid == 0) s_t0 = t0;
+        const long long t = t0 + tid;
+        int np = -1, st = 0;  // -1: not this phase's (past the end, or a heavy / split tile)
+        if (t < P.tiles_total) {
+          np = P.tile_cnt[t];
+          if (np >= kHeavy) {
+            np = -1;
+          } else if (np > 0) {
+            st = P.tile_start[t];
+            P.tile_cnt[t] = 0;  // leave the counters clean for the next call
+          }
+        }
+        s_tile[tid] = (int)t;
+        s_npts[tid] = np;
+        s_start[tid] = st;
+        s_split[tid] = -1;
+      }
+      __syncthreads();
+      if (s_t0 >= P.tiles_total) break;
+      nbatch = kGrab;
     }
-    __syncthreads();
-    const int64_t t0 = s_t0;
-    if (t0 >= P.tiles_total) break;
 #pragma unroll 1
-    for (int gi = 0; gi < kGrab; ++gi) {
-      const int64_t t = t0 + gi;
-      if (t >= P.tiles_total) break;
-      if (s_npts[gi] >= kHeavy) continue;  // phase 1's
-      process_tile(t, s_npts[gi], s_start[gi], -1);
+    for (int gi = 0; gi < nbatch; ++gi) {
+      if (s_npts[gi] < 0) continue;
+      process_tile(s_tile[gi], s_npts[gi], s_start[gi], s_split[gi]);
     }
   }
   __syncthreads();
@@ -779,17 +821,18 @@ extern "C" int tp_encode_f32(const float* feats, int64_t feat_stride, int32_t C,
   }
   constexpr int kSmem = kTileFloats * 4 + kMaxCpt * 4;  // 17 KB
   const size_t smem = kSmem;
-  TP_CUDA(opt_in_smem<encode_reduce_kernel<TP_REDUCE_MAX>>(kSmem));
-  TP_CUDA(opt_in_smem<encode_reduce_kernel<TP_REDUCE_MEAN>>(kSmem));
-  TP_CUDA(opt_in_smem<encode_reduce_kernel<TP_REDUCE_SUM>>(kSmem));
   const int64_t ctas = (L.tiles_total + kGrab - 1) / kGrab;
   const int64_t cap = (int64_t)kSMs * kRedCtasPerSm;  // persistent: one resident wave
   const int grid = (int)(ctas < cap ? ctas : cap);
   static std::atomic<unsigned> next_slot{0};
   const int slot = (int)(next_slot.fetch_add(1) % kEncSchedSlots);
-  if (reduce == TP_REDUCE_MAX || reduce == TP_REDUCE_MAX_PARTIAL) encode_reduce_kernel<TP_REDUCE_MAX><<<grid, kRedThreads, smem, s>>>(P, slot);
-  else if (reduce == TP_REDUCE_MEAN) encode_reduce_kernel<TP_REDUCE_MEAN><<<grid, kRedThreads, smem, s>>>(P, slot);
-  else encode_reduce_kernel<TP_REDUCE_SUM><<<grid, kRedThreads, smem, s>>>(P, slot);
+#define TP_RED(R)                                                                              \
+  if (C == 128) encode_reduce_kernel<R, true><<<grid, kRedThreads, smem, s>>>(P, slot);         \
+  else encode_reduce_kernel<R, false><<<grid, kRedThreads, smem, s>>>(P, slot);
+  if (reduce == TP_REDUCE_MAX || reduce == TP_REDUCE_MAX_PARTIAL) { TP_RED(TP_REDUCE_MAX) }
+  else if (reduce == TP_REDUCE_MEAN) { TP_RED(TP_REDUCE_MEAN) }
+  else { TP_RED(TP_REDUCE_SUM) }
+#undef TP_RED
   TP_LAUNCH_CHECK("encode_reduce_kernel");
   return 0;
 }

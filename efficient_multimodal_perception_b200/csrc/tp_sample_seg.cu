@@ -19,6 +19,7 @@ struct SegParams {
   const int64_t* seg_offsets;  // [nseg+1]
   const int32_t* seg_batch;    // [nseg] or nullptr
   int nseg, batch;
+  int bs4[3];                  // plane batch stride in float4 units
   float* gplane[3];            // backward: channels-last gradient planes (pre-zeroed)
   const float* gout;           // backward: [T, C] point-major
 };
@@ -61,9 +62,10 @@ __device__ __forceinline__ int seg_setup(const SegParams& G, int64_t q, bool qva
   dst[0] = w[0];
   dst[1] = w[1];
   dst[2] = w[2];
-  dst[3] = make_float4(__int_as_float(base[0] * C4), __int_as_float(base[1] * C4), __int_as_float(base[2] * C4),
-                       __int_as_float(anymask));
-  sp[param_base(lane) + 16] = __int_as_float(b);
+  // tap offsets in float4 units INCLUDING the sample's plane offset (< 2^31, host-checked): the gather loop below then
+  // has no per-query 64-bit arithmetic (it was 4 M IMAD + 1.4 M LDC of 18 M warp instructions on configs[2])
+  dst[3] = make_float4(__int_as_float(b * G.bs4[0] + base[0] * C4), __int_as_float(b * G.bs4[1] + base[1] * C4),
+                       __int_as_float(b * G.bs4[2] + base[2] * C4), __int_as_float(anymask));
   return anymask;
 }
 
@@ -80,6 +82,12 @@ sample3_seg_kernel(const SegParams G) {
   const int WC4_0 = P.W[0] * C4, WC4_1 = P.W[1] * C4, WC4_2 = P.W[2] * C4;
   const unsigned long long pol_planes = policy_evict_last(), pol_out = policy_evict_first();
 
+  const float4* const pl0 = reinterpret_cast<const float4*>(P.plane[0]) + l8;
+  const float4* const pl1 = reinterpret_cast<const float4*>(P.plane[1]) + l8;
+  const float4* const pl2 = reinterpret_cast<const float4*>(P.plane[2]) + l8;
+  float4* const gp0 = reinterpret_cast<float4*>(G.gplane[0]) + l8;
+  float4* const gp1 = reinterpret_cast<float4*>(G.gplane[1]) + l8;
+  float4* const gp2 = reinterpret_cast<float4*>(G.gplane[2]) + l8;
   for (int64_t tile = (int64_t)blockIdx.x * kSegWarps + warp; tile < P.tiles; tile += (int64_t)gridDim.x * kSegWarps) {
     const int64_t q = tile * 32 + lane;
     const int anymask = seg_setup<ARITH>(G, q, q < P.Q, sp, lane, C4);
@@ -97,15 +105,11 @@ sample3_seg_kernel(const SegParams G) {
         const float* rec = sp + param_base(qi);
         const float4* prm = reinterpret_cast<const float4*>(rec);
         const float4 w0 = prm[0], w1 = prm[1], w2 = prm[2], bm = prm[3];
-        const int b = __float_as_int(rec[16]);
         const int m = cvalid ? __float_as_int(bm.w) : 0;
         if (!BACKWARD) {
-          const float4* pl0 = reinterpret_cast<const float4*>(P.plane[0] + (int64_t)b * P.bstride[0]) + l8 + ch * 8;
-          const float4* pl1 = reinterpret_cast<const float4*>(P.plane[1] + (int64_t)b * P.bstride[1]) + l8 + ch * 8;
-          const float4* pl2 = reinterpret_cast<const float4*>(P.plane[2] + (int64_t)b * P.bstride[2]) + l8 + ch * 8;
-          const float4 a0 = plane_taps<true>(pl0, __float_as_int(bm.x), C4, WC4_0, w0, m & 15, pol_planes);
-          const float4 a1 = plane_taps<true>(pl1, __float_as_int(bm.y), C4, WC4_1, w1, (m >> 4) & 15, pol_planes);
-          const float4 a2 = plane_taps<true>(pl2, __float_as_int(bm.z), C4, WC4_2, w2, (m >> 8) & 15, pol_planes);
+          const float4 a0 = plane_taps<true>(pl0 + ch * 8, __float_as_int(bm.x), C4, WC4_0, w0, m & 15, pol_planes);
+          const float4 a1 = plane_taps<true>(pl1 + ch * 8, __float_as_int(bm.y), C4, WC4_1, w1, (m >> 4) & 15, pol_planes);
+          const float4 a2 = plane_taps<true>(pl2 + ch * 8, __float_as_int(bm.z), C4, WC4_2, w2, (m >> 8) & 15, pol_planes);
           if (cvalid) {
             float4 r;  // (xy + yz) + xz  (triplane.py:512)
             r.x = __fadd_rn(__fadd_rn(a0.x, a1.x), a2.x);
@@ -117,12 +121,9 @@ sample3_seg_kernel(const SegParams G) {
         } else {
           if (m == 0) continue;
           const float4 g = __ldg(reinterpret_cast<const float4*>(G.gout + qq * C) + ch * 8 + l8);
-          float4* gp0 = reinterpret_cast<float4*>(G.gplane[0] + (int64_t)b * P.bstride[0]) + l8 + ch * 8;
-          float4* gp1 = reinterpret_cast<float4*>(G.gplane[1] + (int64_t)b * P.bstride[1]) + l8 + ch * 8;
-          float4* gp2 = reinterpret_cast<float4*>(G.gplane[2] + (int64_t)b * P.bstride[2]) + l8 + ch * 8;
-          scatter_taps(gp0, __float_as_int(bm.x), C4, WC4_0, w0, m & 15, g);
-          scatter_taps(gp1, __float_as_int(bm.y), C4, WC4_1, w1, (m >> 4) & 15, g);
-          scatter_taps(gp2, __float_as_int(bm.z), C4, WC4_2, w2, (m >> 8) & 15, g);
+          scatter_taps(gp0 + ch * 8, __float_as_int(bm.x), C4, WC4_0, w0, m & 15, g);
+          scatter_taps(gp1 + ch * 8, __float_as_int(bm.y), C4, WC4_1, w1, (m >> 4) & 15, g);
+          scatter_taps(gp2 + ch * 8, __float_as_int(bm.z), C4, WC4_2, w2, (m >> 8) & 15, g);
         }
       }
     }
@@ -150,6 +151,9 @@ static int seg_fill(SegParams& G, const char* who, const tp_plane planes[3], int
     P.plane[k] = planes[k].data;
     G.gplane[k] = const_cast<float*>(planes[k].data);
     P.bstride[k] = planes[k].batch_stride;
+    if (((int64_t)batch + 1) * (planes[k].batch_stride >> 2) >= ((int64_t)1 << 31))
+      return fail(TP_E_SHAPE, "%s: plane %d: batch * batch_stride must stay below 2^33 floats", who, k);
+    G.bs4[k] = (int)(planes[k].batch_stride >> 2);
     P.H[k] = planes[k].H;
     P.W[k] = planes[k].W;
     P.lo[k] = sg->lo[k];

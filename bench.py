@@ -1167,20 +1167,30 @@ def workload_point_sharded(ctx):
         my_pts, my_f = one_dev[lo_i:hi_i].contiguous(), one_f[lo_i:hi_i].contiguous()
         my_off = synth.batch_offsets([hi_i - lo_i]).to(dev)
         sharded = {}
-        for strategy in tpd.STRATEGIES:
-            def sstep(strategy=strategy):
+        # owner slabs with equal point counts instead of equal widths: computed ONCE, outside the timed steps (one small
+        # all-reduce + host sync; a sensor's density profile does not change from frame to frame)
+        bal = tpd.balanced_slab_bounds(my_pts, G["pc_range"], G["voxel_size"], G["grid_size"],
+                                       min_width=ops.pool_kernels(G["grid_size"], G["split"])[:2])
+        for name in list(tpd.STRATEGIES) + ["owner_balanced"]:
+            strategy = "owner" if name == "owner_balanced" else name
+            sb = bal if name == "owner_balanced" else None
+
+            def sstep(strategy=strategy, sb=sb):
                 return tpd.encode_point_sharded(my_f, my_pts, my_off, G["pc_range"], G["voxel_size"], G["grid_size"], G["split"],
-                                                reduce="max", strategy=strategy, capacity=one_pts.shape[0])
+                                                reduce="max", strategy=strategy, capacity=one_pts.shape[0], slab_bounds=sb)
             got = sstep()
-            ok = tpd.planes_equal(got, ref, strategy, rank, world)   # parity BEFORE timing, on every rank
+            ok = tpd.planes_equal(got, ref, strategy, rank, world, slab_bounds=sb)   # parity BEFORE timing, on every rank
             flag = torch.tensor([1 if ok else 0], device=dev)
             ctx.dist.all_reduce(flag, op=ctx.dist.ReduceOp.MIN)
-            assert int(flag) == 1, f"point-sharded encode ({strategy}) differs from the single-GPU planes"
+            assert int(flag) == 1, f"point-sharded encode ({name}) differs from the single-GPU planes"
             del got
             s_ms = time_steps(sstep, max(5, min(args.steps, 20)), 3, ctx)
             (s_ms,) = ctx.max_over_ranks(s_ms)
-            sharded[strategy] = {"ms_per_step": s_ms, "equal_to_single_gpu": True, "points_per_s": one_pts.shape[0] / (s_ms * 1e-3),
-                                 "what": tpd.STRATEGIES[strategy]}
+            sharded[name] = {"ms_per_step": s_ms, "equal_to_single_gpu": True, "points_per_s": one_pts.shape[0] / (s_ms * 1e-3),
+                             "what": tpd.STRATEGIES[strategy]}
+            if sb is not None:
+                sharded[name]["slab_bounds_x"], sharded[name]["slab_bounds_y"] = sb
+                sharded[name]["what"] += "; slab boundaries chosen once for equal point counts (dist.balanced_slab_bounds)"
         del ref
     (ms_one,) = ctx.max_over_ranks(ms_one)
     # e2e: one sample through the host-buffer entry point

@@ -54,19 +54,23 @@ route_points_kernel(const RouteParams P) {
       keep = keep & (ix >= 0) & (ix < P.g.grid[0]) & (iy >= 0) & (iy < P.g.grid[1]) & (iz >= 0) & (iz < P.g.grid[2]);
     }
     const int dx = keep ? slab_owner(P.xb, P.world, ix) : -1, dy = keep ? slab_owner(P.yb, P.world, iy) : -1;
-    int sx = -1, sy = -1;
+    // slots: lane r claims the x-slab rows of destination r, lane 8 + r its y-slab rows — all (at most 16) remote atomics
+    // of the warp are in flight at once (issued one destination after the other they were up to 16 dependent NVLink
+    // round trips per 32 points)
+    int pre_x = 0, pre_y = 0, mine = 0;
+    const unsigned lt = (1u << lane) - 1u;
     for (int r = 0; r < P.world; ++r) {
       const unsigned mx = __ballot_sync(0xffffffffu, dx == r), my = __ballot_sync(0xffffffffu, dy == r);
-      int bx = 0, by = 0;
-      if (lane == 0) {
-        if (mx) bx = atomicAdd_system(P.cnt[r], __popc(mx));
-        if (my) by = atomicAdd_system(P.cnt[r] + 1, __popc(my));
-      }
-      bx = __shfl_sync(0xffffffffu, bx, 0);
-      by = __shfl_sync(0xffffffffu, by, 0);
-      if (dx == r) sx = bx + __popc(mx & ((1u << lane) - 1u));
-      if (dy == r) sy = by + __popc(my & ((1u << lane) - 1u));
+      if (dx == r) pre_x = __popc(mx & lt);
+      if (dy == r) pre_y = __popc(my & lt);
+      if (lane == r) mine = __popc(mx);
+      if (lane == kRouteMaxWorld + r) mine = __popc(my);
     }
+    int base = 0;
+    if (mine) base = atomicAdd_system(P.cnt[lane & (kRouteMaxWorld - 1)] + (lane >= kRouteMaxWorld ? 1 : 0), mine);
+    const int bx = __shfl_sync(0xffffffffu, base, dx < 0 ? 0 : dx);
+    const int by = __shfl_sync(0xffffffffu, base, kRouteMaxWorld + (dy < 0 ? 0 : dy));
+    int sx = dx >= 0 ? bx + pre_x : -1, sy = dy >= 0 ? by + pre_y : -1;
     if (sx >= P.cap) sx = -1;  // capacity is the global point count: cannot happen
     if (sy >= P.cap) sy = -1;
     if (sx >= 0) {
@@ -77,18 +81,35 @@ route_points_kernel(const RouteParams P) {
       int32_t* d = P.idx_y[dy] + (int64_t)sy * 3;
       d[0] = ix; d[1] = iy - P.yb[dy]; d[2] = iz;
     }
-    // feature rows: the warp walks its kept points; 32 lanes x 16 B per row and destination
-    for (unsigned m = __ballot_sync(0xffffffffu, keep); m; m &= m - 1) {
-      const int src = __ffs(m) - 1;
-      const int pdx = __shfl_sync(0xffffffffu, dx, src), pdy = __shfl_sync(0xffffffffu, dy, src);
-      const int psx = __shfl_sync(0xffffffffu, sx, src), psy = __shfl_sync(0xffffffffu, sy, src);
-      const float4* frow = reinterpret_cast<const float4*>(P.feats + (i0 + src) * P.feat_stride);
-      float4* ox = psx >= 0 ? reinterpret_cast<float4*>(P.feat_x[pdx] + (int64_t)psx * C) : nullptr;
-      float4* oy = psy >= 0 ? reinterpret_cast<float4*>(P.feat_y[pdy] + (int64_t)psy * C) : nullptr;
+    // feature rows: the warp walks its kept points four at a time (four row loads in flight); 32 lanes x 16 B per row
+    // and destination
+    unsigned m = __ballot_sync(0xffffffffu, keep);
+    while (m) {
+      int src[4];
+      float4* ox[4];
+      float4* oy[4];
+      const float4* frow[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        src[j] = m ? __ffs(m) - 1 : -1;
+        m &= m - 1;  // 0 stays 0
+        const int sl = src[j] < 0 ? 0 : src[j];
+        const int pdx = __shfl_sync(0xffffffffu, dx, sl), pdy = __shfl_sync(0xffffffffu, dy, sl);
+        const int psx = __shfl_sync(0xffffffffu, sx, sl), psy = __shfl_sync(0xffffffffu, sy, sl);
+        frow[j] = reinterpret_cast<const float4*>(P.feats + (i0 + sl) * P.feat_stride);
+        ox[j] = (src[j] >= 0 && psx >= 0) ? reinterpret_cast<float4*>(P.feat_x[pdx] + (int64_t)psx * C) : nullptr;
+        oy[j] = (src[j] >= 0 && psy >= 0) ? reinterpret_cast<float4*>(P.feat_y[pdy] + (int64_t)psy * C) : nullptr;
+      }
       for (int v = lane; v < P.C4; v += 32) {
-        const float4 f = __ldg(frow + v);
-        if (ox) ox[v] = f;
-        if (oy) oy[v] = f;
+        float4 f[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (src[j] >= 0) f[j] = __ldg(frow[j] + v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (ox[j]) ox[j][v] = f[j];
+          if (oy[j]) oy[j][v] = f[j];
+        }
       }
     }
   }

@@ -43,13 +43,23 @@ def main():
         # owner exchange over NVLink peer memory: one sample per call; every rank ends up with its slabs of the planes
         ref1 = ops.encode(feats[0].to(dev), synth.batch_offsets([30000]).to(dev), G["pc_range"], G["voxel_size"], G["grid_size"],
                           G["split"], points=raw[0].to(dev), reduce=reduce)
-        for rep in range(2):  # twice: the buffers are reused and must be reset correctly
+        bal = tpd.balanced_slab_bounds(my_raw[0].to(dev), G["pc_range"], G["voxel_size"], G["grid_size"],
+                                       min_width=ops.pool_kernels(G["grid_size"], G["split"])[:2])
+        for rep in range(3):  # twice with equal-width slabs (the buffers are reused and must be reset correctly), once balanced
+            sb = bal if rep == 2 else None
             got = tpd.encode_point_sharded(my_feats[0].to(dev), my_raw[0].to(dev), synth.batch_offsets([my_raw[0].shape[0]]).to(dev),
-                                           G["pc_range"], G["voxel_size"], G["grid_size"], G["split"], reduce=reduce, strategy="owner")
-            good = tpd.planes_equal(got, ref1, "owner", rank, world, rtol=0.0 if reduce == "max" else 1e-5)
+                                           G["pc_range"], G["voxel_size"], G["grid_size"], G["split"], reduce=reduce, strategy="owner",
+                                           slab_bounds=sb)
+            good = tpd.planes_equal(got, ref1, "owner", rank, world, rtol=0.0 if reduce == "max" else 1e-5, slab_bounds=sb)
             ok &= bool(good)
             if not good:
-                print(f"[rank {rank}] {reduce}/owner (pass {rep}): mismatch", flush=True)
+                (x0, x1), (y0, y1) = (sb[0][rank:rank + 2], sb[1][rank:rank + 2]) if sb else (tpd.shard_bounds(128, rank, world),) * 2
+                refs = (ref1[0][:, x0:x1], ref1[1][:, y0:y1], ref1[2][:, x0:x1])
+                info = []
+                for a, b in zip(got, refs):
+                    d = (a != b).nonzero()
+                    info.append((tuple(a.shape), int(d.shape[0]), d[:2].tolist(), d[-1:].tolist()))
+                print(f"[rank {rank}] {reduce}/owner (pass {rep}, bounds {sb}): mismatch {info}", flush=True)
     # C-ABI collective hooks (tp_comm_*, tp_allreduce_planes): same result as torch.distributed
     import ctypes as C_
     from efficient_multimodal_perception_b200 import _lib as L

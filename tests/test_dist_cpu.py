@@ -90,6 +90,22 @@ def _worker(rank, world, port, ret):
         g_inds = [i_all[off_all[b]:off_all[b + 1]].int() for b in range(len(inds))]
         g = O.encode_pooled(f_all, O.cat_indices(g_inds), GRID, SPLIT, len(inds))
         ok &= all(torch.equal(a, b) for a, b in zip(g[:3], full[:3]))
+        # owner-strategy slab boundaries by point count: the same on every rank, increasing, covering the grid, and the
+        # x-slabs of a centre-heavy cloud hold about the same number of points
+        gen = torch.Generator().manual_seed(5)
+        cloud = torch.randn(4000, 3, generator=gen) * torch.tensor([6.0, 9.0, 1.0])
+        lo_r, hi_r = tpd.shard_bounds(cloud.shape[0], rank, world)
+        rng, vs, grid = [-25.0, -25.0, -5.0, 25.0, 25.0, 3.0], (0.4, 0.4, 0.1), [128, 128, 80]
+        xb, yb = tpd.balanced_slab_bounds(cloud[lo_r:hi_r], rng, vs, grid)
+        both = [None, None]
+        dist.all_gather_object(both, (xb, yb))
+        ok &= both[0] == both[1]
+        for b in (xb, yb):
+            ok &= len(b) == world + 1 and b[0] == 0 and b[-1] == 128 and all(b[i] < b[i + 1] for i in range(world))
+        ix = ((cloud[:, 0] + 25.0) / 0.4).long()
+        inside = (cloud[:, 0].abs() < 25) & (cloud[:, 1].abs() < 25) & (cloud[:, 2] > -5) & (cloud[:, 2] < 3)
+        left = int(((ix < xb[1]) & inside).sum())
+        ok &= abs(left - int(inside.sum()) / 2) < 0.1 * int(inside.sum())
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()

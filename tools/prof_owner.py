@@ -40,10 +40,12 @@ pool = ops.pool_kernels(G["grid_size"], G["split"])
 geom = L.make_geom(G["pc_range"], G["voxel_size"], G["grid_size"], pool)
 xba, yba = (C_.c_int32 * (world + 1))(*xb), (C_.c_int32 * (world + 1))(*yb)
 stream = torch.cuda.current_stream().cuda_stream
-ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
-acc = [0.0] * 6
-for it in range(10):
-    torch.cuda.synchronize(); dist.barrier()
+# stage times from events recorded in a free-running loop (the host runs ahead: no launch gaps inside the stages)
+NIT = 20
+evs = [[torch.cuda.Event(enable_timing=True) for _ in range(7)] for _ in range(NIT)]
+torch.cuda.synchronize(); dist.barrier()
+for it in range(NIT):
+    ev = evs[it]
     ev[0].record()
     ex.head.fill_(255); ex.head[:256].zero_()
     ev[1].record()
@@ -59,10 +61,9 @@ for it in range(10):
     ev[5].record()
     b = ops.encode(ex.feat_y, ex.offsets, [0] * 6, (1, 1, 1), (X, ys, Z), G["split"], grid_ind=ex.idx_y, planes=(False, True, False), pool=pool)
     ev[6].record()
-    torch.cuda.synchronize()
-    for k in range(6):
-        acc[k] += ev[k].elapsed_time(ev[k + 1]) / 10
+torch.cuda.synchronize()
+acc = [sum(evs[it][k].elapsed_time(evs[it][k + 1]) for it in range(5, NIT)) / (NIT - 5) for k in range(6)]
 cnt = ex.buf[:8].view(torch.int32).tolist()
 print(f"rank {rank}: host-issue {host*1e3:.3f} ms, wall {wall*1e3:.3f} ms per step; stages ms: reset {acc[0]:.3f} barrier {acc[1]:.3f} route {acc[2]:.3f} "
-      f"barrier {acc[3]:.3f} encode_x {acc[4]:.3f} encode_y {acc[5]:.3f}; received rows x/y {cnt}", flush=True)
+      f"barrier {acc[3]:.3f} encode_x {acc[4]:.3f} encode_y {acc[5]:.3f}; received rows x/y {cnt[:2]}", flush=True)
 dist.destroy_process_group()

@@ -254,6 +254,27 @@ def e2e_time(call, steps, ctx):
     return ctx.max_over_ranks(dt / steps * 1e3)[0]
 
 
+def copy_ceiling(h2d_bytes: int, d2h_bytes: int, steps: int, ctx):
+    """What the host link alone allows for an e2e step: the same number of bytes up and down between pinned host
+    buffers and the device, all ranks at once, no kernel in between, synchronised every step like the e2e call.
+    Returns {"ms_per_step", "gbs_per_rank", "gbs_all_ranks"}: the e2e number cannot beat bytes / this time."""
+    up_h = torch.empty(max(h2d_bytes, 4) // 4, dtype=torch.float32).pin_memory()
+    down_h = torch.empty(max(d2h_bytes, 4) // 4, dtype=torch.float32).pin_memory()
+    up_d = torch.empty_like(up_h, device=ctx.dev)
+    down_d = torch.empty_like(down_h, device=ctx.dev)
+
+    def call():
+        up_d.copy_(up_h, non_blocking=True)
+        down_h.copy_(down_d, non_blocking=True)
+        torch.cuda.synchronize()
+
+    ms = e2e_time(call, steps, ctx)
+    gbs = (h2d_bytes + d2h_bytes) / (ms * 1e-3) / 1e9
+    return {"ms_per_step": ms, "gbs_per_rank": gbs, "gbs_all_ranks": gbs * ctx.world,
+            "what": "pinned-host <-> device copies of the same byte counts on every rank at once, no kernel: the host-link "
+                    "ceiling of the e2e step on this box"}
+
+
 def bind_to_gpu(local: int, world: int):
     """Pin this rank's threads (and therefore its pinned host buffers, first-touch) near its GPU: the e2e legs move
     ~100 MB per step over PCIe per rank. Uses the GPU's NUMA node when sysfs reports one; virtualised hosts report
@@ -466,7 +487,8 @@ def bench_decode_e2e(args, Q_host, ctx):
 
     steps = max(5, min(args.steps, 100))
     ms = e2e_time(call, steps, ctx)
-    return dict(steps=steps, h2d=tri.numel() * 4 + q.numel() * 4, d2h=out.numel() * 4, ms=ms, out=out)
+    h2d, d2h = tri.numel() * 4 + q.numel() * 4, out.numel() * 4
+    return dict(steps=steps, h2d=h2d, d2h=d2h, ms=ms, out=out, ceiling=copy_ceiling(h2d, d2h, steps, ctx))
 
 
 def bench_decode_head_e2e(args, ctx):
@@ -635,6 +657,7 @@ def workload_decode(ctx):
         "e2e": {"value": world * Q / (e2e["ms"] * 1e-3), "unit": "queries/s",
                 "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e["ms"],
                 "steps": e2e["steps"], "cpu_binding": ctx.numa,
+                "host_link_ceiling": dict(e2e["ceiling"], value=world * Q / (e2e["ceiling"]["ms_per_step"] * 1e-3)),
                 "api": "tp_sample3_grid_host_f32 / tp_sample3_host_f32 (C ABI, pinned host buffers; H2D planes+queries, "
                        "D2H full result, synchronised every step)"},
         "gpu_launches": dec["launches"],

@@ -8,7 +8,10 @@ rows = [r for r in csv.reader(l for l in open(sys.argv[1]) if l.startswith('"'))
 head = rows[0]
 ki, vi, ui = head.index("Kernel Name"), head.index("Metric Value"), head.index("Metric Unit")
 acc = defaultdict(lambda: [0, 0.0])
+mi = head.index("Metric Name") if "Metric Name" in head else None
 for r in rows[1:]:
+    if mi is not None and r[mi] != "gpu__time_duration.sum":
+        continue  # lists captured with more than one metric
     v = float(r[vi].replace(",", ""))
     v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(r[ui], 1.0)
     acc[r[ki]][0] += 1

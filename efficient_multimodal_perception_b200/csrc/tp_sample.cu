@@ -84,16 +84,41 @@ nchw_to_nhwc_kernel(const float* __restrict__ src, int64_t src_bstride, float* _
   }
 }
 
-// All three planes in one launch (slabs: tp_sample_dev.cuh), one wave of CTAs for the configs' plane sizes (384 slabs at
-// B = 1, C = 32, 128x128), grid-stride beyond that. The first instruction releases the dependent decode launch (see
-// tp_common.cuh); the grid never exceeds one wave, so every CTA is resident when the dependent grid starts taking SMs.
+struct Planes3 {
+  const float* src[3];
+  float* dst[3];
+  int64_t src_bstride[3];
+  int HW[3];
+  int tiles_x[3];  // ceil(HW/32) per plane; blockIdx.x runs over the three planes back to back
+};
+
+// all three planes in one launch. grid = (sum_p ceil(HW_p/32), ceil(C/32), B)
+// The first instruction releases a dependent decode launch (tp_common.cuh). A round-2 rewrite on slabs of 32 channels x
+// 128 pixels (16 loads in flight per thread, 16-byte stores, one wave of 384 CTAs) was SLOWER on the same box — 5.5 vs
+// 4.5 us for one sample's planes, 24.4 vs 22.4 us at bs = 8: with every CTA resident at once the launch is a read
+// phase followed by a write phase, while the 1 536 small CTAs of this kernel (1.3 waves) overlap the two.
 __global__ void __launch_bounds__(256)
-nchw_to_nhwc3_kernel(const Planes3 P) {
-  __shared__ float tile[128 * 33];
+nchw_to_nhwc3_kernel(const Planes3 P, int C) {
+  __shared__ float tile[32][33];
   pdl_launch_dependents();
-  for (int s = blockIdx.x; s < P.nslabs; s += gridDim.x) {
-    convert_slab(P, s, tile);
-    __syncthreads();
+  int bx = blockIdx.x, k = 0;
+  if (bx >= P.tiles_x[0]) { bx -= P.tiles_x[0]; k = 1; if (bx >= P.tiles_x[1]) { bx -= P.tiles_x[1]; k = 2; } }
+  const int HW = P.HW[k];
+  const int b = blockIdx.z;
+  const int p0 = bx * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* s = P.src[k] + (int64_t)b * P.src_bstride[k];
+  float* d = P.dst[k] + (int64_t)b * C * HW;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    int c = c0 + ty + j, p = p0 + tx;
+    if (c < C && p < HW) tile[ty + j][tx] = __ldg(s + (int64_t)c * HW + p);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    int p = p0 + ty + j, c = c0 + tx;
+    if (c < C && p < HW) d[(int64_t)p * C + c] = tile[tx][ty + j];
   }
 }
 
@@ -101,39 +126,24 @@ nchw_to_nhwc3_kernel(const Planes3 P) {
 
 using namespace tp;
 
-int tp::planes3_fill(Planes3& P, const char* who, const tp_plane planes_nchw[3], float* const dst[3], int32_t batch, int32_t C) {
-  if (!planes_nchw || !dst) return fail(TP_E_NULL, "%s: null argument", who);
-  if (batch <= 0 || C <= 0) return fail(TP_E_SHAPE, "%s: bad shape B=%d C=%d", who, batch, C);
-  P.C = C;
-  P.cgroups = (C + 31) / 32;
-  int64_t total = 0;
-  bool vec = (C & 3) == 0;
+extern "C" int tp_planes3_nchw_to_nhwc_f32(const tp_plane planes_nchw[3], float* const dst[3], int32_t batch,
+                                           int32_t C, void* stream) {
+  if (!planes_nchw || !dst) return fail(TP_E_NULL, "tp_planes3_nchw_to_nhwc_f32: null argument");
+  if (batch <= 0 || C <= 0) return fail(TP_E_SHAPE, "tp_planes3_nchw_to_nhwc_f32: bad shape B=%d C=%d", batch, C);
+  Planes3 P;
+  int tx = 0;
   for (int k = 0; k < 3; ++k) {
-    if (!planes_nchw[k].data || !dst[k]) return fail(TP_E_NULL, "%s: plane %d is null", who, k);
-    if (planes_nchw[k].H <= 0 || planes_nchw[k].W <= 0) return fail(TP_E_SHAPE, "%s: plane %d shape", who, k);
+    if (!planes_nchw[k].data || !dst[k]) return fail(TP_E_NULL, "tp_planes3_nchw_to_nhwc_f32: plane %d is null", k);
+    if (planes_nchw[k].H <= 0 || planes_nchw[k].W <= 0) return fail(TP_E_SHAPE, "tp_planes3_nchw_to_nhwc_f32: plane %d shape", k);
     P.src[k] = planes_nchw[k].data;
     P.dst[k] = dst[k];
     P.src_bstride[k] = planes_nchw[k].batch_stride;
-    const int64_t hw = (int64_t)planes_nchw[k].H * planes_nchw[k].W;
-    if (hw >= ((int64_t)1 << 31)) return fail(TP_E_SHAPE, "%s: plane %d too large", who, k);
-    P.HW[k] = (int)hw;
-    P.pgroups[k] = (int)((hw + 127) / 128);
-    total += (int64_t)batch * P.cgroups * P.pgroups[k];
-    if (total >= ((int64_t)1 << 31)) return fail(TP_E_SHAPE, "%s: too many slabs", who);
-    P.slab_end[k] = (int)total;
-    vec = vec && ((uintptr_t)dst[k] & 15) == 0;
+    P.HW[k] = planes_nchw[k].H * planes_nchw[k].W;
+    P.tiles_x[k] = (P.HW[k] + 31) / 32;
+    tx += P.tiles_x[k];
   }
-  P.nslabs = (int)total;
-  P.vec = vec ? 1 : 0;
-  return 0;
-}
-
-extern "C" int tp_planes3_nchw_to_nhwc_f32(const tp_plane planes_nchw[3], float* const dst[3], int32_t batch,
-                                           int32_t C, void* stream) {
-  Planes3 P;
-  if (int rc = planes3_fill(P, "tp_planes3_nchw_to_nhwc_f32", planes_nchw, dst, batch, C)) return rc;
-  const int grid = P.nslabs < kSMs * 8 ? P.nslabs : kSMs * 8;
-  nchw_to_nhwc3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+  dim3 grid(tx, (C + 31) / 32, batch);
+  nchw_to_nhwc3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P, C);
   TP_LAUNCH_CHECK("nchw_to_nhwc3_kernel");
   return 0;
 }

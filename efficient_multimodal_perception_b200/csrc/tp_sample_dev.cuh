@@ -20,90 +20,10 @@ struct SampleParams {
   int C;
 };
 
-// ---- NCHW -> channels-last conversion of the three planes ----------------------------------------
-// A slab = 32 channels x 128 consecutive pixels of one (plane, sample): 16 scalar loads in flight per thread (128-byte
-// rows per warp), transposed through a padded shared tile [128][33] and written as 16-byte pieces of the pixels'
-// channel rows (tp_sample.cu: nchw_to_nhwc3_kernel).
-struct Planes3 {
-  const float* src[3];
-  float* dst[3];
-  int64_t src_bstride[3];
-  int HW[3];
-  int pgroups[3];   // ceil(HW / 128) per plane
-  int slab_end[3];  // cumulative slab count: plane k owns slabs [slab_end[k-1], slab_end[k])
-  int cgroups;      // ceil(C / 32)
-  int C, nslabs, vec;
-};
-
-struct SlabPos {
-  const float* src;  // sample's NCHW plane
-  float* dst;        // sample's channels-last plane
-  int HW, p0, c0;
-};
-__device__ __forceinline__ SlabPos slab_pos(const Planes3& P, int s) {
-  const int k = s >= P.slab_end[1] ? 2 : (s >= P.slab_end[0] ? 1 : 0);
-  int r = s - (k ? P.slab_end[k - 1] : 0);
-  const int pg = r % P.pgroups[k]; r /= P.pgroups[k];
-  const int cg = r % P.cgroups;
-  const int b = r / P.cgroups;
-  SlabPos sp;
-  sp.HW = P.HW[k];
-  sp.p0 = pg * 128;
-  sp.c0 = cg * 32;
-  sp.src = P.src[k] + (int64_t)b * P.src_bstride[k];
-  sp.dst = P.dst[k] + (int64_t)b * P.C * sp.HW;
-  return sp;
-}
-// tile [128 px][33] <- the slab through registers (16 loads in flight per thread); ends with a barrier
-__device__ __forceinline__ void slab_load(const Planes3& P, int s, float* tile) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const SlabPos sp = slab_pos(P, s);
-  float v[4][4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int c = sp.c0 + warp + 8 * j;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int p = sp.p0 + lane + 32 * i;
-      v[j][i] = (c < P.C && p < sp.HW) ? __ldg(sp.src + (int64_t)c * sp.HW + p) : 0.f;
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) tile[(lane + 32 * i) * 33 + warp + 8 * j] = v[j][i];
-  __syncthreads();
-}
-// tile -> 16-byte pieces of the pixels' channel rows (tile complete and visible to the CTA); no trailing barrier
-__device__ __forceinline__ void slab_store(const Planes3& P, int s, const float* tile) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, C = P.C;
-  const SlabPos sp = slab_pos(P, s);
-  if (P.vec) {  // C % 4 == 0, 16-byte aligned destination
-    const int l8 = threadIdx.x & 7, c = sp.c0 + 4 * l8;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int pl = (threadIdx.x >> 3) + 32 * i, p = sp.p0 + pl;
-      const float* t = tile + pl * 33 + 4 * l8;
-      if (c < C && p < sp.HW) *reinterpret_cast<float4*>(sp.dst + (int64_t)p * C + c) = make_float4(t[0], t[1], t[2], t[3]);
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int pl = warp + 8 * i, p = sp.p0 + pl, c = sp.c0 + lane;
-      if (c < C && p < sp.HW) sp.dst[(int64_t)p * C + c] = tile[pl * 33 + lane];
-    }
-  }
-}
-__device__ __forceinline__ void convert_slab(const Planes3& P, int s, float* tile) {
-  slab_load(P, s, tile);
-  slab_store(P, s, tile);
-}
-
 // host side, tp_sample.cu: the per-query launch (pdl: it directly follows our conversion kernel, see tp_common.cuh),
 // the workspace layout of the channels-last copies and the conversion launch
 int sample3_flat(const tp_plane planes[3], int32_t C, const float* queries, int64_t Q, int32_t batch,
                  const tp_sample_geom* sg, int32_t arith, float* out, void* stream, bool pdl);
-int planes3_fill(Planes3& P, const char* who, const tp_plane planes_nchw[3], float* const dst[3], int32_t batch, int32_t C);
 int planes3_workspace(const char* who, const tp_plane planes_nchw[3], int32_t C, int32_t batch, float* ws,
                       int64_t ws_floats, tp_plane nhwc[3], float* dsts[3]);
 int planes3_to_workspace(const char* who, const tp_plane planes_nchw[3], int32_t C, int32_t batch, float* ws,

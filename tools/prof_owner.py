@@ -19,8 +19,14 @@ my_p, my_f = pts[lo:hi].to(dev), feats[lo:hi].contiguous().to(dev)
 off = synth.batch_offsets([hi - lo]).to(dev)
 cap = pts.shape[0]
 
+BAL = len(sys.argv) > 1 and sys.argv[1] == "balanced"
+bounds = tpd.balanced_slab_bounds(my_p, G["pc_range"], G["voxel_size"], G["grid_size"],
+                                  min_width=ops.pool_kernels(G["grid_size"], G["split"])[:2]) if BAL else None
+
+
 def step():
-    return tpd.encode_point_sharded(my_f, my_p, off, G["pc_range"], G["voxel_size"], G["grid_size"], G["split"], strategy="owner", capacity=cap)
+    return tpd.encode_point_sharded(my_f, my_p, off, G["pc_range"], G["voxel_size"], G["grid_size"], G["split"], strategy="owner",
+                                    capacity=cap, slab_bounds=bounds)
 
 for _ in range(5):
     step()
@@ -34,8 +40,8 @@ wall = (time.perf_counter() - t0) / 20
 # stages, by hand
 ex = tpd._OwnerExchange.get(dev, None, cap, C)
 X, Y, Z = G["grid_size"]
-xb = [tpd.shard_bounds(X, r, world)[0] for r in range(world)] + [X]
-yb = [tpd.shard_bounds(Y, r, world)[0] for r in range(world)] + [Y]
+xb = bounds[0] if BAL else [tpd.shard_bounds(X, r, world)[0] for r in range(world)] + [X]
+yb = bounds[1] if BAL else [tpd.shard_bounds(Y, r, world)[0] for r in range(world)] + [Y]
 pool = ops.pool_kernels(G["grid_size"], G["split"])
 geom = L.make_geom(G["pc_range"], G["voxel_size"], G["grid_size"], pool)
 xba, yba = (C_.c_int32 * (world + 1))(*xb), (C_.c_int32 * (world + 1))(*yb)
@@ -47,7 +53,7 @@ torch.cuda.synchronize(); dist.barrier()
 for it in range(NIT):
     ev = evs[it]
     ev[0].record()
-    ex.head.fill_(255); ex.head[:256].zero_()
+    ex.head32.fill_(-1); ex.head32[:64].zero_()
     ev[1].record()
     ex.hdl.barrier(channel=0)
     ev[2].record()

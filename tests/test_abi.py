@@ -130,3 +130,38 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(L, "LIB_PATH", "/nonexistent/libtriplane.so")
     with pytest.raises(TriplaneError, match="no CPU/PyTorch fallback"):
         L.lib()
+
+
+def test_reference_layout_entry_points_validate_workspace_without_a_device():
+    """The *_nchw_* forms (conversion + decode in one call) reject a missing / short workspace and bad shapes before
+    any launch: every decode entry point has one."""
+    lib = L.lib()
+    sg = L.make_sample_geom([0, 0, 0], [1, 1, 1], [1, 1, 1])
+    planes = (L.tp_plane * 3)()
+    for k in range(3):
+        planes[k].data, planes[k].batch_stride, planes[k].H, planes[k].W = 256, 32 * 8 * 8, 8, 8
+    dims = (C.c_int32 * 3)(4, 4, 16)
+    org, stp = (C.c_float * 3)(0, 0, 0), (C.c_float * 3)(1, 1, 1)
+    need = 3 * 32 * 8 * 8
+    # no workspace
+    assert lib.tp_sample3_nchw_f32(C.byref(planes), 32, 256, 10, 1, C.byref(sg), 0, 256, None, need, None) == -1
+    assert lib.tp_sample3_grid_nchw_f32(C.byref(planes), 32, 256, C.byref(dims), 1, C.byref(sg), 0, 256, None, need, None) == -1
+    # short workspace
+    for call in (
+        lambda ws: lib.tp_sample3_nchw_f32(C.byref(planes), 32, 256, 10, 1, C.byref(sg), 0, 256, 256, ws, None),
+        lambda ws: lib.tp_sample3_grid_nchw_f32(C.byref(planes), 32, 256, C.byref(dims), 1, C.byref(sg), 0, 256, 256, ws, None),
+        lambda ws: lib.tp_sample3_lattice_nchw_f32(C.byref(planes), 32, C.byref(dims), C.byref(org), C.byref(stp), 1, C.byref(sg), 0,
+                                                   256, 256, ws, None),
+        lambda ws: lib.tp_sample3_seg_nchw_f32(C.byref(planes), 32, 256, 10, 256, None, 1, 1, C.byref(sg), 0, 256, 256, ws, None),
+        lambda ws: lib.tp_sample3_grid_head_nchw_tf32(C.byref(planes), 256, C.byref(dims), 1, C.byref(sg), 0, 256, 256, 256, 5, 256,
+                                                      256, ws, None),
+    ):
+        assert call(need - 1) == -4 and b"workspace" in lib.tp_last_error()
+    # empty problems return before touching anything
+    assert lib.tp_sample3_seg_nchw_f32(C.byref(planes), 32, None, 0, None, None, 1, 1, C.byref(sg), 0, None, None, 0, None) == 0
+    zero = (C.c_int32 * 3)(0, 4, 16)
+    assert lib.tp_sample3_grid_head_nchw_tf32(C.byref(planes), None, C.byref(zero), 1, C.byref(sg), 0, None, None, None, 5, None,
+                                              None, 0, None) == 0
+    # lattice form: null origin
+    assert lib.tp_sample3_lattice_nchw_f32(C.byref(planes), 32, C.byref(dims), None, C.byref(stp), 1, C.byref(sg), 0, 256, 256,
+                                           need, None) == -1

@@ -70,20 +70,8 @@ for name, (lat, C) in cases.items():
 
     a, m, mn = timeit(flat)
     print(f"{name:12s} B={B} Q={Q} flat      avg {a:7.1f} us med {m:7.1f} min {mn:7.1f}  {byts / a / 1e3:7.0f} GB/s", flush=True)
-    for tile in ("0", "1", ""):
-        if tile:
-            os.environ["TP_GRID_TILE"] = tile
-        else:
-            os.environ.pop("TP_GRID_TILE", None)
-        a, m, mn = timeit(grid)
-        print(f"{name:12s} B={B} Q={Q} grid[{tile or 'auto'}] avg {a:7.1f} us med {m:7.1f} min {mn:7.1f}  {byts / a / 1e3:7.0f} GB/s", flush=True)
-    os.environ.pop("TP_GRID_TILE", None)
-    for flags in ("0", "1", "2", "3"):
-        os.environ["TP_GRID_FLAGS"] = flags
-        a, m, mn = timeit(grid)
-        print(f"{name:12s} flags={flags} avg {a:7.1f} us med {m:7.1f} min {mn:7.1f}  {byts / a / 1e3:7.0f} GB/s", flush=True)
-    os.environ.pop("TP_GRID_FLAGS", None)
-    os.environ.pop("TP_GRID_TILE", None)
+    a, m, mn = timeit(grid)
+    print(f"{name:12s} B={B} Q={Q} lattice   avg {a:7.1f} us med {m:7.1f} min {mn:7.1f}  {byts / a / 1e3:7.0f} GB/s", flush=True)
     ref = torch.empty_like(outs[0])
     ops.sample3(nhwc[0], q[0], LO, VS, HALF, channels_last=True, out=ref)
     ops.sample3(nhwc[0], q[0], LO, VS, HALF, channels_last=True, out=outs[0], grid_dims=dims)

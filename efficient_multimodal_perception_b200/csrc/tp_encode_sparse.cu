@@ -104,22 +104,37 @@ __device__ __forceinline__ int sp_plane_of(const SparseParams& P, int64_t c) {
 // One thread per cell, cells in memory order (coalesced counter reads). An occupied cell takes a slot in its group's
 // list; the slots of shared cells (several points: they will be max-ed with atomics) are zeroed by the WHOLE warp, 32
 // lanes x 16 B per row — one thread zeroing 512 B with 32 dependent stores was what made this pass take 97 us.
+// Slots are claimed per CTA: the ~60 k occupied cells of a sample share only Zp + Xp + Yp (70) group counters, so one
+// global atomic per cell is ~7 k same-address atomics per counter (79 us for a 27 MB scan at bs = 8); here a cell takes
+// its rank from a shared-memory counter and one thread per group reserves the CTA's range.
+constexpr int kSpMaxGroups = 256;  // = the size of the gcount region
+
 __global__ void __launch_bounds__(256)
 sparse_list_kernel(const SparseParams P) {
-  const int lane = threadIdx.x & 31;
-  for (int64_t c0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll; c0 < P.cells_total; c0 += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t c = c0 + lane;
+  __shared__ int s_cnt[kSpMaxGroups], s_base[kSpMaxGroups];
+  const int lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int ngroups = P.ngroups;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < P.cells_total; base += (int64_t)gridDim.x * blockDim.x) {
+    s_cnt[tid] = 0;
+    __syncthreads();
+    const int64_t c = base + tid;
     const int n = c < P.cells_total ? P.cnt[c] : 0;
+    int p = 0, g = 0, r = 0;
     if (n > 0) {
-      const int p = sp_plane_of(P, c);
-      const int g = (int)((c - P.cell0[p]) % P.G[p]);
-      const int s = atomicAdd(P.gcount + P.goff[p] + g, 1);
-      P.lists[P.cell0[p] + (int64_t)g * P.rows[p] * P.batch + s] = (int)(c - P.cell0[p]);
+      p = sp_plane_of(P, c);
+      g = (int)((c - P.cell0[p]) % P.G[p]);
+      r = atomicAdd(&s_cnt[P.goff[p] + g], 1);
     }
+    __syncthreads();
+    if (tid < ngroups && s_cnt[tid] > 0) s_base[tid] = atomicAdd(P.gcount + tid, s_cnt[tid]);
+    __syncthreads();
+    if (n > 0)
+      P.lists[P.cell0[p] + (int64_t)g * P.rows[p] * P.batch + s_base[P.goff[p] + g] + r] = (int)(c - P.cell0[p]);
     for (unsigned m = __ballot_sync(0xffffffffu, n > 1); m; m &= m - 1) {  // shared cells: max starts from key 0
-      uint4* row = reinterpret_cast<uint4*>(P.slots + (c0 + __ffs(m) - 1) * P.C);
+      uint4* row = reinterpret_cast<uint4*>(P.slots + (base + (tid & ~31) + __ffs(m) - 1) * P.C);
       for (int k = lane; k < P.C4; k += 32) row[k] = make_uint4(0u, 0u, 0u, 0u);
     }
+    // s_base is rewritten only after the next iteration's first two barriers; s_cnt after its first: no barrier here
   }
 }
 

@@ -598,8 +598,8 @@ def decode_config(args, Q, world, nsets=None):
                         f"x C={C_DEC} from 3 fp32 {PLANE}x{PLANE} triplanes, bs=1 per GPU",
             "queries": args.queries, "Q": Q, "C": C_DEC, "planes": [PLANE, PLANE],
             "query_tensor": (f"[1,{','.join(map(str, QUERY_DIMS[args.queries]))},3] through the 5-D entry point "
-                             "tp_sample3_grid_nhwc_f32 (per-block lattice detection on the device)"
-                             if QUERY_DIMS[args.queries] else "[1,Q,3] point list through tp_sample3_nhwc_f32"),
+                             "tp_sample3_grid_nchw_f32 (per-block lattice detection on the device)"
+                             if QUERY_DIMS[args.queries] else "[1,Q,3] point list through tp_sample3_nchw_f32"),
             "step": "NCHW->NHWC conversion of the 3 planes (1 launch) + fused gather kernel (1 launch), CUDA-graph replay",
             "l2": "rotating buffer sets, total footprint > 3x L2 (no flush kernel)",
             "parallelism": f"queries sharded over {world} GPU(s), no collective"}

@@ -122,6 +122,15 @@ def test_ops_refuse_cpu_tensors():
         ops.sample3(torch.zeros(1, 3, 4, 8, 8), torch.zeros(1, 5, 3), [0] * 3, [1] * 3, [4] * 3)
     with pytest.raises(TriplaneError, match="CUDA tensor"):
         ops.voxel_index(torch.zeros(5, 3), [0] * 6, [1] * 3)
+    # the round-2 decode entry points: no silent CPU path either
+    tri, lo, vs, half = torch.zeros(1, 3, 32, 8, 8), [0] * 3, [1] * 3, [4] * 3
+    with pytest.raises(TriplaneError, match="CUDA tensor"):
+        ops.sample3_lattice(tri, (4, 4, 16), [0] * 3, [1] * 3, lo, vs, half)
+    with pytest.raises(TriplaneError, match="CUDA tensor"):
+        ops.sample3_segments(tri, torch.zeros(5, 3), torch.tensor([0, 5]), None, lo, vs, half)
+    with pytest.raises(TriplaneError, match="CUDA tensor"):
+        ops.sample3_head(tri, torch.zeros(1, 256, 3), lo, vs, half, torch.zeros(64, 32), torch.zeros(32, 64),
+                         torch.zeros(5, 32), grid_dims=(4, 4, 16))
 
 
 def test_missing_library_fails_loudly(monkeypatch):

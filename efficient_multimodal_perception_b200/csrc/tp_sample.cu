@@ -90,6 +90,7 @@ struct Planes3 {
   int64_t src_bstride[3];
   int HW[3];
   int tiles_x[3];  // ceil(HW/32) per plane; blockIdx.x runs over the three planes back to back
+  int vec;         // 16-byte stores possible
 };
 
 // all three planes in one launch. grid = (sum_p ceil(HW_p/32), ceil(C/32), B)
@@ -115,6 +116,13 @@ nchw_to_nhwc3_kernel(const Planes3 P, int C) {
     if (c < C && p < HW) tile[ty + j][tx] = __ldg(s + (int64_t)c * HW + p);
   }
   __syncthreads();
+  if (P.vec) {  // C % 4 == 0, 16-byte aligned destination: one 16-byte store per thread (pixel tid >> 3, channels 4 (tid & 7) ..)
+    const int pl = threadIdx.x >> 3, l8 = threadIdx.x & 7, p = p0 + pl, c = c0 + 4 * l8;
+    if (c < C && p < HW)
+      *reinterpret_cast<float4*>(d + (int64_t)p * C + c) =
+          make_float4(tile[4 * l8][pl], tile[4 * l8 + 1][pl], tile[4 * l8 + 2][pl], tile[4 * l8 + 3][pl]);
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
     int p = p0 + ty + j, c = c0 + tx;
@@ -142,6 +150,8 @@ extern "C" int tp_planes3_nchw_to_nhwc_f32(const tp_plane planes_nchw[3], float*
     P.tiles_x[k] = (P.HW[k] + 31) / 32;
     tx += P.tiles_x[k];
   }
+  P.vec = (C & 3) == 0;
+  for (int k = 0; k < 3; ++k) P.vec = P.vec && ((uintptr_t)dst[k] & 15) == 0;
   dim3 grid(tx, (C + 31) / 32, batch);
   nchw_to_nhwc3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P, C);
   TP_LAUNCH_CHECK("nchw_to_nhwc3_kernel");

@@ -64,7 +64,7 @@ sample3_kernel(const SampleParams P, const int sched_slot) {
 // NCHW -> NHWC through a padded 32x32 shared tile. grid = (ceil(HW/32), ceil(C/32), B)
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_kernel(const float* __restrict__ src, int64_t src_bstride, float* __restrict__ dst,
-                    int C, int HW) {
+                    int C, int HW, int vec) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -77,6 +77,13 @@ nchw_to_nhwc_kernel(const float* __restrict__ src, int64_t src_bstride, float* _
     if (c < C && p < HW) tile[ty + j][tx] = __ldg(s + (int64_t)c * HW + p);
   }
   __syncthreads();
+  if (vec) {  // C % 4 == 0, 16-byte aligned destination: one 16-byte store per thread
+    const int pl = threadIdx.x >> 3, l8 = threadIdx.x & 7, p = p0 + pl, c = c0 + 4 * l8;
+    if (c < C && p < HW)
+      *reinterpret_cast<float4*>(d + (int64_t)p * C + c) =
+          make_float4(tile[4 * l8][pl], tile[4 * l8 + 1][pl], tile[4 * l8 + 2][pl], tile[4 * l8 + 3][pl]);
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
     int p = p0 + ty + j, c = c0 + tx;
@@ -166,7 +173,8 @@ extern "C" int tp_planes_nchw_to_nhwc_f32(const float* src, int64_t src_batch_st
     return fail(TP_E_SHAPE, "tp_planes_nchw_to_nhwc_f32: bad shape B=%d C=%d H=%d W=%d", batch, C, H, W);
   const int HW = H * W;
   dim3 grid((HW + 31) / 32, (C + 31) / 32, batch);
-  nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_batch_stride, dst, C, HW);
+  const int vec = ((C & 3) == 0 && ((uintptr_t)dst & 15) == 0) ? 1 : 0;
+  nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_batch_stride, dst, C, HW, vec);
   TP_LAUNCH_CHECK("nchw_to_nhwc_kernel");
   return 0;
 }
